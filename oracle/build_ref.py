@@ -1,0 +1,159 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE ONLY — builds the real reference into oracle/_ref/.
+
+Compiles the reference's own C++ sources *from where they lie* under /root/reference/src
+(no reference source is copied into this repository; patched temporaries live in a
+scratch directory under $TMPDIR and only binaries are written to oracle/_ref/).
+
+The reference cannot be built as shipped here: GLM is an external, un-vendored,
+unpinned dependency (cmake/FindGLM.cmake) and is not installed.  We compile against
+oracle/glm_shim (our restatement of GLM 0.9.9 scalar semantics for the ~20 functions
+the reference uses).  The reference's CMake build is NOT run.
+
+Outputs (per variant v in ours1931, ours2006, meng, jh):
+  oracle/_ref/simple_spectral_<v>          pristine sources, -O3 -march=x86-64-v3 -DNDEBUG
+                                            (CPU timing arm; multi-threaded, nondeterministic)
+  oracle/_ref/simple_spectral_<v>_hooked   sources + oracle/ref_hooks.hpp spliced into
+                                            renderer.cpp, -O2 -DNDEBUG -ffp-contract=off
+                                            (parity oracle; per-sample seeding + dumps,
+                                             inert unless SSB_* env vars are set)
+Variants are the reference's compile-time macros (stdafx.hpp:66,81), selected by
+editing the scratch copy of stdafx.hpp exactly as the reference's author intends.
+"""
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("SSB_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+SHIM = os.path.join(HERE, "glm_shim")
+
+VARIANTS = {
+    "ours1931": dict(alg=1, observer=1931),
+    "ours2006": dict(alg=1, observer=2006),
+    "meng": dict(alg=2, observer=1931),
+    "jh": dict(alg=3, observer=1931),
+}
+CXX_SOURCES = [
+    "main.cpp", "renderer.cpp", "scene.cpp", "geometry.cpp", "material.cpp", "spectrum.cpp",
+    "framebuffer.cpp", "util/color.cpp", "util/random.cpp", "util/spherical-tri.cpp",
+]
+C_SOURCES = ["jakob-and-hanika-2019/rgb2spec.c"]
+LODEPNG = "util/lodepng/lodepng.cpp"
+
+FLAGS_PRISTINE = ["-O3", "-march=x86-64-v3", "-DNDEBUG"]
+FLAGS_HOOKED = ["-O2", "-DNDEBUG", "-ffp-contract=off"]
+
+
+def run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise SystemExit("oracle/build_ref.py: command failed")
+    return r
+
+
+def sub_once(text, pattern, repl, what):
+    new, n = re.subn(pattern, repl, text, count=1, flags=re.M)
+    if n != 1:
+        raise SystemExit(f"oracle/build_ref.py: patch point not found: {what}")
+    return new
+
+
+def patch_variant(src_dir, alg, observer):
+    p = os.path.join(src_dir, "stdafx.hpp")
+    t = open(p, encoding="utf-8-sig").read()
+    t = sub_once(t, r"#define RENDER_MODE_SPECTRAL_ALGNUM 1", f"#define RENDER_MODE_SPECTRAL_ALGNUM {alg}", "ALGNUM")
+    if observer == 2006:
+        t = sub_once(t, r"#if 1(\s+#define CIE_OBSERVER 1931)", r"#if 0\1", "CIE_OBSERVER")
+    open(p, "w", encoding="utf-8").write(t)
+
+
+def patch_hooks(src_dir):
+    shutil.copy(os.path.join(HERE, "ref_hooks.hpp"), os.path.join(src_dir, "ssb_ref_hooks.hpp"))
+    # the hooks read a few private members
+    for name in ("spectrum.hpp", "material.hpp"):
+        p = os.path.join(src_dir, name)
+        t = open(p, encoding="utf-8-sig").read().replace("private:", "public:")
+        open(p, "w", encoding="utf-8").write(t)
+    p = os.path.join(src_dir, "renderer.cpp")
+    t = open(p, encoding="utf-8-sig").read()
+    t = sub_once(t, r'(#include "scene.hpp"\n)', r'\1#include "ssb_ref_hooks.hpp"\n', "include")
+    # thread count override (renderer.cpp:45)
+    t = sub_once(t, r"_threads\.resize\(std::thread::hardware_concurrency\(\)\);",
+                 "_threads.resize(ssb_hooks::threads(std::thread::hardware_concurrency()));\n"
+                 "\tssb_hooks::dump_tables(scene);", "threads")
+    # per-sample seeding + sample dump (renderer.cpp:293-295, spectral branch)
+    t = sub_once(t, r"avg \+= _render_sample\(rng, i,j\) \* 0\.001f;",
+                 "{ ssb_hooks::seed_sample(rng,i,j,k); auto ssb_s = _render_sample(rng, i,j); "
+                 "ssb_hooks::record_sample(i,j,k,ssb_s); avg += ssb_s * 0.001f; }", "sample")
+    # pixel dump (after renderer.cpp:296)
+    t = sub_once(t, r"(avg \*= 1000\.0 / static_cast<double>\(options\.spp\);\n)",
+                 r"\1\t\tssb_hooks::record_pixel(i,j,avg);\n", "pixel")
+    # begin / finish
+    t = sub_once(t, r"(\t_num_tiles_start = _tiles\.size\(\);)",
+                 r"\tssb_hooks::begin(options.res[0],options.res[1],options.spp);\n\1", "begin")
+    t = sub_once(t, r"(\t\tframebuffer\.save\(options\.output_path\);)", r"\t\tssb_hooks::finish();\n\1", "finish")
+    open(p, "w", encoding="utf-8").write(t)
+
+
+def build_one(tmp, name, alg, observer, hooked, lodepng_obj):
+    tag = name + ("_hooked" if hooked else "")
+    src_dir = os.path.join(tmp, tag, "src")
+    shutil.copytree(os.path.join(REF, "src"), src_dir, ignore=shutil.ignore_patterns("lodepng*"))
+    for root, _, files in os.walk(src_dir):
+        os.chmod(root, 0o755)
+        for f in files:
+            os.chmod(os.path.join(root, f), 0o644)
+    patch_variant(src_dir, alg, observer)
+    if hooked:
+        patch_hooks(src_dir)
+    flags = FLAGS_HOOKED if hooked else FLAGS_PRISTINE
+    inc = ["-I", SHIM, "-I", os.path.join(REF, "src")]  # lodepng.h is found through the original tree
+    objs = []
+    for s in CXX_SOURCES:
+        o = os.path.join(tmp, tag, s.replace("/", "_") + ".o")
+        # util/*.cpp include "lodepng/lodepng.h" relative to util/, which is not copied: add that dir
+        run(["g++", "-std=c++17", "-w", *flags, *inc, "-I", os.path.join(REF, "src", "util"),
+             "-c", os.path.join(src_dir, s), "-o", o])
+        objs.append(o)
+    for s in C_SOURCES:
+        o = os.path.join(tmp, tag, s.replace("/", "_") + ".o")
+        run(["gcc", "-w", *flags, "-c", os.path.join(src_dir, s), "-o", o])
+        objs.append(o)
+    out = os.path.join(OUT, "simple_spectral_" + tag)
+    run(["g++", *objs, lodepng_obj, "-o", out, "-pthread", "-lm"])
+    return out
+
+
+def main():
+    if not os.path.isdir(os.path.join(REF, "src")):
+        print("oracle/build_ref.py: reference not present at", REF, "- keeping prebuilt oracle/_ref/")
+        return 0
+    which = sys.argv[1:] or list(VARIANTS)
+    os.makedirs(OUT, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="ssb_ref_build_")
+    try:
+        lodepng_obj = os.path.join(tmp, "lodepng.o")
+        # lodepng (vendored by the reference) is compiled straight from /root/reference
+        run(["g++", "-std=c++17", "-w", "-O2", "-DNDEBUG", "-c", os.path.join(REF, "src", LODEPNG), "-o", lodepng_obj])
+        jobs = []
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            for name in which:
+                v = VARIANTS[name]
+                for hooked in (False, True):
+                    jobs.append(ex.submit(build_one, tmp, name, v["alg"], v["observer"], hooked, lodepng_obj))
+            for j in jobs:
+                print("built", os.path.relpath(j.result(), os.path.dirname(HERE)))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
