@@ -1,0 +1,577 @@
+// ssb_capi.cu — C ABI (include/ssb200.h) of the B200 spectral path-tracing integrator.
+// Host side: deep-copies the caller's flat scene / colour tables, packs them into the device
+// "blob" the trace kernel stages into shared memory, owns the device buffers and the stream, and
+// launches the kernels of ssb_kernels.cuh.  There is NO CPU fallback: every entry point that
+// computes fails with SSB_ERR_DATA when CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ssb200.h"
+#include "ssb_kernels.cuh"
+
+using namespace ssbk;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_last_error = buf;
+	return code;
+}
+
+#define SSB_CUDA(expr)                                                                                  \
+	do {                                                                                                \
+		cudaError_t err__ = (expr);                                                                     \
+		if (err__ != cudaSuccess)                                                                       \
+			return fail(SSB_ERR_DATA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(err__), __FILE__, __LINE__, #expr); \
+	} while (0)
+
+struct HostSpectrum {
+	std::vector<float> data;
+	float low = 0, high = 0;
+	uint32_t filter = 0;
+	bool present = false;
+};
+struct HostMaterial {
+	uint32_t kind = 0, albedo_mode = 0, texture = 0;
+	HostSpectrum albedo, emission;
+};
+
+int copy_spectrum(const ssb_spectrum& s, HostSpectrum& out, const char* what, bool required) {
+	out = HostSpectrum();
+	if (!s.data || s.n == 0) {
+		if (required) return fail(SSB_ERR_ARG, "%s: missing spectrum", what);
+		return SSB_OK;
+	}
+	if (s.n < 2) return fail(SSB_ERR_DATA, "%s: must have at-least two elements in sampled spectrum", what);  // spectrum.cpp:17-20
+	if (!(s.high > s.low)) return fail(SSB_ERR_ARG, "%s: high must exceed low", what);
+	if (s.filter > SSB_FILTER_NEAREST) return fail(SSB_ERR_ARG, "%s: unknown filter", what);
+	out.data.assign(s.data, s.data + s.n);
+	out.low = s.low; out.high = s.high; out.filter = s.filter; out.present = true;
+	return SSB_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct ssb_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+	int sm_count = 0;
+
+	// host copies of the uploaded tables
+	bool have_scene = false, have_color = false, blob_dirty = true;
+	ssb_camera camera{};
+	std::vector<ssb_quad> quads;
+	std::vector<HostMaterial> materials;
+	std::vector<uint32_t> lights;
+	HostSpectrum xbar, ybar, zbar, basis_r, basis_g, basis_b;
+	float xyz_to_lrgb[9] = { 0 };
+	float d65_rad_Y = 1.0f;
+	uint32_t jh_res = 0;
+	ssb_meng_tables meng{};
+	bool have_meng = false;
+
+	// device
+	std::vector<uchar4*> d_textures;
+	std::vector<uint32_t> tex_w, tex_h;
+	unsigned char* d_blob = nullptr;
+	size_t blob_bytes = 0, blob_capacity = 0;
+	float* d_jh_scale = nullptr;
+	float* d_jh_data = nullptr;
+	int32_t* d_meng_grid = nullptr;
+	float* d_meng_points = nullptr;
+	double* d_accum = nullptr;
+	uint32_t accum_w = 0, accum_h = 0;
+	float4* d_samples = nullptr;
+	size_t samples_capacity = 0;  // in float4
+	unsigned long long* d_counter = nullptr;
+	double* d_xyza = nullptr;
+	float4* d_srgba = nullptr;
+	size_t resolve_capacity = 0;  // pixels
+
+	ssb_stats stats{};
+};
+
+namespace {
+
+void free_textures(ssb_ctx* c) {
+	for (uchar4* p : c->d_textures) cudaFree(p);
+	c->d_textures.clear(); c->tex_w.clear(); c->tex_h.clear();
+}
+
+DevSpectrum pack_spectrum(const HostSpectrum& s, std::vector<float>& pool) {
+	DevSpectrum d{};
+	if (!s.present) { d.offset = 0; d.n_filter = 0; d.low = 0; d.recip = 0; return d; }
+	d.offset = (uint32_t)pool.size();
+	pool.insert(pool.end(), s.data.begin(), s.data.end());
+	uint32_t n = (uint32_t)s.data.size();
+	d.n_filter = n | (s.filter == SSB_FILTER_NEAREST ? 0x80000000u : 0u);
+	d.low = s.low;
+	float numer = s.high - s.low;        // spectrum.cpp:22-25
+	float denom = (float)(n - 1);
+	d.recip = denom / numer;
+	return d;
+}
+
+// Build the shared-memory image: [DevHeader][quads][materials][lights][textures][float pool]
+int build_blob(ssb_ctx* c) {
+	if (!c->have_scene) return fail(SSB_ERR_ARG, "ssb_render: no scene uploaded");
+	if (!c->have_color) return fail(SSB_ERR_ARG, "ssb_render: no colour tables uploaded");
+	std::vector<float> pool;
+	DevHeader hdr{};
+	hdr.nquads = (uint32_t)c->quads.size();
+	hdr.nmaterials = (uint32_t)c->materials.size();
+	hdr.nlights = (uint32_t)c->lights.size();
+	hdr.ntextures = (uint32_t)c->d_textures.size();
+	hdr.xbar = pack_spectrum(c->xbar, pool);
+	hdr.ybar = pack_spectrum(c->ybar, pool);
+	hdr.zbar = pack_spectrum(c->zbar, pool);
+	hdr.basis_r = pack_spectrum(c->basis_r, pool);
+	hdr.basis_g = pack_spectrum(c->basis_g, pool);
+	hdr.basis_b = pack_spectrum(c->basis_b, pool);
+	for (int v = 0; v < 256; ++v) {  // Color::srgb_to_lrgb (color.hpp:91-97) of texel/255 (material.cpp:51-55)
+		float srgb = (float)v * (1.0f / 255.0f);
+		hdr.srgb_lut[v] = srgb < 0.04045f ? srgb / 12.92f : powf((srgb + 0.055f) / 1.055f, 2.4f);
+	}
+	std::vector<DevMaterial> mats(c->materials.size());
+	for (size_t m = 0; m < mats.size(); ++m) {
+		const HostMaterial& hm = c->materials[m];
+		mats[m].kind = hm.kind; mats[m].albedo_mode = hm.albedo_mode; mats[m].texture = hm.texture; mats[m].pad = 0;
+		mats[m].albedo = pack_spectrum(hm.albedo, pool);
+		mats[m].emission = pack_spectrum(hm.emission, pool);
+	}
+	std::vector<DevTexture> texs(c->d_textures.size());
+	for (size_t t = 0; t < texs.size(); ++t) { texs[t].rgba = c->d_textures[t]; texs[t].width = c->tex_w[t]; texs[t].height = c->tex_h[t]; }
+
+	size_t off = align_up(sizeof(DevHeader), 16);
+	hdr.off_quads = (uint32_t)off; off = align_up(off + c->quads.size() * sizeof(ssb_quad), 16);
+	hdr.off_materials = (uint32_t)off; off = align_up(off + mats.size() * sizeof(DevMaterial), 16);
+	hdr.off_lights = (uint32_t)off; off = align_up(off + c->lights.size() * sizeof(uint32_t), 16);
+	hdr.off_textures = (uint32_t)off; off = align_up(off + texs.size() * sizeof(DevTexture), 16);
+	hdr.off_pool = (uint32_t)off; off = align_up(off + pool.size() * sizeof(float), 16);
+	hdr.total_bytes = (uint32_t)off;
+	if (off > 160 * 1024) return fail(SSB_ERR_UNSUPPORTED, "scene tables (%zu bytes) exceed the shared-memory budget", off);
+
+	std::vector<unsigned char> blob(off, 0);
+	memcpy(blob.data(), &hdr, sizeof(hdr));
+	if (!c->quads.empty()) memcpy(blob.data() + hdr.off_quads, c->quads.data(), c->quads.size() * sizeof(ssb_quad));
+	if (!mats.empty()) memcpy(blob.data() + hdr.off_materials, mats.data(), mats.size() * sizeof(DevMaterial));
+	if (!c->lights.empty()) memcpy(blob.data() + hdr.off_lights, c->lights.data(), c->lights.size() * sizeof(uint32_t));
+	if (!texs.empty()) memcpy(blob.data() + hdr.off_textures, texs.data(), texs.size() * sizeof(DevTexture));
+	if (!pool.empty()) memcpy(blob.data() + hdr.off_pool, pool.data(), pool.size() * sizeof(float));
+
+	if (off > c->blob_capacity) {
+		if (c->d_blob) cudaFree(c->d_blob);
+		c->d_blob = nullptr; c->blob_capacity = 0;
+		SSB_CUDA(cudaMalloc(&c->d_blob, off));
+		c->blob_capacity = off;
+	}
+	SSB_CUDA(cudaMemcpyAsync(c->d_blob, blob.data(), off, cudaMemcpyHostToDevice, c->stream));
+	SSB_CUDA(cudaStreamSynchronize(c->stream));  // `blob` is a pageable temporary
+	c->blob_bytes = off;
+	c->blob_dirty = false;
+	return SSB_OK;
+}
+
+int ensure_accum(ssb_ctx* c, uint32_t w, uint32_t h) {
+	if (c->d_accum && c->accum_w == w && c->accum_h == h) return SSB_OK;
+	if (c->d_accum) cudaFree(c->d_accum);
+	c->d_accum = nullptr;
+	SSB_CUDA(cudaMalloc(&c->d_accum, (size_t)w * h * 4 * sizeof(double)));
+	SSB_CUDA(cudaMemsetAsync(c->d_accum, 0, (size_t)w * h * 4 * sizeof(double), c->stream));
+	c->accum_w = w; c->accum_h = h;
+	return SSB_OK;
+}
+
+int validate_options(const ssb_options* o, uint32_t& x1, uint32_t& y1, uint32_t& s1) {
+	if (!o) return fail(SSB_ERR_ARG, "options is NULL");
+	if (o->width == 0 || o->height == 0 || o->spp == 0) return fail(SSB_ERR_ARG, "width, height and spp must be positive");
+	x1 = o->x1 ? o->x1 : o->width; y1 = o->y1 ? o->y1 : o->height; s1 = o->sample_end ? o->sample_end : o->spp;
+	if (x1 > o->width || y1 > o->height || o->x0 > x1 || o->y0 > y1 || o->sample_begin > s1)
+		return fail(SSB_ERR_ARG, "work subset out of range");
+	if (o->upsampling < SSB_UPSAMPLE_OURS || o->upsampling > SSB_UPSAMPLE_JH) return fail(SSB_ERR_UNSUPPORTED, "unknown upsampling mode %u", o->upsampling);
+	if (o->max_depth == 0 || o->max_depth > SSB_MAX_DEPTH) return fail(SSB_ERR_UNSUPPORTED, "max_depth must be in [1,%u]", SSB_MAX_DEPTH);
+	if (!(o->lambda_max > o->lambda_min)) return fail(SSB_ERR_ARG, "lambda_max must exceed lambda_min");
+	return SSB_OK;
+}
+
+const size_t kSampleBudget = (size_t)64 << 20;  // float4 slots per pass (1 GiB)
+
+}  // namespace
+
+extern "C" {
+
+uint32_t ssb_abi_version(void) { return SSB_ABI_VERSION; }
+const char* ssb_last_error(void) { return g_last_error.c_str(); }
+
+void ssb_default_options(ssb_options* opt, uint32_t width, uint32_t height, uint32_t spp) {
+	if (!opt) return;
+	memset(opt, 0, sizeof(*opt));
+	opt->width = width; opt->height = height; opt->spp = spp;
+	opt->upsampling = SSB_UPSAMPLE_OURS;       // RENDER_MODE_SPECTRAL_ALGNUM 1 (stdafx.hpp:66)
+	opt->lambda_min = 380.0f; opt->lambda_max = 780.0f;  // CIE 1931 (stdafx.hpp:115-117)
+	opt->max_depth = 10;                       // MAX_DEPTH (stdafx.hpp:47)
+	opt->explicit_light_sampling = 1;          // EXPLICIT_LIGHT_SAMPLING (stdafx.hpp:44)
+	opt->flat_field_correction = 1;            // FLAT_FIELD_CORRECTION (stdafx.hpp:55)
+	opt->eps = 0.001f;                         // EPS (stdafx.hpp:58)
+	opt->seed = 1;
+}
+
+int ssb_create(int device, ssb_ctx** out) {
+	if (!out) return fail(SSB_ERR_ARG, "ssb_create: out is NULL");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(SSB_ERR_DATA, "ssb_create: no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+	if (device < 0 || device >= count) return fail(SSB_ERR_ARG, "ssb_create: device %d out of range [0,%d)", device, count);
+	SSB_CUDA(cudaSetDevice(device));
+	ssb_ctx* c = new ssb_ctx();
+	c->device = device;
+	cudaDeviceProp prop{};
+	SSB_CUDA(cudaGetDeviceProperties(&prop, device));
+	c->sm_count = prop.multiProcessorCount;
+	if (prop.major < 10) {
+		delete c;
+		return fail(SSB_ERR_UNSUPPORTED, "ssb_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+	}
+	SSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	SSB_CUDA(cudaEventCreate(&c->ev_begin)); SSB_CUDA(cudaEventCreate(&c->ev_end));
+	SSB_CUDA(cudaEventCreate(&c->ev_t0)); SSB_CUDA(cudaEventCreate(&c->ev_t1));
+	SSB_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
+	*out = c;
+	return SSB_OK;
+}
+
+void ssb_destroy(ssb_ctx* c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	free_textures(c);
+	cudaFree(c->d_blob); cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points);
+	cudaFree(c->d_accum); cudaFree(c->d_samples); cudaFree(c->d_counter); cudaFree(c->d_xyza); cudaFree(c->d_srgba);
+	if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+	if (c->ev_end) cudaEventDestroy(c->ev_end);
+	if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+	if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int ssb_upload_scene(ssb_ctx* c, const ssb_scene* scene) {
+	if (!c || !scene) return fail(SSB_ERR_ARG, "ssb_upload_scene: NULL argument");
+	if (scene->nquads == 0 || !scene->quads) return fail(SSB_ERR_ARG, "ssb_upload_scene: empty primitive list");
+	if (scene->nquads > SSB_MAX_QUADS) return fail(SSB_ERR_UNSUPPORTED, "ssb_upload_scene: %u quads exceed SSB_MAX_QUADS=%u", scene->nquads, SSB_MAX_QUADS);
+	if (scene->nmaterials == 0 || !scene->materials || scene->nmaterials > SSB_MAX_MATERIALS)
+		return fail(SSB_ERR_ARG, "ssb_upload_scene: bad material list");
+	if (scene->ntextures && !scene->textures) return fail(SSB_ERR_ARG, "ssb_upload_scene: textures is NULL");
+	SSB_CUDA(cudaSetDevice(c->device));
+	std::vector<HostMaterial> mats(scene->nmaterials);
+	for (uint32_t m = 0; m < scene->nmaterials; ++m) {
+		const ssb_material& sm = scene->materials[m];
+		if (sm.kind > SSB_MATERIAL_MIRROR || sm.albedo_mode > SSB_ALBEDO_TEXTURE) return fail(SSB_ERR_ARG, "material %u: bad kind/mode", m);
+		mats[m].kind = sm.kind; mats[m].albedo_mode = sm.albedo_mode; mats[m].texture = sm.texture;
+		int rc;
+		if (sm.albedo_mode == SSB_ALBEDO_CONSTANT) { if ((rc = copy_spectrum(sm.albedo, mats[m].albedo, "material albedo", true)) != SSB_OK) return rc; }
+		else if (sm.texture >= scene->ntextures) return fail(SSB_ERR_ARG, "material %u: texture index out of range", m);
+		if ((rc = copy_spectrum(sm.emission, mats[m].emission, "material emission", true)) != SSB_OK) return rc;
+	}
+	std::vector<uint32_t> lights;
+	for (uint32_t q = 0; q < scene->nquads; ++q) {
+		if (scene->quads[q].material >= scene->nmaterials) return fail(SSB_ERR_ARG, "quad %u: material index out of range", q);
+		if (scene->quads[q].is_light) lights.push_back(q);  // Scene::_init (scene.cpp:26-29)
+	}
+	if (lights.size() > SSB_MAX_LIGHTS) return fail(SSB_ERR_UNSUPPORTED, "more than %u lights", SSB_MAX_LIGHTS);
+	// textures: RGB8 -> RGBA8 on the device
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	free_textures(c);
+	for (uint32_t t = 0; t < scene->ntextures; ++t) {
+		const ssb_texture& tx = scene->textures[t];
+		if (!tx.rgb8 || tx.width == 0 || tx.height == 0) return fail(SSB_ERR_DATA, "texture %u: could not load texture", t);  // material.cpp:15-18
+		size_t n = (size_t)tx.width * tx.height;
+		std::vector<uchar4> rgba(n);
+		for (size_t i = 0; i < n; ++i) rgba[i] = make_uchar4(tx.rgb8[3 * i], tx.rgb8[3 * i + 1], tx.rgb8[3 * i + 2], 255);
+		uchar4* d = nullptr;
+		SSB_CUDA(cudaMalloc(&d, n * sizeof(uchar4)));
+		c->d_textures.push_back(d); c->tex_w.push_back(tx.width); c->tex_h.push_back(tx.height);
+		SSB_CUDA(cudaMemcpy(d, rgba.data(), n * sizeof(uchar4), cudaMemcpyHostToDevice));
+	}
+	c->camera = scene->camera;
+	c->quads.assign(scene->quads, scene->quads + scene->nquads);
+	c->materials.swap(mats);
+	c->lights.swap(lights);
+	c->have_scene = true; c->blob_dirty = true;
+	return SSB_OK;
+}
+
+int ssb_upload_color(ssb_ctx* c, const ssb_color* color) {
+	if (!c || !color) return fail(SSB_ERR_ARG, "ssb_upload_color: NULL argument");
+	SSB_CUDA(cudaSetDevice(c->device));
+	int rc;
+	if ((rc = copy_spectrum(color->xbar, c->xbar, "xbar", true)) != SSB_OK) return rc;
+	if ((rc = copy_spectrum(color->ybar, c->ybar, "ybar", true)) != SSB_OK) return rc;
+	if ((rc = copy_spectrum(color->zbar, c->zbar, "zbar", true)) != SSB_OK) return rc;
+	if ((rc = copy_spectrum(color->basis_r, c->basis_r, "basis_r", false)) != SSB_OK) return rc;
+	if ((rc = copy_spectrum(color->basis_g, c->basis_g, "basis_g", false)) != SSB_OK) return rc;
+	if ((rc = copy_spectrum(color->basis_b, c->basis_b, "basis_b", false)) != SSB_OK) return rc;
+	memcpy(c->xyz_to_lrgb, color->xyz_to_lrgb, sizeof(c->xyz_to_lrgb));
+	c->d65_rad_Y = color->d65_rad_Y;
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); c->d_jh_scale = c->d_jh_data = nullptr; c->jh_res = 0;
+	if (color->jh_res) {
+		if (!color->jh_scale || !color->jh_data) return fail(SSB_ERR_ARG, "ssb_upload_color: JH tables missing");
+		size_t res = color->jh_res, nd = 3 * res * res * res * 3;
+		SSB_CUDA(cudaMalloc(&c->d_jh_scale, res * sizeof(float)));
+		SSB_CUDA(cudaMalloc(&c->d_jh_data, nd * sizeof(float)));
+		SSB_CUDA(cudaMemcpy(c->d_jh_scale, color->jh_scale, res * sizeof(float), cudaMemcpyHostToDevice));
+		SSB_CUDA(cudaMemcpy(c->d_jh_data, color->jh_data, nd * sizeof(float), cudaMemcpyHostToDevice));
+		c->jh_res = color->jh_res;
+	}
+	cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points); c->d_meng_grid = nullptr; c->d_meng_points = nullptr; c->have_meng = false;
+	if (color->meng) {
+		const ssb_meng_tables& m = *color->meng;
+		if (!m.grid || !m.points || m.grid_w == 0 || m.grid_h == 0 || m.npoints == 0 || m.nsamples < 2) return fail(SSB_ERR_ARG, "ssb_upload_color: bad Meng tables");
+		size_t ng = (size_t)m.grid_w * m.grid_h * 8, np = (size_t)m.npoints * (5 + m.nsamples);
+		SSB_CUDA(cudaMalloc(&c->d_meng_grid, ng * sizeof(int32_t)));
+		SSB_CUDA(cudaMalloc(&c->d_meng_points, np * sizeof(float)));
+		SSB_CUDA(cudaMemcpy(c->d_meng_grid, m.grid, ng * sizeof(int32_t), cudaMemcpyHostToDevice));
+		SSB_CUDA(cudaMemcpy(c->d_meng_points, m.points, np * sizeof(float), cudaMemcpyHostToDevice));
+		c->meng = m; c->meng.grid = nullptr; c->meng.points = nullptr;
+		c->have_meng = true;
+	}
+	c->have_color = true; c->blob_dirty = true;
+	return SSB_OK;
+}
+
+int ssb_clear(ssb_ctx* c) {
+	if (!c) return fail(SSB_ERR_ARG, "ssb_clear: NULL context");
+	SSB_CUDA(cudaSetDevice(c->device));
+	if (c->d_accum) SSB_CUDA(cudaMemsetAsync(c->d_accum, 0, (size_t)c->accum_w * c->accum_h * 4 * sizeof(double), c->stream));
+	return SSB_OK;
+}
+
+int ssb_render(ssb_ctx* c, const ssb_options* o) {
+	if (!c) return fail(SSB_ERR_ARG, "ssb_render: NULL context");
+	uint32_t x1, y1, s1;
+	int rc = validate_options(o, x1, y1, s1);
+	if (rc != SSB_OK) return rc;
+	SSB_CUDA(cudaSetDevice(c->device));
+	if (c->blob_dirty && (rc = build_blob(c)) != SSB_OK) return rc;
+	if (o->explicit_light_sampling && c->lights.empty()) return fail(SSB_ERR_ARG, "explicit light sampling needs at least one light (scene.cpp:30)");
+	if (o->upsampling == SSB_UPSAMPLE_OURS && !c->basis_r.present) {
+		for (const HostMaterial& m : c->materials)
+			if (m.albedo_mode == SSB_ALBEDO_TEXTURE) return fail(SSB_ERR_ARG, "OURS upsampling needs the basis spectra");
+	}
+	if (o->upsampling == SSB_UPSAMPLE_JH && !c->jh_res) return fail(SSB_ERR_ARG, "JH upsampling needs the coefficient tables");
+	if (o->upsampling == SSB_UPSAMPLE_MENG && !c->have_meng) return fail(SSB_ERR_ARG, "MENG upsampling needs the grid tables");
+	if ((rc = ensure_accum(c, o->width, o->height)) != SSB_OK) return rc;
+	if (o->sample_begin == 0) SSB_CUDA(cudaMemsetAsync(c->d_accum, 0, (size_t)o->width * o->height * 4 * sizeof(double), c->stream));
+
+	const uint32_t rect_w = x1 - o->x0, rect_h = y1 - o->y0;
+	const size_t npix_rect = (size_t)rect_w * rect_h;
+	const uint32_t nsamp_total = s1 - o->sample_begin;
+	c->stats = ssb_stats{};
+	if (npix_rect == 0 || nsamp_total == 0) return SSB_OK;
+	if (npix_rect > kSampleBudget) return fail(SSB_ERR_UNSUPPORTED, "pixel rectangle too large for one pass");
+	uint32_t chunk = (uint32_t)std::min<size_t>(nsamp_total, std::max<size_t>(1, kSampleBudget / npix_rect));
+	size_t need = npix_rect * chunk;
+	if (need > c->samples_capacity) {
+		if (c->d_samples) cudaFree(c->d_samples);
+		c->d_samples = nullptr; c->samples_capacity = 0;
+		SSB_CUDA(cudaMalloc(&c->d_samples, need * sizeof(float4)));
+		c->samples_capacity = need;
+	}
+
+	KParams P{};
+	P.blob = c->d_blob;
+	P.samples = c->d_samples;
+	P.work_counter = c->d_counter;
+	P.width = o->width; P.height = o->height; P.x0 = o->x0; P.y0 = o->y0; P.rect_w = rect_w; P.rect_h = rect_h;
+	P.indirect_only = o->indirect_only; P.upsampling = o->upsampling; P.max_depth = o->max_depth;
+	P.els = o->explicit_light_sampling; P.flat_field = o->flat_field_correction;
+	P.eps = o->eps; P.lambda_min = o->lambda_min;
+	P.lambda_step = (o->lambda_max - o->lambda_min) / (float)4;  // LAMBDA_STEP (stdafx.hpp:289)
+	P.seed = o->seed;
+	memcpy(P.pv_inv, c->camera.pv_inv, sizeof(P.pv_inv));
+	memcpy(P.cam_pos, c->camera.pos, sizeof(P.cam_pos));
+	memcpy(P.cam_dir, c->camera.dir, sizeof(P.cam_dir));
+	P.jh_scale = c->d_jh_scale; P.jh_data = c->d_jh_data; P.jh_res = c->jh_res;
+	P.meng_grid = c->d_meng_grid; P.meng_points = c->d_meng_points;
+	P.meng_grid_w = c->meng.grid_w; P.meng_grid_h = c->meng.grid_h; P.meng_npoints = c->meng.npoints; P.meng_nsamples = c->meng.nsamples;
+	memcpy(P.meng_xy_to_uv, c->meng.xy_to_uv, sizeof(P.meng_xy_to_uv));
+	P.meng_sample_min = c->meng.sample_min; P.meng_sample_max = c->meng.sample_max;
+
+	const size_t smem = c->blob_bytes;
+	SSB_CUDA(cudaFuncSetAttribute(ssb_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int blocks_per_sm = 0;
+	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ssb_trace_kernel, SSB_TRACE_THREADS, smem));
+	if (blocks_per_sm < 1) return fail(SSB_ERR_UNSUPPORTED, "trace kernel does not fit on an SM with %zu bytes of tables", smem);
+
+	SSB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	double trace_ms = 0.0;
+	uint32_t launches = 0;
+	for (uint32_t k0 = 0; k0 < nsamp_total; k0 += chunk) {
+		uint32_t ns = std::min(chunk, nsamp_total - k0);
+		P.sample_begin = o->sample_begin + k0;
+		P.nsamp = ns;
+		P.total_work = (unsigned long long)npix_rect * ns;
+		SSB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
+		// persistent grid: SMs x resident CTAs, never more CTAs than there is work for
+		unsigned long long want = (P.total_work + SSB_TRACE_THREADS - 1) / SSB_TRACE_THREADS;
+		unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * blocks_per_sm, want);
+		SSB_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+		ssb_trace_kernel<<<grid, SSB_TRACE_THREADS, smem, c->stream>>>(P);
+		SSB_CUDA(cudaGetLastError());
+		SSB_CUDA(cudaEventRecord(c->ev_t1, c->stream));
+		unsigned agrid = (unsigned)((npix_rect + 127) / 128);
+		ssb_accumulate_kernel<<<agrid, 128, 0, c->stream>>>(c->d_samples, c->d_accum, o->width, o->x0, o->y0, rect_w, rect_h, ns);
+		SSB_CUDA(cudaGetLastError());
+		launches += 2;
+		if (nsamp_total > chunk) {  // multi-pass: collect per-pass trace time (single pass is read after the end event)
+			SSB_CUDA(cudaEventSynchronize(c->ev_t1));
+			float ms = 0; SSB_CUDA(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1)); trace_ms += ms;
+		}
+	}
+	SSB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SSB_CUDA(cudaEventSynchronize(c->ev_end));
+	float ms = 0;
+	SSB_CUDA(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
+	if (nsamp_total <= chunk) { float t = 0; SSB_CUDA(cudaEventElapsedTime(&t, c->ev_t0, c->ev_t1)); trace_ms = t; }
+	c->stats.samples = (uint64_t)npix_rect * nsamp_total;
+	c->stats.device_ms = ms;
+	c->stats.trace_ms = trace_ms;
+	c->stats.launches = launches;
+	return SSB_OK;
+}
+
+int ssb_read_accum(ssb_ctx* c, double* dst) {
+	if (!c || !dst) return fail(SSB_ERR_ARG, "ssb_read_accum: NULL argument");
+	if (!c->d_accum) return fail(SSB_ERR_ARG, "ssb_read_accum: nothing rendered yet");
+	SSB_CUDA(cudaSetDevice(c->device));
+	SSB_CUDA(cudaMemcpyAsync(dst, c->d_accum, (size_t)c->accum_w * c->accum_h * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	return SSB_OK;
+}
+int ssb_write_accum(ssb_ctx* c, const double* src) {
+	if (!c || !src) return fail(SSB_ERR_ARG, "ssb_write_accum: NULL argument");
+	if (!c->d_accum) return fail(SSB_ERR_ARG, "ssb_write_accum: no accumulator yet");
+	SSB_CUDA(cudaSetDevice(c->device));
+	SSB_CUDA(cudaMemcpyAsync(c->d_accum, src, (size_t)c->accum_w * c->accum_h * 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	return SSB_OK;
+}
+int ssb_accum_device(ssb_ctx* c, double** dptr, size_t* count) {
+	if (!c || !dptr) return fail(SSB_ERR_ARG, "ssb_accum_device: NULL argument");
+	if (!c->d_accum) return fail(SSB_ERR_ARG, "ssb_accum_device: nothing rendered yet");
+	SSB_CUDA(cudaSetDevice(c->device));
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	*dptr = c->d_accum;
+	if (count) *count = (size_t)c->accum_w * c->accum_h * 4;
+	return SSB_OK;
+}
+
+int ssb_resolve(ssb_ctx* c, const ssb_options* o, double* xyza_host, float* srgba_host) {
+	if (!c || !o) return fail(SSB_ERR_ARG, "ssb_resolve: NULL argument");
+	if (!c->d_accum || c->accum_w != o->width || c->accum_h != o->height) return fail(SSB_ERR_ARG, "ssb_resolve: no accumulator for this resolution");
+	if (o->spp == 0) return fail(SSB_ERR_ARG, "ssb_resolve: spp must be positive");
+	SSB_CUDA(cudaSetDevice(c->device));
+	size_t npix = (size_t)o->width * o->height;
+	if (npix > c->resolve_capacity) {
+		cudaFree(c->d_xyza); cudaFree(c->d_srgba); c->d_xyza = nullptr; c->d_srgba = nullptr; c->resolve_capacity = 0;
+		SSB_CUDA(cudaMalloc(&c->d_xyza, npix * 4 * sizeof(double)));
+		SSB_CUDA(cudaMalloc(&c->d_srgba, npix * sizeof(float4)));
+		c->resolve_capacity = npix;
+	}
+	const float* m = c->xyz_to_lrgb;
+	double scale = 1000.0 / (double)o->spp;  // renderer.cpp:296
+	unsigned grid = (unsigned)((npix + 127) / 128);
+	ssb_resolve_kernel<<<grid, 128, 0, c->stream>>>(c->d_accum, xyza_host ? c->d_xyza : nullptr, srgba_host ? c->d_srgba : nullptr,
+	                                                (uint32_t)npix, scale, o->upsampling, c->d65_rad_Y,
+	                                                m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
+	SSB_CUDA(cudaGetLastError());
+	c->stats.launches += 1;
+	if (xyza_host) SSB_CUDA(cudaMemcpyAsync(xyza_host, c->d_xyza, npix * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if (srgba_host) SSB_CUDA(cudaMemcpyAsync(srgba_host, c->d_srgba, npix * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	return SSB_OK;
+}
+
+int ssb_render_frame(ssb_ctx* c, const ssb_options* o, double* xyza_host, float* srgba_host) {
+	if (!c || !o) return fail(SSB_ERR_ARG, "ssb_render_frame: NULL argument");
+	ssb_options full = *o;
+	full.sample_begin = 0; full.sample_end = 0;
+	int rc = ssb_render(c, &full);
+	if (rc != SSB_OK) return rc;
+	ssb_stats st = c->stats;
+	rc = ssb_resolve(c, &full, xyza_host, srgba_host);
+	st.launches += 1;
+	c->stats = st;
+	return rc;
+}
+
+int ssb_get_stats(ssb_ctx* c, ssb_stats* out) {
+	if (!c || !out) return fail(SSB_ERR_ARG, "ssb_get_stats: NULL argument");
+	*out = c->stats;
+	return SSB_OK;
+}
+int ssb_synchronize(ssb_ctx* c) {
+	if (!c) return fail(SSB_ERR_ARG, "ssb_synchronize: NULL context");
+	SSB_CUDA(cudaSetDevice(c->device));
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	return SSB_OK;
+}
+
+int ssb_debug_eval_math(ssb_ctx* c, uint32_t fn, const float* x_host, float arg, float* out_host, size_t n) {
+	if (!c || !x_host || !out_host) return fail(SSB_ERR_ARG, "ssb_debug_eval_math: NULL argument");
+	if (n == 0) return SSB_OK;
+	SSB_CUDA(cudaSetDevice(c->device));
+	float *dx = nullptr, *dout = nullptr;
+	SSB_CUDA(cudaMalloc(&dx, n * sizeof(float)));
+	SSB_CUDA(cudaMalloc(&dout, n * sizeof(float)));
+	SSB_CUDA(cudaMemcpy(dx, x_host, n * sizeof(float), cudaMemcpyHostToDevice));
+	ssb_eval_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(fn, dx, arg, dout, n);
+	cudaError_t e = cudaStreamSynchronize(c->stream);
+	if (e == cudaSuccess) e = cudaMemcpy(out_host, dout, n * sizeof(float), cudaMemcpyDeviceToHost);
+	cudaFree(dx); cudaFree(dout);
+	if (e != cudaSuccess) return fail(SSB_ERR_DATA, "ssb_debug_eval_math: %s", cudaGetErrorString(e));
+	return SSB_OK;
+}
+
+int ssb_debug_trace_samples(ssb_ctx* c, const ssb_options* o, uint32_t px, uint32_t py, float* out_host) {
+	if (!c || !o || !out_host) return fail(SSB_ERR_ARG, "ssb_debug_trace_samples: NULL argument");
+	ssb_options one = *o;
+	one.x0 = px; one.x1 = px + 1; one.y0 = py; one.y1 = py + 1;
+	// keep the accumulator untouched: render into the sample buffer only by using a scratch accumulator pass
+	uint32_t x1, y1, s1;
+	int rc = validate_options(&one, x1, y1, s1);
+	if (rc != SSB_OK) return rc;
+	std::vector<double> saved;
+	bool had = c->d_accum && c->accum_w == o->width && c->accum_h == o->height;
+	if (had) { saved.resize((size_t)o->width * o->height * 4); if ((rc = ssb_read_accum(c, saved.data())) != SSB_OK) return rc; }
+	uint32_t begin = one.sample_begin;
+	if (begin == 0) one.sample_begin = 0;
+	rc = ssb_render(c, &one);
+	if (rc != SSB_OK) return rc;
+	uint32_t ns = s1 - begin;
+	if ((size_t)ns > kSampleBudget) return fail(SSB_ERR_UNSUPPORTED, "too many samples");
+	SSB_CUDA(cudaMemcpy(out_host, c->d_samples, (size_t)ns * sizeof(float4), cudaMemcpyDeviceToHost));
+	if (had) rc = ssb_write_accum(c, saved.data());
+	return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,837 @@
+// ssb_kernels.cuh — sm_100a kernels of the spectral path-tracing hot path.
+//
+// Replaces Renderer::_render_pixel / _render_sample and everything they reach
+// (reference src/renderer.cpp:103-308).  fp32 throughout (+ the f64
+// islands the reference has: camera ray, zero-barycentric fallback, accumulation), compiled with
+// -fmad=false so that no multiply-add is contracted: operation order is the reference's.
+//
+// Design (B200-first, not a translation of the reference's recursive std::function):
+//   * ssb_trace_kernel — persistent kernel, one CTA set per SM, grid = SMs x resident CTAs.
+//     One lane = one path.  The recursion L() is turned into a per-lane state machine in which
+//     EVERY loop iteration performs exactly one ray query (closest-hit or shadow) for every lane,
+//     so the dominant cost (the linear scan over the quad list, scene.cpp:433-445) always runs
+//     converged; lanes whose path ended regenerate a new path in place (warp-ballot compaction of
+//     the work queue: one atomic per warp per chunk), so lanes do not idle while the longest path
+//     of the warp finishes.
+//   * the scene, materials, spectra, observer/basis tables and the sRGB LUT are one contiguous
+//     "blob" that each CTA pulls into shared memory with a single TMA bulk copy
+//     (cp.async.bulk.shared::cluster.global + mbarrier).
+//   * the reference folds radiance on the way back UP the recursion (renderer.cpp:216,248); to keep
+//     that exact rounding, each lane keeps a small per-depth stack (local memory, L1-resident) and
+//     folds it backwards when its path ends.
+//   * each sample's float4 (X,Y,Z,hit) goes to a [sample][pixel] buffer; ssb_accumulate_kernel then
+//     adds sample*0.001f to the double XYZA accumulator in sample order — the reference's exact
+//     summation order (renderer.cpp:292-295), deterministic run to run (no float/double atomics).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/ssb200.h"
+#include "ssb_math.cuh"
+
+namespace ssbk {
+
+// ------------------------------------------------------------------ device blob layout
+struct DevSpectrum {  // _Spectrum (spectrum.hpp:12-70), data in the float pool
+	uint32_t offset;    // index of the first sample in the pool
+	uint32_t n_filter;  // n | (nearest ? 1u<<31 : 0)
+	float low;
+	float recip;        // _delta_lambda_recip = float(n-1)/(high-low), spectrum.cpp:22-25
+};
+struct DevMaterial {
+	uint32_t kind, albedo_mode, texture, pad;
+	DevSpectrum albedo, emission;
+};
+struct DevTexture {
+	const uchar4* rgba;  // RGB8 re-packed to RGBA8 at upload: one aligned 4-byte load per texel
+	uint32_t width, height;
+};
+struct DevHeader {
+	uint32_t nquads, nmaterials, nlights, ntextures;
+	uint32_t off_quads, off_materials, off_lights, off_textures, off_pool;  // byte offsets from blob start
+	uint32_t total_bytes;  // multiple of 16
+	uint32_t pad[2];
+	DevSpectrum xbar, ybar, zbar, basis_r, basis_g, basis_b;
+	float srgb_lut[256];  // Color::srgb_to_lrgb(v/255) for v = 0..255 (color.hpp:91-97), built with the host libm
+};
+
+struct KParams {
+	const unsigned char* blob;
+	float4* samples;               // [nsamp][npix_rect]
+	unsigned long long* work_counter;
+	unsigned long long total_work;  // npix_rect * nsamp
+	uint32_t width, height, x0, y0, rect_w, rect_h, sample_begin, nsamp;
+	uint32_t indirect_only, upsampling, max_depth, els, flat_field;
+	float eps, lambda_min, lambda_step;
+	unsigned long long seed;
+	double pv_inv[16];
+	float cam_pos[3], cam_dir[3];
+	const float* jh_scale;
+	const float* jh_data;
+	uint32_t jh_res;
+	const int32_t* meng_grid;
+	const float* meng_points;
+	uint32_t meng_grid_w, meng_grid_h, meng_npoints, meng_nsamples;
+	float meng_xy_to_uv[6];
+	float meng_sample_min, meng_sample_max;
+};
+
+struct Hero { float v[4]; };
+
+#define SSB_PI_F 3.14159265358979323846f
+
+// ------------------------------------------------------------------ small helpers (GLM scalar semantics)
+__device__ __forceinline__ float glm_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float glm_max(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ float glm_clamp(float x, float lo, float hi) { return glm_min(glm_max(x, lo), hi); }
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+	return (ax * bx + ay * by) + az * bz;
+}
+__device__ __forceinline__ float sel3(float x, float y, float z, int i) { return i == 0 ? x : (i == 1 ? y : z); }
+
+// ------------------------------------------------------------------ RNG (util/random.hpp:16-78)
+struct Rng { unsigned long long state, inc; };
+__device__ __forceinline__ uint32_t rng_next(Rng& r) {
+	unsigned long long s = r.state;
+	uint32_t xorshifted = (uint32_t)(((s >> 18u) ^ s) >> 27u);
+	uint32_t rot = (uint32_t)(s >> 59u);
+	uint32_t result = __funnelshift_r(xorshifted, xorshifted, rot);  // rotr32
+	r.state = s * 6364136223846793005ull + r.inc;
+	return result;
+}
+__device__ __forceinline__ float rand_1f(Rng& r) {  // libstdc++ generate_canonical<float,24>
+	float ret = (float)rng_next(r) * 2.3283064365386963e-10f;  // /2^32, exact scaling
+	if (ret >= 1.0f) ret = __uint_as_float(0x3f7fffffu);       // nextafter(1,0)
+	return ret;
+}
+__device__ __forceinline__ double rand_1d(Rng& r) {  // generate_canonical<double,53>: (u0 + u1*2^32)/2^64
+	double sum = (double)rng_next(r);
+	sum += (double)rng_next(r) * 4294967296.0;
+	double ret = sum * 5.421010862427522e-20;  // /2^64, exact scaling
+	if (ret >= 1.0) ret = __longlong_as_double(0x3fefffffffffffffll);
+	return ret;
+}
+__device__ __forceinline__ uint32_t rand_choice(Rng& r, uint32_t n) {  // Lemire, libstdc++ _S_nd
+	unsigned long long product = (unsigned long long)rng_next(r) * (unsigned long long)n;
+	uint32_t low = (uint32_t)product;
+	if (low < n) {
+		uint32_t threshold = (0u - n) % n;
+		while (low < threshold) {
+			product = (unsigned long long)rng_next(r) * (unsigned long long)n;
+			low = (uint32_t)product;
+		}
+	}
+	return (uint32_t)(product >> 32);
+}
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+// ------------------------------------------------------------------ shared-memory view of the blob
+struct SceneView {
+	const DevHeader* hdr;
+	const ssb_quad* quads;
+	const DevMaterial* materials;
+	const uint32_t* lights;
+	const DevTexture* textures;
+	const float* pool;
+};
+
+// _Spectrum::_sample_linear / _sample_nearest (spectrum.cpp:29-60)
+__device__ __forceinline__ float spec_sample(const float* pool, const DevSpectrum& s, float lambda) {
+	uint32_t n = s.n_filter & 0x7fffffffu;
+	float i = (lambda - s.low) * s.recip;
+	if (s.n_filter >> 31) {
+		int ii = (int)roundf(i);
+		return ((uint32_t)ii < n) ? pool[s.offset + ii] : 0.0f;
+	}
+	float i0f = floorf(i);
+	float frac = i - i0f;
+	int i0 = (int)i0f;
+	int i1 = i0 + 1;
+	float val0 = ((uint32_t)i0 < n) ? pool[s.offset + i0] : 0.0f;
+	float val1 = ((uint32_t)i1 < n) ? pool[s.offset + i1] : 0.0f;
+	return val0 * (1.0f - frac) + val1 * frac;
+}
+// _Spectrum::operator[] (spectrum.cpp:61-67)
+__device__ __forceinline__ Hero spec_hero(const float* pool, const DevSpectrum& s, float lambda_0, float step) {
+	Hero h;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) h.v[i] = spec_sample(pool, s, lambda_0 + (float)i * step);
+	return h;
+}
+
+// ------------------------------------------------------------------ upsampling (util/color.cpp:166-232)
+__device__ __forceinline__ int jh_find_interval(const float* values, int size_, float x) {  // rgb2spec.c:56-75
+	int left = 0, last_interval = size_ - 2, size = last_interval;
+	while (size > 0) {
+		int half = size >> 1, middle = left + half + 1;
+		if (values[middle] < x) { left = middle; size -= half + 1; }
+		else size = half;
+	}
+	return left < last_interval ? left : last_interval;
+}
+__device__ __noinline__ Hero jh_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
+	// rgb2spec_fetch (rgb2spec.c:77-118) + rgb2spec_eval_precise (:129-133), no FMA (parity build)
+	float rgb[3] = { r, g, b };
+	int i = 0, res = (int)P.jh_res;
+	for (int j = 1; j < 3; ++j) if (rgb[j] >= rgb[i]) i = j;
+	float z = rgb[i], scale = (float)(res - 1) / z;
+	float x = rgb[(i + 1) % 3] * scale, y = rgb[(i + 2) % 3] * scale;
+	uint32_t xu = (x != x) ? 0u : (uint32_t)x, yu = (y != y) ? 0u : (uint32_t)y;  // see oracle note on NaN
+	uint32_t xi = min(xu, (uint32_t)(res - 2)), yi = min(yu, (uint32_t)(res - 2));
+	uint32_t zi = (uint32_t)jh_find_interval(P.jh_scale, res, z);
+	uint32_t offset = (((i * res + zi) * res + yi) * res + xi) * 3, dx = 3, dy = 3 * res, dz = 3 * res * res;
+	float x1 = x - (float)xi, x0 = 1.f - x1, y1 = y - (float)yi, y0 = 1.f - y1;
+	float z1 = (z - P.jh_scale[zi]) / (P.jh_scale[zi + 1] - P.jh_scale[zi]), z0 = 1.f - z1;
+	const float* d = P.jh_data;
+	float coeff[3];
+	for (int j = 0; j < 3; ++j) {
+		coeff[j] = ((__ldg(d + offset) * x0 + __ldg(d + offset + dx) * x1) * y0 +
+		            (__ldg(d + offset + dy) * x0 + __ldg(d + offset + dy + dx) * x1) * y1) * z0 +
+		           ((__ldg(d + offset + dz) * x0 + __ldg(d + offset + dz + dx) * x1) * y0 +
+		            (__ldg(d + offset + dz + dy) * x0 + __ldg(d + offset + dz + dy + dx) * x1) * y1) * z1;
+		offset++;
+	}
+	Hero h;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		float lambda = lambda_0 + (float)k * P.lambda_step;
+		float xx = (coeff[0] * lambda + coeff[1]) * lambda + coeff[2];
+		float yy = 1.f / sqrtf(xx * xx + 1.f);
+		h.v[k] = (.5f * xx) * yy + .5f;
+	}
+	return h;
+}
+// spectrum_xyz_to_p (meng-et-al.-2015/spectrum_grid.h:13-137)
+__device__ __noinline__ float meng_xyz_to_p(const KParams& P, float lambda, const float* xyz) {
+	float xyY[3], uv[2];
+	const float norm = (float)(1.0 / (double)((xyz[0] + xyz[1]) + xyz[2]));
+	if (!(norm < 3.402823466e+38f)) return 0.0f;
+	xyY[0] = xyz[0] * norm; xyY[1] = xyz[1] * norm; xyY[2] = xyz[1];
+	uv[0] = P.meng_xy_to_uv[0] * xyY[0] + P.meng_xy_to_uv[1] * xyY[1] + P.meng_xy_to_uv[2];
+	uv[1] = P.meng_xy_to_uv[3] * xyY[0] + P.meng_xy_to_uv[4] * xyY[1] + P.meng_xy_to_uv[5];
+	if (uv[0] < 0.0f || uv[0] >= (float)P.meng_grid_w || uv[1] < 0.0f || uv[1] >= (float)P.meng_grid_h) return 0.f;
+	int uvi[2] = { (int)uv[0], (int)uv[1] };
+	const int cell_idx = uvi[0] + (int)P.meng_grid_w * uvi[1];
+	const int32_t* cell = P.meng_grid + 8 * cell_idx;
+	const int inside = cell[0], num = cell[1];
+	const int32_t* idx = cell + 2;
+	const uint32_t stride = 5 + P.meng_nsamples;
+	float p[6];
+	const int ns = (int)P.meng_nsamples;
+	const float sb = (lambda - P.meng_sample_min) / (P.meng_sample_max - P.meng_sample_min) * (float)(ns - 1);
+	const int sb0 = (int)sb;
+	const int sb1 = sb + 1 < (float)ns ? (int)(sb + 1) : ns - 1;
+	const float sbf = sb - (float)sb0;
+	for (int i = 0; i < num; ++i) {
+		const float* spectrum = P.meng_points + (size_t)stride * idx[i] + 5;
+		p[i] = spectrum[sb0] * (1.0f - sbf) + spectrum[sb1] * sbf;
+	}
+	float interpolated_p = 0.0f;
+	if (inside) {
+		uv[0] -= (float)uvi[0]; uv[1] -= (float)uvi[1];
+		interpolated_p = p[0] * (1.0f - uv[0]) * (1.0f - uv[1]) + p[2] * (1.0f - uv[0]) * uv[1] +
+		                 p[3] * uv[0] * uv[1] + p[1] * uv[0] * (1.0f - uv[1]);
+	} else {
+#define SSB_MENG_UV(k, c) (P.meng_points[(size_t)stride * idx[k] + 3 + (c)])
+		const float ex = uv[0] - SSB_MENG_UV(0, 0), ey = uv[1] - SSB_MENG_UV(0, 1);
+		float e0x = SSB_MENG_UV(1, 0) - SSB_MENG_UV(0, 0), e0y = SSB_MENG_UV(1, 1) - SSB_MENG_UV(0, 1);
+		float uu = e0x * ey - ex * e0y;
+		for (int i = 0; i < num - 1; i++) {
+			float e1x, e1y;
+			if (i == num - 2) { e1x = SSB_MENG_UV(1, 0) - SSB_MENG_UV(0, 0); e1y = SSB_MENG_UV(1, 1) - SSB_MENG_UV(0, 1); }
+			else { e1x = SSB_MENG_UV(i + 2, 0) - SSB_MENG_UV(0, 0); e1y = SSB_MENG_UV(i + 2, 1) - SSB_MENG_UV(0, 1); }
+			float vv = ex * e1y - e1x * ey;
+			const float area = e0x * e1y - e1x * e0y;
+			const float u = uu / area, v = vv / area;
+			float w = 1.0f - u - v;
+			if (u < 0.0f || v < 0.0f || w < 0.0f) { uu = -vv; e0x = e1x; e0y = e1y; continue; }
+			interpolated_p = p[0] * w + p[i + 1] * v + p[(i == num - 2) ? 1 : (i + 2)] * u;
+			break;
+		}
+#undef SSB_MENG_UV
+	}
+	return interpolated_p / norm;
+}
+__device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
+	// color.cpp:189-200: xyz_rel = transpose(M) * 100 * lrgb
+	const float M[9] = { 0.41231515f, 0.3576f, 0.1805f, 0.2126f, 0.7152f, 0.0722f, 0.01932727f, 0.1192f, 0.95063333f };
+	float xyz_rel[3];
+	for (int rr = 0; rr < 3; ++rr)
+		xyz_rel[rr] = ((M[rr * 3 + 0] * 100.0f) * r + (M[rr * 3 + 1] * 100.0f) * g) + (M[rr * 3 + 2] * 100.0f) * b;
+	Hero h;
+	for (int k = 0; k < 4; ++k) h.v[k] = meng_xyz_to_p(P, lambda_0 + (float)k * P.lambda_step, xyz_rel);
+	return h;
+}
+
+// material albedo at (st, lambda_0): constant spectrum or sRGB texture + upsampling
+// (material.cpp:45-97,120-143; color.cpp:166-232)
+__device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneView& S, const DevMaterial& m,
+                                                float st_x, float st_y, float lambda_0) {
+	if (m.albedo_mode == SSB_ALBEDO_CONSTANT) return spec_hero(S.pool, m.albedo, lambda_0, P.lambda_step);
+	const DevTexture tex = S.textures[m.texture];
+	float index_x = st_x * (float)tex.width;
+	float index_y = (float)tex.height - st_y * (float)tex.height;
+	int i = (int)floorf(index_x), j = (int)floorf(index_y);
+	i = max(i, 0); i = min(i, (int)tex.width - 1);
+	j = max(j, 0); j = min(j, (int)tex.height - 1);
+	uchar4 px = __ldg(tex.rgba + ((size_t)j * tex.width + (size_t)i));
+	float r = S.hdr->srgb_lut[px.x], g = S.hdr->srgb_lut[px.y], b = S.hdr->srgb_lut[px.z];
+	if (P.upsampling == SSB_UPSAMPLE_OURS) {
+		Hero br = spec_hero(S.pool, S.hdr->basis_r, lambda_0, P.lambda_step);
+		Hero bg = spec_hero(S.pool, S.hdr->basis_g, lambda_0, P.lambda_step);
+		Hero bb = spec_hero(S.pool, S.hdr->basis_b, lambda_0, P.lambda_step);
+		Hero h;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) h.v[k] = (r * br.v[k] + g * bg.v[k]) + b * bb.v[k];
+		return h;
+	} else if (P.upsampling == SSB_UPSAMPLE_JH) {
+		return jh_upsample(P, r, g, b, lambda_0);
+	}
+	return meng_upsample(P, r, g, b, lambda_0);
+}
+
+// ------------------------------------------------------------------ ray / scene intersection
+struct RayConst {  // per-ray constants of the watertight test (geometry.cpp:17-37), hoisted out of the scan
+	int kx, ky, kz;
+	float Sx, Sy, Sz;
+	float okx, oky, okz;  // ray origin permuted
+};
+__device__ __forceinline__ RayConst ray_setup(float ox, float oy, float oz, float dx, float dy, float dz) {
+	RayConst rc;
+	float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+	int kx, ky, kz;
+	if (ax > ay) {
+		if (ax > az) { kz = 0; kx = 1; ky = 2; } else { kz = 2; kx = 0; ky = 1; }
+	} else {
+		if (ay > az) { kz = 1; kx = 2; ky = 0; } else { kz = 2; kx = 0; ky = 1; }
+	}
+	float dkz = sel3(dx, dy, dz, kz);
+	if (dkz < 0.0f) { int t = kx; kx = ky; ky = t; }
+	rc.kx = kx; rc.ky = ky; rc.kz = kz;
+	rc.Sx = sel3(dx, dy, dz, kx) / dkz;
+	rc.Sy = sel3(dx, dy, dz, ky) / dkz;
+	rc.Sz = 1.0f / dkz;
+	rc.okx = sel3(ox, oy, oz, kx); rc.oky = sel3(ox, oy, oz, ky); rc.okz = sel3(ox, oy, oz, kz);
+	return rc;
+}
+
+struct Hit {
+	int quad;  // -1: none
+	int tri;
+	float dist;
+	float bx, by, bz;  // barycentrics (UVW * det_recip)
+};
+
+// PrimTri::intersect (geometry.cpp:12-101); true when the hit record was updated
+__device__ __forceinline__ bool tri_intersect(const ssb_tri& t, const RayConst& rc, float eps, Hit& hit) {
+	// vertices relative to the ray origin, permuted: A = v0 - orig etc. (geometry.cpp:40-47)
+	float Akx = t.v[0].pos[rc.kx] - rc.okx, Aky = t.v[0].pos[rc.ky] - rc.oky, Akz = t.v[0].pos[rc.kz] - rc.okz;
+	float Bkx = t.v[1].pos[rc.kx] - rc.okx, Bky = t.v[1].pos[rc.ky] - rc.oky, Bkz = t.v[1].pos[rc.kz] - rc.okz;
+	float Ckx = t.v[2].pos[rc.kx] - rc.okx, Cky = t.v[2].pos[rc.ky] - rc.oky, Ckz = t.v[2].pos[rc.kz] - rc.okz;
+	float Ax = Akx - rc.Sx * Akz, Bx = Bkx - rc.Sx * Bkz, Cx = Ckx - rc.Sx * Ckz;
+	float Ay = Aky - rc.Sy * Akz, By = Bky - rc.Sy * Bkz, Cy = Cky - rc.Sy * Ckz;
+	// UVW = cross(ABCy, ABCx)
+	float U = By * Cx - Bx * Cy;
+	float V = Cy * Ax - Cx * Ay;
+	float W = Ay * Bx - Ax * By;
+	if (U != 0.0f && V != 0.0f && W != 0.0f) {
+		if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+	} else {
+		double Ud = (double)By * (double)Cx - (double)Bx * (double)Cy;
+		double Vd = (double)Cy * (double)Ax - (double)Cx * (double)Ay;
+		double Wd = (double)Ay * (double)Bx - (double)Ax * (double)By;
+		if ((Ud < 0.0 || Vd < 0.0 || Wd < 0.0) && (Ud > 0.0 || Vd > 0.0 || Wd > 0.0)) return false;
+		U = (float)Ud; V = (float)Vd; W = (float)Wd;
+	}
+	float det = (U + V) + W;
+	if (!(fabsf(det) > eps)) return false;
+	float T = (U * (rc.Sz * Akz) + V * (rc.Sz * Bkz)) + W * (rc.Sz * Ckz);
+	if (((__float_as_uint(det) ^ __float_as_uint(T)) & 0x80000000u) != 0u) return false;
+	float det_recip = 1.0f / det;
+	float dist = T * det_recip;
+	if (dist >= eps && dist < hit.dist) {
+		hit.dist = dist;
+		hit.bx = U * det_recip; hit.by = V * det_recip; hit.bz = W * det_recip;
+		return true;
+	}
+	return false;
+}
+
+// Scene::intersect (scene.cpp:433-445) + PrimQuad::intersect (geometry.cpp:128-139)
+__device__ __forceinline__ void scene_intersect(const SceneView& S, const RayConst& rc, float eps, int ignore, Hit& hit) {
+	hit.quad = -1; hit.tri = 0; hit.dist = __int_as_float(0x7f800000);
+	hit.bx = hit.by = hit.bz = 0.0f;
+	const int nq = (int)S.hdr->nquads;
+	for (int q = 0; q < nq; ++q) {
+		if (q == ignore) continue;
+		const ssb_quad& quad = S.quads[q];
+		if (tri_intersect(quad.tri[0], rc, eps, hit)) { hit.quad = q; hit.tri = 0; }
+		else if (tri_intersect(quad.tri[1], rc, eps, hit)) { hit.quad = q; hit.tri = 1; }
+	}
+}
+
+// ------------------------------------------------------------------ light sampling
+// Math::SphericalTriangle (util/spherical-tri.cpp:18-124) + Math::rand_toward_sphericaltri
+// (util/random.cpp:101-154, Arvo 1995) + PrimTri::get_rand_toward (geometry.cpp:103-116), fused.
+__device__ __forceinline__ float underestimate_pi() { return __uint_as_float(0x40490FDAu); }
+
+__device__ __forceinline__ void func_bar(float xx, float xy, float xz, float yx, float yy, float yz,
+                                         float& ox, float& oy, float& oz) {  // random.cpp:139-144
+	float d = dot3(xx, xy, xz, yx, yy, yz);
+	float dx = xx - d * yx, dy = xy - d * yy, dz = xz - d * yz;
+	float lensq = dot3(dx, dy, dz, dx, dy, dz);
+	if (lensq == 0.0f) { ox = oy = oz = 0.0f; return; }
+	float inv = 1.0f / sqrtf(lensq);
+	ox = dx * inv; oy = dy * inv; oz = dz * inv;
+}
+
+__device__ __noinline__ void sample_spherical_triangle(const ssb_tri& t, float px, float py, float pz, float r0, float r1,
+                                                       float& wx, float& wy, float& wz, float& pdf) {
+	// unit vectors toward the vertices: glm::normalize(v - from) = v * (1/sqrt(dot))
+	float Ax = t.v[0].pos[0] - px, Ay = t.v[0].pos[1] - py, Az = t.v[0].pos[2] - pz;
+	float Bx = t.v[1].pos[0] - px, By = t.v[1].pos[1] - py, Bz = t.v[1].pos[2] - pz;
+	float Cx = t.v[2].pos[0] - px, Cy = t.v[2].pos[1] - py, Cz = t.v[2].pos[2] - pz;
+	float ia = 1.0f / sqrtf(dot3(Ax, Ay, Az, Ax, Ay, Az)); Ax *= ia; Ay *= ia; Az *= ia;
+	float ib = 1.0f / sqrtf(dot3(Bx, By, Bz, Bx, By, Bz)); Bx *= ib; By *= ib; Bz *= ib;
+	float ic = 1.0f / sqrtf(dot3(Cx, Cy, Cz, Cx, Cy, Cz)); Cx *= ic; Cy *= ic; Cz *= ic;
+
+	float cos_a = glm_clamp(dot3(Bx, By, Bz, Cx, Cy, Cz), -1.0f, 1.0f);
+	float cos_b = glm_clamp(dot3(Ax, Ay, Az, Cx, Cy, Cz), -1.0f, 1.0f);
+	float cos_c = glm_clamp(dot3(Ax, Ay, Az, Bx, By, Bz), -1.0f, 1.0f);
+	float a = glm_clamp(ssbm::acosf_exact(cos_a), 0.0f, underestimate_pi());
+	float b = glm_clamp(ssbm::acosf_exact(cos_b), 0.0f, underestimate_pi());
+	float c = glm_clamp(ssbm::acosf_exact(cos_c), 0.0f, underestimate_pi());
+	float sin_a = ssbm::sinf_exact(a), sin_b = ssbm::sinf_exact(b), sin_c = ssbm::sinf_exact(c);
+	float numer0 = cos_a - cos_b * cos_c;
+	float numer1 = cos_b - cos_c * cos_a;
+	float numer2 = cos_c - cos_a * cos_b;
+	float denom0 = sin_b * sin_c, denom1 = sin_c * sin_a, denom2 = sin_a * sin_b;
+	float alpha, cos_alpha, surface_area;
+	const float nan = __int_as_float(0x7fc00000);
+	if (denom0 > 0 && denom1 > 0 && denom2 > 0) {
+		cos_alpha = glm_clamp(numer0 / denom0, -1.0f, 1.0f);
+		float cos_beta = glm_clamp(numer1 / denom1, -1.0f, 1.0f);
+		float cos_gamma = glm_clamp(numer2 / denom2, -1.0f, 1.0f);
+		alpha = glm_clamp(ssbm::acosf_exact(cos_alpha), 0.0f, underestimate_pi());
+		float beta = glm_clamp(ssbm::acosf_exact(cos_beta), 0.0f, underestimate_pi());
+		float gamma = glm_clamp(ssbm::acosf_exact(cos_gamma), 0.0f, underestimate_pi());
+		surface_area = ((alpha + beta) + gamma) - SSB_PI_F;
+		if (!(surface_area >= 0)) surface_area = 0;
+	} else {
+		// degenerate branches (spherical-tri.cpp:74-122): only alpha / cos_alpha are consumed downstream
+		surface_area = 0;
+		if (sin_a > 0) {
+			if (sin_b > 0) {
+				if (sin_c > 0) { alpha = cos_alpha = nan; }
+				else { cos_alpha = 1; alpha = SSB_PI_F * 0.5f; }
+			} else {
+				if (sin_c > 0) { cos_alpha = 1; alpha = SSB_PI_F * 0.5f; }
+				else { alpha = cos_alpha = nan; }
+			}
+		} else {
+			if (sin_b > 0 && sin_c > 0) { cos_alpha = glm_clamp(numer0 / denom0, -1.0f, 1.0f); alpha = ssbm::acosf_exact(cos_alpha); }
+			else { alpha = cos_alpha = nan; }
+		}
+	}
+	pdf = 1.0f / surface_area;  // geometry.cpp:115 (inf when the area is 0)
+
+	// Arvo sampling (random.cpp:101-154)
+	float sin_alpha = ssbm::sinf_exact(alpha);
+	float q;
+	if (sin_alpha > 0) {
+		float random_area = r0 * surface_area;
+		float phi = random_area - alpha;
+		float s = ssbm::sinf_exact(phi), tt = ssbm::cosf_exact(phi);
+		float u = tt - cos_alpha;
+		float v = s + sin_alpha * cos_c;
+		float denom = (v * s + u * tt) * sin_alpha;
+		if (denom != 0.0f) q = ((v * tt - u * s) * cos_alpha - v) / denom;
+		else q = cos_c;
+	} else {
+		q = (float)cos((double)(b * r0));  // ::cos(double), random.cpp:135
+	}
+	q = glm_clamp(q, -1.0f, 1.0f);
+	float fx, fy, fz;
+	func_bar(Cx, Cy, Cz, Ax, Ay, Az, fx, fy, fz);
+	float sq = sqrtf(1.0f - q * q);
+	float Chx = q * Ax + sq * fx, Chy = q * Ay + sq * fy, Chz = q * Az + sq * fz;
+	float z = 1.0f - r1 * (1.0f - dot3(Chx, Chy, Chz, Bx, By, Bz));
+	z = glm_clamp(z, -1.0f, 1.0f);
+	func_bar(Chx, Chy, Chz, Bx, By, Bz, fx, fy, fz);
+	float sz = sqrtf(1.0f - z * z);
+	wx = z * Bx + sz * fx; wy = z * By + sz * fy; wz = z * Bz + sz * fz;
+}
+
+// ------------------------------------------------------------------ per-lane path state
+#define SSB_STACK_FLOATS 10  // local[4], f[4], n_dot_l, pdf
+
+enum : int { ST_CLOSEST = 0, ST_SHADOW = 1 };
+
+// ------------------------------------------------------------------ TMA bulk copy of the blob into shared memory
+__device__ __forceinline__ void stage_blob(unsigned char* smem, const unsigned char* gmem, uint32_t bytes,
+                                           unsigned long long* bar) {
+	const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(bar);
+	const uint32_t dst_addr = (uint32_t)__cvta_generic_to_shared(smem);
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+		asm volatile(
+			"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_addr),
+			"l"(gmem), "r"(bytes), "r"(bar_addr)
+			: "memory");
+	}
+	// all threads wait for phase 0 to complete
+	uint32_t done = 0;
+	while (!done) {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done)
+			: "r"(bar_addr)
+			: "memory");
+	}
+}
+
+#ifndef SSB_TRACE_THREADS
+#define SSB_TRACE_THREADS 128
+#endif
+#ifndef SSB_TRACE_MIN_BLOCKS
+#define SSB_TRACE_MIN_BLOCKS 4
+#endif
+#define SSB_WORK_CHUNK 128u  // work items a warp reserves per atomic
+
+__global__ void __launch_bounds__(SSB_TRACE_THREADS, SSB_TRACE_MIN_BLOCKS)
+ssb_trace_kernel(const __grid_constant__ KParams P) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long blob_bar;
+	{
+		const DevHeader* gh = reinterpret_cast<const DevHeader*>(P.blob);
+		stage_blob(smem_raw, P.blob, __ldg(&gh->total_bytes), &blob_bar);
+	}
+	SceneView S;
+	S.hdr = reinterpret_cast<const DevHeader*>(smem_raw);
+	S.quads = reinterpret_cast<const ssb_quad*>(smem_raw + S.hdr->off_quads);
+	S.materials = reinterpret_cast<const DevMaterial*>(smem_raw + S.hdr->off_materials);
+	S.lights = reinterpret_cast<const uint32_t*>(smem_raw + S.hdr->off_lights);
+	S.textures = reinterpret_cast<const DevTexture*>(smem_raw + S.hdr->off_textures);
+	S.pool = reinterpret_cast<const float*>(smem_raw + S.hdr->off_pool);
+
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const uint32_t npix_rect = P.rect_w * P.rect_h;
+	const float eps = P.eps;
+	const bool els = P.els != 0;
+
+	// warp-uniform work queue
+	unsigned long long wq_next = 0, wq_end = 0;
+	bool exhausted = false;
+
+	// per-lane path state
+	bool alive = false;
+	int state = ST_CLOSEST;
+	Rng rng; rng.state = 0; rng.inc = 1;
+	unsigned long long out_index = 0;
+	float ox = 0, oy = 0, oz = 0;     // ray origin (becomes the hit point once something was hit)
+	float dx = 0, dy = 0, dz = 1;     // path direction
+	float sx = 0, sy = 0, sz = 1;     // shadow-ray direction (ST_SHADOW)
+	float nx = 0, ny = 0, nz = 0;     // geometric normal at the current vertex
+	float lambda_0 = 0, ff_scale = 1.0f;
+	Hero f_s, local;                  // BSDF value and radiance gathered at the current vertex
+	f_s.v[0] = f_s.v[1] = f_s.v[2] = f_s.v[3] = 0; local = f_s;
+	float l_ndl = 0, l_pdf = 1;       // light sample: n.l and pdf
+	int depth = 0, ignore = -1, cur_quad = -1, light_quad = -1;
+	bool last_was_delta = true, hit_anything = false;
+	float stk[SSB_MAX_DEPTH * SSB_STACK_FLOATS];
+
+	while (true) {
+		// ---------------------------------------------------------------- regeneration
+		bool need = !alive && !exhausted;
+		unsigned need_mask = __ballot_sync(full, need);
+		while (need_mask) {
+			unsigned long long avail = wq_end - wq_next;
+			unsigned rank = __popc(need_mask & ((1u << lane) - 1u));
+			unsigned cnt = __popc(need_mask);
+			if (need && rank < avail) {
+				// -------- start a new path: Renderer::_render_sample prologue (renderer.cpp:103-138)
+				unsigned long long work = wq_next + rank;
+				uint32_t kk = (uint32_t)(work / npix_rect);
+				uint32_t pr = (uint32_t)(work - (unsigned long long)kk * npix_rect);
+				uint32_t pi = P.x0 + pr % P.rect_w, pj = P.y0 + pr / P.rect_w;
+				uint32_t k = P.sample_begin + kk;
+				out_index = work;
+				unsigned long long sample_index = (unsigned long long)k * ((unsigned long long)P.width * P.height) +
+				                                  ((unsigned long long)pj * P.width + pi);
+				rng.state = mix64(P.seed ^ mix64(sample_index));
+				rng.inc = mix64(rng.state) | 1ull;
+				double sub_y = rand_1d(rng);  // g++ evaluates dvec2(rand_1d(),rand_1d()) right-to-left
+				double sub_x = rand_1d(rng);
+				double st_x = ((double)pi + sub_x) / (double)P.width;
+				double st_y = ((double)pj + sub_y) / (double)P.height;
+				double ndc_x = st_x * 2.0 - 1.0, ndc_y = st_y * 2.0 - 1.0;
+				double pt[4];
+#pragma unroll
+				for (int r = 0; r < 4; ++r)
+					pt[r] = (P.pv_inv[0 + r] * ndc_x + P.pv_inv[4 + r] * ndc_y) + (P.pv_inv[8 + r] * 0.0 + P.pv_inv[12 + r] * 1.0);
+				double w = pt[3];
+				double ddx = pt[0] / w - (double)P.cam_pos[0], ddy = pt[1] / w - (double)P.cam_pos[1], ddz = pt[2] / w - (double)P.cam_pos[2];
+				double inv = 1.0 / sqrt((ddx * ddx + ddy * ddy) + ddz * ddz);
+				ox = P.cam_pos[0]; oy = P.cam_pos[1]; oz = P.cam_pos[2];
+				dx = (float)(ddx * inv); dy = (float)(ddy * inv); dz = (float)(ddz * inv);
+				lambda_0 = P.lambda_min + rand_1f(rng) * P.lambda_step;
+				if (!P.flat_field) ff_scale = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
+				depth = 0; ignore = -1; last_was_delta = true; hit_anything = false; state = ST_CLOSEST;
+				alive = true; need = false;
+			}
+			wq_next += (cnt < avail) ? cnt : avail;
+			need_mask = __ballot_sync(full, need);
+			if (!need_mask) break;
+			unsigned long long base = 0;
+			if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)SSB_WORK_CHUNK);
+			base = __shfl_sync(full, base, 0);
+			if (base >= P.total_work) { exhausted = true; break; }
+			wq_next = base;
+			wq_end = (base + SSB_WORK_CHUNK < P.total_work) ? base + SSB_WORK_CHUNK : P.total_work;
+		}
+		if (!__any_sync(full, alive)) break;
+
+		// ---------------------------------------------------------------- one ray query for every live lane
+		Hit hit;
+		hit.quad = -1; hit.tri = 0; hit.dist = 0; hit.bx = hit.by = hit.bz = 0;
+		if (alive) {
+			RayConst rc = (state == ST_SHADOW) ? ray_setup(ox, oy, oz, sx, sy, sz) : ray_setup(ox, oy, oz, dx, dy, dz);
+			scene_intersect(S, rc, eps, (state == ST_SHADOW) ? cur_quad : ignore, hit);
+		}
+
+		bool do_bsdf = false, finish = false;
+		Hero rad;  // value returned by the deepest L() call when the path ends
+		rad.v[0] = rad.v[1] = rad.v[2] = rad.v[3] = 0.0f;
+
+		if (alive && state == ST_SHADOW) {
+			// ---- shadow ray came back (renderer.cpp:196-218)
+			if (hit.quad == light_quad) {
+				const DevMaterial& lm = S.materials[S.quads[light_quad].material];
+				Hero emitted = spec_hero(S.pool, lm.emission, lambda_0, P.lambda_step);
+				const DevMaterial& m = S.materials[S.quads[cur_quad].material];
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					float fe = (m.kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;  // MaterialMirror::evaluate_bsdf = 0
+					local.v[c] = local.v[c] + ((emitted.v[c] * l_ndl) * fe) / l_pdf;
+				}
+			}
+			do_bsdf = true;
+		} else if (alive) {
+			// ---- closest hit of the path ray: body of L() (renderer.cpp:147-255)
+			if (hit.quad < 0) {
+				finish = true;  // miss: L() returns 0
+			} else {
+				hit_anything = true;
+				cur_quad = hit.quad;
+				const ssb_quad& quad = S.quads[hit.quad];
+				const ssb_tri& tri = quad.tri[hit.tri];
+				const DevMaterial& m = S.materials[quad.material];
+				nx = tri.normal[0]; ny = tri.normal[1]; nz = tri.normal[2];
+				float st_x = (hit.bx * tri.v[0].st[0] + hit.by * tri.v[1].st[0]) + hit.bz * tri.v[2].st[0];
+				float st_y = (hit.bx * tri.v[0].st[1] + hit.by * tri.v[1].st[1]) + hit.bz * tri.v[2].st[1];
+				local.v[0] = local.v[1] = local.v[2] = local.v[3] = 0.0f;
+				if (!els || (last_was_delta && (!P.indirect_only || depth > 0))) {
+					Hero e = spec_hero(S.pool, m.emission, lambda_0, P.lambda_step);
+#pragma unroll
+					for (int c = 0; c < 4; ++c) local.v[c] = local.v[c] + e.v[c];
+				}
+				if ((uint32_t)depth + 1u < P.max_depth) {
+					// hit position (Ray::at): becomes the origin of the shadow ray and of the next path ray
+					float d_ = hit.dist;
+					ox = ox + d_ * dx; oy = oy + d_ * dy; oz = oz + d_ * dz;
+					// albedo lookup (the reference does it twice with identical arguments:
+					// evaluate_bsdf + interact_bsdf, material.cpp:120-143)
+					Hero alb = material_albedo(P, S, m, st_x, st_y, lambda_0);
+#pragma unroll
+					for (int c = 0; c < 4; ++c) f_s.v[c] = (m.kind == SSB_MATERIAL_LAMBERT) ? alb.v[c] / SSB_PI_F : alb.v[c];
+					do_bsdf = true;
+					if (els && (!P.indirect_only || depth > 0)) {
+						// Scene::get_rand_toward_light (scene.cpp:417-431)
+						uint32_t li = rand_choice(rng, S.hdr->nlights);
+						light_quad = (int)S.lights[li];
+						const ssb_quad& lq = S.quads[light_quad];
+						const ssb_tri& lt = (rand_1f(rng) <= 0.5f) ? lq.tri[0] : lq.tri[1];
+						float r0 = rand_1f(rng);
+						float r1 = rand_1f(rng);
+						float pdf;
+						sample_spherical_triangle(lt, ox, oy, oz, r0, r1, sx, sy, sz, pdf);
+						pdf *= 0.5f;
+						pdf /= (float)S.hdr->nlights;
+						l_pdf = pdf;
+						l_ndl = dot3(sx, sy, sz, nx, ny, nz);
+						if (l_ndl > 0.0f) { state = ST_SHADOW; do_bsdf = false; }
+					}
+				} else {
+					rad = local; finish = true;
+				}
+			}
+		}
+
+		if (do_bsdf) {
+			// ---- interact_bsdf + recursion decision (renderer.cpp:222-251)
+			state = ST_CLOSEST;
+			const DevMaterial& m = S.materials[S.quads[cur_quad].material];
+			float wix, wiy, wiz, pdf_w_i;
+			if (m.kind == SSB_MATERIAL_LAMBERT) {
+				// Math::rand_coshemi (random.cpp:29-49)
+				float hx, hy, hz;
+				do {
+					float angle = rand_1f(rng) * (2.0f * SSB_PI_F);
+					float co = ssbm::cosf_exact(angle), si = ssbm::sinf_exact(angle);
+					float radius_sq = rand_1f(rng);
+					float radius = sqrtf(radius_sq);
+					hx = radius * co; hy = sqrtf(1.0f - radius_sq); hz = radius * si;
+					pdf_w_i = hy;
+				} while (pdf_w_i <= eps);
+				pdf_w_i *= 1.0f / SSB_PI_F;
+				// Math::get_rotated_to / get_basis (math-helpers.hpp:14-38)
+				float sign = copysignf(1.0f, nz);
+				float a = -1.0f / (sign + nz);
+				float b = nx * ny * a;
+				float bxx = 1.0f + sign * nx * nx * a, bxy = sign * b, bxz = -sign * nx;
+				float bzx = b, bzy = sign + ny * ny * a, bzz = -ny;
+				wix = (hx * bxx + hy * nx) + hz * bzx;
+				wiy = (hx * bxy + hy * ny) + hz * bzy;
+				wiz = (hx * bxz + hy * nz) + hz * bzz;
+			} else {
+				// MaterialMirror::interact_bsdf (material.cpp:154-167): reflect(w_o = -ray.dir, N)
+				float vx = -dx, vy = -dy, vz = -dz;
+				float d2 = 2.0f * dot3(vx, vy, vz, nx, ny, nz);
+				wix = -vx + d2 * nx; wiy = -vy + d2 * ny; wiz = -vz + d2 * nz;
+				pdf_w_i = __int_as_float(0x7f800000);
+			}
+			bool recurse = false;
+			float n_dot_l = 0.0f;
+			float ff = (f_s.v[0] * f_s.v[0] + f_s.v[1] * f_s.v[1]) + (f_s.v[2] * f_s.v[2] + f_s.v[3] * f_s.v[3]);
+			if (ff > 0.0f) {
+				if (isfinite(pdf_w_i)) n_dot_l = dot3(wix, wiy, wiz, nx, ny, nz);
+				else { n_dot_l = 1.0f; pdf_w_i = 1.0f; }
+				recurse = n_dot_l > 0.0f;
+			}
+			if (recurse) {
+				float* e = stk + depth * SSB_STACK_FLOATS;
+#pragma unroll
+				for (int c = 0; c < 4; ++c) { e[c] = local.v[c]; e[4 + c] = f_s.v[c]; }
+				e[8] = n_dot_l; e[9] = pdf_w_i;
+				dx = wix; dy = wiy; dz = wiz;
+				ignore = cur_quad;
+				last_was_delta = false;  // the reference passes `false` unconditionally (renderer.cpp:248)
+				depth += 1;
+				// Dead-work skip (result-identical): with explicit light sampling the L() call at the last
+				// depth can add neither emission (last_was_delta == false) nor children: it returns 0 and
+				// hit_anything is already set.  No random numbers are drawn there either.
+				if (els && (uint32_t)depth + 1u >= P.max_depth) finish = true;  // rad = 0
+			} else {
+				rad = local; finish = true;
+			}
+		}
+
+		if (finish) {
+			// ---- unwind the recursion: radiance = local + ((child * n.l) * f_s) / pdf (renderer.cpp:248)
+			for (int d = depth - 1; d >= 0; --d) {
+				const float* e = stk + d * SSB_STACK_FLOATS;
+#pragma unroll
+				for (int c = 0; c < 4; ++c) rad.v[c] = e[c] + ((rad.v[c] * e[8]) * e[4 + c]) / e[9];
+			}
+			if (!P.flat_field) {
+#pragma unroll
+				for (int c = 0; c < 4; ++c) rad.v[c] = rad.v[c] * ff_scale;
+			}
+			// Color::specradflux_to_ciexyz (color.hpp:115-139)
+			Hero xb = spec_hero(S.pool, S.hdr->xbar, lambda_0, P.lambda_step);
+			Hero yb = spec_hero(S.pool, S.hdr->ybar, lambda_0, P.lambda_step);
+			Hero zb = spec_hero(S.pool, S.hdr->zbar, lambda_0, P.lambda_step);
+			float X = 0.0f, Y = 0.0f, Z = 0.0f;
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				X += (xb.v[c] * rad.v[c]) * P.lambda_step;
+				Y += (yb.v[c] * rad.v[c]) * P.lambda_step;
+				Z += (zb.v[c] * rad.v[c]) * P.lambda_step;
+			}
+			P.samples[out_index] = make_float4(X, Y, Z, hit_anything ? 1.0f : 0.0f);
+			alive = false;
+		}
+	}
+}
+
+// avg += double4(sample * 0.001f), in sample order (renderer.cpp:292-295)
+__global__ void ssb_accumulate_kernel(const float4* __restrict__ samples, double* __restrict__ accum,
+                                      uint32_t width, uint32_t x0, uint32_t y0, uint32_t rect_w, uint32_t rect_h,
+                                      uint32_t nsamp) {
+	uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t npix_rect = rect_w * rect_h;
+	if (pr >= npix_rect) return;
+	uint32_t pi = x0 + pr % rect_w, pj = y0 + pr / rect_w;
+	double* a = accum + 4 * ((size_t)pj * width + pi);
+	double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+	for (uint32_t k = 0; k < nsamp; ++k) {
+		float4 s = samples[(size_t)k * npix_rect + pr];
+		a0 += (double)(s.x * 0.001f); a1 += (double)(s.y * 0.001f);
+		a2 += (double)(s.z * 0.001f); a3 += (double)(s.w * 0.001f);
+	}
+	a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
+}
+
+// avg *= 1000/spp; framebuffer = (ciexyz_to_srgb(float3(avg)), float(avg.a)) (renderer.cpp:296-298, color.cpp:237-257)
+__global__ void ssb_resolve_kernel(const double* __restrict__ accum, double* __restrict__ xyza, float4* __restrict__ srgba,
+                                   uint32_t npix, double scale, uint32_t upsampling, float d65_rad_Y,
+                                   float m0, float m1, float m2, float m3, float m4, float m5, float m6, float m7, float m8) {
+	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= npix) return;
+	double avg[4];
+#pragma unroll
+	for (int c = 0; c < 4; ++c) avg[c] = accum[4 * (size_t)p + c] * scale;
+	if (xyza) {
+#pragma unroll
+		for (int c = 0; c < 4; ++c) xyza[4 * (size_t)p + c] = avg[c];
+	}
+	if (srgba) {
+		float x = (float)avg[0], y = (float)avg[1], z = (float)avg[2];
+		float lr, lg, lb;
+		if (upsampling == SSB_UPSAMPLE_MENG) {
+			x = x / d65_rad_Y; y = y / d65_rad_Y; z = z / d65_rad_Y;
+			lr = (3.24156456f * x + -1.53766524f * y) + -0.49870224f * z;
+			lg = (-0.96920119f * x + 1.87588535f * y) + 0.04155324f * z;
+			lb = (0.05562416f * x + -0.20395525f * y) + 1.05685902f * z;
+		} else {
+			lr = (m0 * x + m3 * y) + m6 * z;
+			lg = (m1 * x + m4 * y) + m7 * z;
+			lb = (m2 * x + m5 * y) + m8 * z;
+		}
+		float4 o;
+		o.x = lr < 0.0031308f ? 12.92f * lr : 1.055f * ssbm::powf_exact(lr, 1.0f / 2.4f) - 0.055f;
+		o.y = lg < 0.0031308f ? 12.92f * lg : 1.055f * ssbm::powf_exact(lg, 1.0f / 2.4f) - 0.055f;
+		o.z = lb < 0.0031308f ? 12.92f * lb : 1.055f * ssbm::powf_exact(lb, 1.0f / 2.4f) - 0.055f;
+		o.w = (float)avg[3];
+		srgba[p] = o;
+	}
+}
+
+__global__ void ssb_eval_math_kernel(uint32_t fn, const float* __restrict__ x, float arg, float* __restrict__ out, size_t n) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float v = x[i], r;
+	switch (fn) {
+		case 0: r = ssbm::sinf_exact(v); break;
+		case 1: r = ssbm::cosf_exact(v); break;
+		case 2: r = ssbm::acosf_exact(v); break;
+		default: r = ssbm::powf_exact(v, arg); break;
+	}
+	out[i] = r;
+}
+
+}  // namespace ssbk

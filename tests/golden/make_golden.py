@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures from the REAL reference (oracle/_ref/*_hooked, built by
+oracle/build_ref.py from /root/reference).  Run here (the reference cannot travel); commit the output.
+
+  tables_<scene>_<variant>.bin         Color::data + camera + flattened scene as the reference built them
+                                       (ref_hooks.hpp dump_tables) — inputs for oracle and CUDA path
+  xyza_<scene>_<variant>_<W>x<H>_spp<N>_seed<S>.npy
+                                       per-pixel double XYZA of the reference at per-sample seeding
+  golden_index.json                    sha256 of larger reference renders (BASELINE config 1)
+"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+REFBIN = os.path.join(ROOT, "oracle", "_ref")
+DATA_ROOT = os.environ.get("SSB_REFERENCE_ROOT", "/root/reference")
+
+CASES = [  # (scene, variant)
+    ("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("plane-srgb", "ours1931"),
+    ("cornell", "ours2006"), ("cornell-srgb", "ours2006"),
+    ("cornell-srgb", "jh"), ("plane-srgb", "jh"),
+    ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
+]
+SMALL = dict(w=32, h=24, spp=4, seed=7)
+C1 = dict(w=128, h=128, spp=16, seed=1)  # BASELINE.json configs[0]
+
+
+def run_ref(scene, variant, w, h, spp, seed, tables=None, indirect_only=False):
+    exe = os.path.join(REFBIN, f"simple_spectral_{variant}_hooked")
+    with tempfile.TemporaryDirectory() as tmp:
+        env = dict(os.environ, SSB_SEED=str(seed), SSB_DUMP_XYZA=os.path.join(tmp, "xyza.bin"))
+        if tables:
+            env["SSB_DUMP_TABLES"] = tables
+        cmd = [exe, f"--scene={scene}", f"-w={w}", f"-h={h}", f"-spp={spp}", f"--output={tmp}/o.pfm"]
+        if indirect_only:
+            cmd.append("--indirect-only")
+        subprocess.run(cmd, cwd=DATA_ROOT, env=env, check=True, stdout=subprocess.DEVNULL)
+        return np.fromfile(os.path.join(tmp, "xyza.bin"), dtype=np.float64).reshape(h, w, 4)
+
+
+def main():
+    index = {}
+    for scene, variant in CASES:
+        tables = os.path.join(HERE, f"tables_{scene}_{variant}.bin")
+        x = run_ref(scene, variant, tables=tables, **SMALL)
+        name = f"xyza_{scene}_{variant}_{SMALL['w']}x{SMALL['h']}_spp{SMALL['spp']}_seed{SMALL['seed']}.npy"
+        np.save(os.path.join(HERE, name), x)
+        print("wrote", name, "mean", x.mean(axis=(0, 1)))
+    x = run_ref("cornell-srgb", "ours1931", indirect_only=True, **SMALL)
+    np.save(os.path.join(HERE, f"xyza_cornell-srgb_ours1931_indirect_{SMALL['w']}x{SMALL['h']}_spp{SMALL['spp']}_seed{SMALL['seed']}.npy"), x)
+    for scene, variant in (("cornell-srgb", "ours1931"), ("cornell", "ours1931")):
+        x = run_ref(scene, variant, **C1)
+        key = f"{scene}_{variant}_{C1['w']}x{C1['h']}_spp{C1['spp']}_seed{C1['seed']}"
+        index[key] = dict(sha256=hashlib.sha256(x.tobytes()).hexdigest(), mean=list(x.mean(axis=(0, 1))),
+                          pixel_64_64=list(x[64, 64]))
+        print(key, index[key]["sha256"])
+    json.dump(index, open(os.path.join(HERE, "golden_index.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

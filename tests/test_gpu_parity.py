@@ -1,0 +1,126 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle and the committed reference fixtures.
+Bar: bit-identical per-sample float4 and per-pixel double XYZA; sRGB within 1e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("plane-srgb", "ours1931"),
+         ("cornell", "ours2006"), ("cornell-srgb", "ours2006"),
+         ("cornell-srgb", "jh"), ("plane-srgb", "jh"), ("cornell-srgb", "meng"), ("plane-srgb", "meng")]
+
+
+def _skip_if_no_assets(scene, variant):
+    if pu.needs_assets(scene, variant) and not pu.have_assets():
+        pytest.fail("data files not staged on the GPU box (assets/data): run __graft_entry__.build() first")
+
+
+@pytest.mark.parametrize("fn,lo,hi", [(0, -119.0, 119.0), (1, -119.0, 119.0), (2, -1.0, 1.0)])
+def test_device_math_bit_exact(fn, lo, hi):
+    """sinf/cosf/acosf on the device == the host libm the reference links (glibc), bit for bit."""
+    rng = np.random.default_rng(123 + fn)
+    x = np.concatenate([rng.uniform(lo, hi, 1 << 20), rng.uniform(-7.0, 7.0, 1 << 20).clip(lo, hi),
+                        np.array([0.0, -0.0, lo, hi, 1e-8, -1e-8, 0.5, -0.5, 0.78539816, 1.0, -1.0])]).astype(np.float32)
+    flat = pu.load_flat("cornell", "ours1931")
+    with pu.gpu_context(flat) as ctx:
+        got = ctx.eval_math(fn, x)
+    import ctypes as C
+    want = np.empty_like(x)
+    pu.oracle().ssb_oracle_eval_math(fn, x.ctypes.data_as(C.POINTER(C.c_float)), 0.0, want.ctypes.data_as(C.POINTER(C.c_float)), x.size)
+    assert pu.bits_equal(got, want), f"{(got.view(np.uint32) != want.view(np.uint32)).sum()} mismatches"
+
+
+@pytest.mark.parametrize("y", [2.4, 1.0 / 2.4])
+def test_device_powf_bit_exact(y):
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(0.0, 1.0, 1 << 20), np.exp(rng.uniform(-20, 20, 1 << 20)), np.arange(256) / 255.0]).astype(np.float32)
+    x = x[x > 1e-30]
+    flat = pu.load_flat("cornell", "ours1931")
+    with pu.gpu_context(flat) as ctx:
+        got = ctx.eval_math(3, x, np.float32(y))
+    import ctypes as C
+    want = np.empty_like(x)
+    pu.oracle().ssb_oracle_eval_math(3, x.ctypes.data_as(C.POINTER(C.c_float)), np.float32(y), want.ctypes.data_as(C.POINTER(C.c_float)), x.size)
+    assert pu.bits_equal(got, want)
+
+
+@pytest.mark.parametrize("scene,variant", CASES)
+def test_gpu_matches_oracle_and_reference_fixture(scene, variant):
+    _skip_if_no_assets(scene, variant)
+    flat = pu.load_flat(scene, variant)
+    opt = pu.options(variant, 32, 24, 4, seed=7)
+    acc_o, samp_o, _ = pu.oracle_render(flat, opt, want_samples=True)
+    xo, so = pu.oracle_resolve(flat, opt, acc_o)
+    with pu.gpu_context(flat) as ctx:
+        xg, sg = ctx.render_frame(opt)
+        acc_g = ctx.read_accum(opt.width, opt.height)
+        for (px, py) in ((0, 0), (16, 12), (31, 23), (5, 20)):
+            sm = ctx.trace_samples(opt, px, py)
+            assert pu.bits_equal(sm, samp_o[py, px]), f"per-sample mismatch at pixel ({px},{py})"
+    assert pu.bits_equal(acc_g, acc_o), f"accumulator differs: max rel {pu.rel_err(acc_g, acc_o).max()}"
+    assert pu.bits_equal(xg, xo)
+    ref = np.load(os.path.join(pu.GOLDEN, f"xyza_{scene}_{variant}_32x24_spp4_seed7.npy"))
+    assert pu.bits_equal(xg, ref), "differs from the real reference's XYZA fixture"
+    ok = np.isclose(sg, so, rtol=1e-6, atol=1e-7, equal_nan=True)
+    assert ok.all()
+    assert pu.bits_equal(sg, so), "sRGB tonemap not bit-identical"
+
+
+def test_gpu_config1_bit_exact():
+    """BASELINE.json configs[0]: cornell-srgb 128x128 spp16 — CUDA == oracle == reference (sha)."""
+    import hashlib, json
+    _skip_if_no_assets("cornell-srgb", "ours1931")
+    flat = pu.load_flat("cornell-srgb", "ours1931")
+    opt = pu.options("ours1931", 128, 128, 16, seed=1)
+    with pu.gpu_context(flat) as ctx:
+        xg, _ = ctx.render_frame(opt)
+    idx = json.load(open(os.path.join(pu.GOLDEN, "golden_index.json")))["cornell-srgb_ours1931_128x128_spp16_seed1"]
+    assert hashlib.sha256(xg.tobytes()).hexdigest() == idx["sha256"]
+
+
+def test_gpu_subsets_compose():
+    """tile rectangles x sample ranges accumulate to the full-frame result (the multi-GPU sharding contract)."""
+    flat = pu.load_flat("cornell", "ours1931")
+    full = pu.options("ours1931", 40, 30, 6, seed=3)
+    with pu.gpu_context(flat) as ctx:
+        ctx.render(full)
+        want = ctx.read_accum(40, 30)
+        first = True
+        for (s0, s1) in ((0, 2), (2, 6)):
+            for (x0, x1) in ((0, 17), (17, 40)):
+                o = pu.options("ours1931", 40, 30, 6, seed=3, x0=x0, x1=x1, sample_begin=s0, sample_end=s1)
+                if s0 == 0 and not first:
+                    # sample_begin == 0 clears the accumulator: carry it over explicitly
+                    keep = ctx.read_accum(40, 30)
+                    ctx.render(o)
+                    got_part = ctx.read_accum(40, 30)
+                    ctx.write_accum(keep + got_part)
+                else:
+                    ctx.render(o)
+                first = False
+        got = ctx.read_accum(40, 30)
+    assert pu.bits_equal(got, want)
+
+
+def test_gpu_full_size_properties():
+    """BASELINE configs[1] size (512x512 spp64): size-independent properties — alpha is the hit fraction,
+    corners miss the box, image-mean within Monte-Carlo noise of the config-1 reference mean."""
+    import json
+    _skip_if_no_assets("cornell-srgb", "ours1931")
+    flat = pu.load_flat("cornell-srgb", "ours1931")
+    opt = pu.options("ours1931", 512, 512, 64, seed=1)
+    with pu.gpu_context(flat) as ctx:
+        xg, sg = ctx.render_frame(opt)
+        st = ctx.stats()
+    assert st.samples == 512 * 512 * 64
+    assert np.isfinite(xg).all()
+    a = xg[..., 3]
+    assert (a >= 0).all() and (a <= 1.0 + 1e-6).all()
+    assert a[0, 0] == 0 and a[-1, -1] == 0 and abs(a[256, 256] - 1.0) < 1e-6
+    ref_mean = np.array(json.load(open(os.path.join(pu.GOLDEN, "golden_index.json")))["cornell-srgb_ours1931_128x128_spp16_seed1"]["mean"])
+    got_mean = xg.mean(axis=(0, 1))
+    assert np.allclose(got_mean, ref_mean, rtol=0.02), (got_mean, ref_mean)
