@@ -193,6 +193,15 @@ int ssb_accum_device(ssb_ctx* ctx, double** dptr, size_t* count);
  * Either output may be NULL.  HOST pointers, width*height*4 elements, row 0 = bottom. */
 int ssb_resolve(ssb_ctx* ctx, const ssb_options* opt, double* xyza_host, float* srgba_host);
 
+/* Same, but the results stay on the device (borrowed pointers into context-owned buffers, valid until
+ * the next resolve at another resolution / ssb_destroy); no host synchronisation. */
+int ssb_resolve_device(ssb_ctx* ctx, const ssb_options* opt, double** xyza_dev, float** srgba_dev);
+
+/* Issue all subsequent work of this context on the caller's CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the context's own stream).  ssb_render / ssb_clear / ssb_resolve_device are then
+ * asynchronous with respect to the host; entry points that return host data synchronise that stream. */
+int ssb_set_stream(ssb_ctx* ctx, void* cuda_stream);
+
 /* The whole seam in one call — what Renderer::render_start()+render_wait() do for a frame:
  * clear, render all samples, resolve, copy back. */
 int ssb_render_frame(ssb_ctx* ctx, const ssb_options* opt, double* xyza_host, float* srgba_host);

@@ -47,14 +47,16 @@ def lib():
     L.ssb_write_accum.argtypes = [C.c_void_p, P(C.c_double)]
     L.ssb_accum_device.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]
     L.ssb_resolve.argtypes = [C.c_void_p, P(_abi.ssb_options), P(C.c_double), P(C.c_float)]
+    L.ssb_resolve_device.argtypes = [C.c_void_p, P(_abi.ssb_options), P(C.c_void_p), P(C.c_void_p)]
+    L.ssb_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.ssb_render_frame.argtypes = [C.c_void_p, P(_abi.ssb_options), P(C.c_double), P(C.c_float)]
     L.ssb_get_stats.argtypes = [C.c_void_p, P(_abi.ssb_stats)]
     L.ssb_synchronize.argtypes = [C.c_void_p]
     L.ssb_debug_eval_math.argtypes = [C.c_void_p, C.c_uint32, P(C.c_float), C.c_float, P(C.c_float), C.c_size_t]
     L.ssb_debug_trace_samples.argtypes = [C.c_void_p, P(_abi.ssb_options), C.c_uint32, C.c_uint32, P(C.c_float)]
     for name in ("ssb_create", "ssb_upload_scene", "ssb_upload_color", "ssb_render", "ssb_clear", "ssb_read_accum",
-                 "ssb_write_accum", "ssb_accum_device", "ssb_resolve", "ssb_render_frame", "ssb_get_stats",
-                 "ssb_synchronize", "ssb_debug_eval_math", "ssb_debug_trace_samples"):
+                 "ssb_write_accum", "ssb_accum_device", "ssb_resolve", "ssb_resolve_device", "ssb_set_stream",
+                 "ssb_render_frame", "ssb_get_stats", "ssb_synchronize", "ssb_debug_eval_math", "ssb_debug_trace_samples"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -63,7 +65,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_last_error", "ssb_default_options", "ssb_create", "ssb_destroy", "ssb_upload_scene",
     "ssb_upload_color", "ssb_render", "ssb_clear", "ssb_read_accum", "ssb_write_accum", "ssb_accum_device",
-    "ssb_resolve", "ssb_render_frame", "ssb_get_stats", "ssb_synchronize", "ssb_debug_eval_math",
+    "ssb_resolve", "ssb_resolve_device", "ssb_set_stream", "ssb_render_frame", "ssb_get_stats", "ssb_synchronize", "ssb_debug_eval_math",
     "ssb_debug_trace_samples",
 )
 
@@ -135,6 +137,14 @@ class Context:
                                 xyza.ctypes.data_as(C.POINTER(C.c_double)) if want_xyza else None,
                                 srgba.ctypes.data_as(C.POINTER(C.c_float)) if want_srgba else None))
         return xyza, srgba
+
+    def resolve_device(self, opt):
+        x, s = C.c_void_p(), C.c_void_p()
+        check(lib().ssb_resolve_device(self._h, C.byref(opt), C.byref(x), C.byref(s)))
+        return x.value, s.value
+
+    def set_stream(self, cuda_stream):
+        check(lib().ssb_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
     def render_frame(self, opt, xyza=None, srgba=None, want_xyza=True, want_srgba=True):
         import numpy as np

@@ -1,0 +1,165 @@
+// ssb_host.hpp — host side of the drop-in: a C++ mirror of the reference's Scene / Material /
+// Color / Framebuffer / Renderer surface for the hot path (the reference is C++17, so the host
+// layer above the C ABI is C++ too).  It loads the same data/*.csv spectra, texture and tables
+// (cwd-relative "data/..." paths under a data root, as the reference does), builds the same
+// hard-coded scenes, flattens them to the POD structs of include/ssb200.h and drives the CUDA
+// path through the C ABI.  Init-time arithmetic (Color::init, camera matrices) follows the
+// reference operation by operation, in GLM 0.9.9 scalar semantics, so that the uploaded tables
+// are bit-identical to what the reference computes (checked against dumps of the real reference:
+// tests/test_host_layer.py).
+#pragma once
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/ssb200.h"
+
+namespace ssbh {
+
+// reference: `throw int` codes carried with a message
+struct Error {
+	int code;
+	std::string message;
+};
+
+// ---- _Spectrum (src/spectrum.hpp:12-70, spectrum.cpp:11-173)
+struct Spectrum {
+	std::vector<float> data;
+	float low = 0, high = 0;
+	float delta_lambda = 0, delta_lambda_recip = 0;
+	uint32_t filter = SSB_FILTER_LINEAR;
+
+	Spectrum() = default;
+	Spectrum(float value, float lambda_min, float lambda_max);  // constant over [LAMBDA_MIN,LAMBDA_MAX]
+	Spectrum(std::vector<float> const& data, float low, float high);
+
+	float sample_nearest(float lambda) const;
+	float sample_linear(float lambda) const;
+	Spectrum operator*(float sc) const;
+	static float integrate(Spectrum const& spec);
+	static float integrate(Spectrum const& spec0, Spectrum const& spec1);
+	ssb_spectrum flat() const;
+};
+
+std::vector<std::vector<float>> load_spectral_data(std::string const& csv_path);  // spectrum.cpp:177-213
+
+// ---- PNG texture (material.cpp:10-29; the reference decodes with lodepng, we with zlib)
+struct Texture {
+	uint32_t width = 0, height = 0;
+	std::vector<uint8_t> rgb8;  // scanlines top-to-bottom
+};
+Texture load_png_rgb8(std::string const& path);
+
+// ---- Color::data (src/util/color.hpp:22-69, color.cpp:72-155)
+struct ColorData {
+	int observer = 1931;       // CIE_OBSERVER
+	uint32_t upsampling = SSB_UPSAMPLE_OURS;
+	float lambda_min = 380, lambda_max = 780;
+	Spectrum std_obs_xbar, std_obs_ybar, std_obs_zbar;
+	Spectrum D65_orig, D65_rad;
+	float D65_orig_XYZ[3] = { 0, 0, 0 }, D65_rad_XYZ[3] = { 0, 0, 0 };
+	Spectrum basis_r, basis_g, basis_b;
+	float matr_lrgb_to_xyz[9] = { 0 }, matr_xyz_to_lrgb[9] = { 0 };  // column-major
+	// Jakob-Hanika model (rgb2spec.c:16-43)
+	uint32_t jh_res = 0;
+	std::vector<float> jh_scale, jh_data;
+	// Meng et al. tables (serialised by tools/gen_meng_tables.c)
+	ssb_meng_tables meng{};
+	std::vector<int32_t> meng_grid;
+	std::vector<float> meng_points;
+	bool have_meng = false;
+
+	ssb_color flat() const;  // pointers into this object
+};
+// Color::init(): observer 1931|2006, upsampling SSB_UPSAMPLE_*; data_root contains "data/"
+ColorData color_init(std::string const& data_root, int observer, uint32_t upsampling);
+
+// ---- materials / scene (src/material.hpp, scene.hpp, scene.cpp)
+struct Material {
+	std::string name;
+	uint32_t kind = SSB_MATERIAL_LAMBERT;
+	uint32_t albedo_mode = SSB_ALBEDO_CONSTANT;
+	Spectrum albedo;
+	int texture = -1;
+	Spectrum emission;
+	bool is_emissive() const;  // material.cpp:100-106
+};
+
+struct Camera {  // scene.hpp:16-33
+	float pos[3], dir[3], up[3];
+	uint32_t res[2];
+	float near_, far_, vfov_deg;
+	double matr_P[16], matr_V[16], matr_PV_inv[16];
+};
+
+struct Scene {
+	std::string name;
+	Camera camera{};
+	std::vector<Material> materials;  // first-use order over the primitive list
+	std::vector<Texture> textures;
+	std::vector<ssb_quad> quads;      // insertion order = tie-break / ignore identity
+	std::vector<uint32_t> lights;
+
+	// flat view (pointers into this object; rebuilt by flatten())
+	std::vector<ssb_material> flat_materials;
+	std::vector<ssb_texture> flat_textures;
+	ssb_scene flat{};
+	void flatten();
+};
+// Scene::get_new_cornell / get_new_cornell_srgb / get_new_plane_srgb (scene.cpp:32-415); unknown name -> Error{-3}
+Scene scene_new(std::string const& name, std::string const& data_root, ColorData const& color, bool explicit_light_sampling);
+
+// ---- Framebuffer (src/framebuffer.hpp:8-43, framebuffer.cpp)
+struct Framebuffer {
+	uint32_t res[2] = { 0, 0 };
+	std::vector<float> pixels;  // sRGBA float4, row 0 = bottom
+	void reset(uint32_t w, uint32_t h);  // checkerboard init (framebuffer.cpp:15-33)
+	void save(std::string const& path) const;  // .csv / .hdr / .pfm / else PNG (framebuffer.cpp:39-176)
+};
+
+// ---- Renderer (src/renderer.hpp:13-82): same Options, render_start/wait/stop/is_rendering
+struct RendererOptions {
+	std::string scene_name;
+	uint32_t res[2] = { 0, 0 };
+	uint32_t spp = 0;
+	bool indirect_only = false;
+	std::string output_path;
+	// the reference's compile-time configuration (stdafx.hpp:44-90), runtime here
+	int observer = 1931;
+	uint32_t upsampling = SSB_UPSAMPLE_OURS;
+	bool explicit_light_sampling = true;
+	uint32_t max_depth = 10;
+	bool flat_field_correction = true;
+	uint64_t seed = 1;
+	int device = 0;
+	std::string data_root = ".";
+};
+
+class Renderer {
+public:
+	RendererOptions const options;
+	Framebuffer framebuffer;
+	ColorData color;
+	Scene scene;
+	std::vector<double> xyza;  // per-pixel double XYZA (the reference's local `avg`, renderer.cpp:292-296)
+
+	explicit Renderer(RendererOptions const& options);
+	~Renderer();
+	Renderer(Renderer const&) = delete;
+	Renderer& operator=(Renderer const&) = delete;
+
+	void render_start();  // renders the frame on the GPU (the reference spawns worker threads here)
+	void render_stop() {}
+	void render_wait();   // saves the image like the reference's last worker thread (renderer.cpp:388-394)
+	bool is_rendering() const { return false; }
+	ssb_options make_options() const;
+	ssb_stats last_stats{};
+
+private:
+	ssb_ctx* ctx_ = nullptr;
+	bool rendered_ = false;
+};
+
+}  // namespace ssbh

@@ -69,8 +69,12 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct ssb_ctx {
 	int device = 0;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+	cudaStream_t stream = nullptr;      // the stream every kernel / copy of this context is issued on
+	cudaStream_t own_stream = nullptr;  // created by ssb_create; `stream` may be replaced by ssb_set_stream
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	std::vector<cudaEvent_t> ev_pass;   // (t0,t1) pairs around each trace-kernel launch of the last ssb_render
+	uint32_t passes = 0;
+	bool stats_pending = false;
 	int sm_count = 0;
 
 	// host copies of the uploaded tables
@@ -89,6 +93,8 @@ struct ssb_ctx {
 	// device
 	std::vector<uchar4*> d_textures;
 	std::vector<uint32_t> tex_w, tex_h;
+	unsigned char* d_rgb_staging = nullptr;
+	size_t rgb_staging_capacity = 0;
 	unsigned char* d_blob = nullptr;
 	size_t blob_bytes = 0, blob_capacity = 0;
 	float* d_jh_scale = nullptr;
@@ -109,7 +115,7 @@ struct ssb_ctx {
 
 namespace {
 
-void free_textures(ssb_ctx* c) {
+[[maybe_unused]] void free_textures(ssb_ctx* c) {
 	for (uchar4* p : c->d_textures) cudaFree(p);
 	c->d_textures.clear(); c->tex_w.clear(); c->tex_h.clear();
 }
@@ -250,9 +256,9 @@ int ssb_create(int device, ssb_ctx** out) {
 		delete c;
 		return fail(SSB_ERR_UNSUPPORTED, "ssb_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
 	}
-	SSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	SSB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	c->stream = c->own_stream;
 	SSB_CUDA(cudaEventCreate(&c->ev_begin)); SSB_CUDA(cudaEventCreate(&c->ev_end));
-	SSB_CUDA(cudaEventCreate(&c->ev_t0)); SSB_CUDA(cudaEventCreate(&c->ev_t1));
 	SSB_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
 	*out = c;
 	return SSB_OK;
@@ -265,11 +271,11 @@ void ssb_destroy(ssb_ctx* c) {
 	free_textures(c);
 	cudaFree(c->d_blob); cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points);
 	cudaFree(c->d_accum); cudaFree(c->d_samples); cudaFree(c->d_counter); cudaFree(c->d_xyza); cudaFree(c->d_srgba);
+	cudaFree(c->d_rgb_staging);
 	if (c->ev_begin) cudaEventDestroy(c->ev_begin);
 	if (c->ev_end) cudaEventDestroy(c->ev_end);
-	if (c->ev_t0) cudaEventDestroy(c->ev_t0);
-	if (c->ev_t1) cudaEventDestroy(c->ev_t1);
-	if (c->stream) cudaStreamDestroy(c->stream);
+	for (cudaEvent_t e : c->ev_pass) cudaEventDestroy(e);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 }
 
@@ -299,18 +305,29 @@ int ssb_upload_scene(ssb_ctx* c, const ssb_scene* scene) {
 	if (lights.size() > SSB_MAX_LIGHTS) return fail(SSB_ERR_UNSUPPORTED, "more than %u lights", SSB_MAX_LIGHTS);
 	// textures: RGB8 -> RGBA8 on the device
 	SSB_CUDA(cudaStreamSynchronize(c->stream));
-	free_textures(c);
+	std::vector<uchar4*> old_tex; old_tex.swap(c->d_textures);
+	std::vector<uint32_t> old_w; old_w.swap(c->tex_w);
+	std::vector<uint32_t> old_h; old_h.swap(c->tex_h);
 	for (uint32_t t = 0; t < scene->ntextures; ++t) {
 		const ssb_texture& tx = scene->textures[t];
 		if (!tx.rgb8 || tx.width == 0 || tx.height == 0) return fail(SSB_ERR_DATA, "texture %u: could not load texture", t);  // material.cpp:15-18
 		size_t n = (size_t)tx.width * tx.height;
-		std::vector<uchar4> rgba(n);
-		for (size_t i = 0; i < n; ++i) rgba[i] = make_uchar4(tx.rgb8[3 * i], tx.rgb8[3 * i + 1], tx.rgb8[3 * i + 2], 255);
 		uchar4* d = nullptr;
-		SSB_CUDA(cudaMalloc(&d, n * sizeof(uchar4)));
+		if (t < old_tex.size() && old_w[t] == tx.width && old_h[t] == tx.height) { d = old_tex[t]; old_tex[t] = nullptr; }
+		else SSB_CUDA(cudaMalloc(&d, n * sizeof(uchar4)));
 		c->d_textures.push_back(d); c->tex_w.push_back(tx.width); c->tex_h.push_back(tx.height);
-		SSB_CUDA(cudaMemcpy(d, rgba.data(), n * sizeof(uchar4), cudaMemcpyHostToDevice));
+		if (3 * n > c->rgb_staging_capacity) {
+			cudaFree(c->d_rgb_staging); c->d_rgb_staging = nullptr; c->rgb_staging_capacity = 0;
+			SSB_CUDA(cudaMalloc(&c->d_rgb_staging, 3 * n));
+			c->rgb_staging_capacity = 3 * n;
+		}
+		// one H2D copy of the caller's RGB8 scanlines (fast when the caller's buffer is pinned), repack on the device
+		SSB_CUDA(cudaMemcpyAsync(c->d_rgb_staging, tx.rgb8, 3 * n, cudaMemcpyHostToDevice, c->stream));
+		ssb_repack_rgb8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_rgb_staging, d, n);
+		SSB_CUDA(cudaGetLastError());
 	}
+	for (uchar4* p : old_tex) if (p) cudaFree(p);
+	SSB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's host buffers may be released after return
 	c->camera = scene->camera;
 	c->quads.assign(scene->quads, scene->quads + scene->nquads);
 	c->materials.swap(mats);
@@ -385,7 +402,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	const uint32_t rect_w = x1 - o->x0, rect_h = y1 - o->y0;
 	const size_t npix_rect = (size_t)rect_w * rect_h;
 	const uint32_t nsamp_total = s1 - o->sample_begin;
-	c->stats = ssb_stats{};
+	c->stats = ssb_stats{}; c->stats_pending = false; c->passes = 0;
 	if (npix_rect == 0 || nsamp_total == 0) return SSB_OK;
 	if (npix_rect > kSampleBudget) return fail(SSB_ERR_UNSUPPORTED, "pixel rectangle too large for one pass");
 	uint32_t chunk = (uint32_t)std::min<size_t>(nsamp_total, std::max<size_t>(1, kSampleBudget / npix_rect));
@@ -423,8 +440,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	if (blocks_per_sm < 1) return fail(SSB_ERR_UNSUPPORTED, "trace kernel does not fit on an SM with %zu bytes of tables", smem);
 
 	SSB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
-	double trace_ms = 0.0;
-	uint32_t launches = 0;
+	uint32_t launches = 0, passes = 0;
 	for (uint32_t k0 = 0; k0 < nsamp_total; k0 += chunk) {
 		uint32_t ns = std::min(chunk, nsamp_total - k0);
 		P.sample_begin = o->sample_begin + k0;
@@ -434,28 +450,22 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 		// persistent grid: SMs x resident CTAs, never more CTAs than there is work for
 		unsigned long long want = (P.total_work + SSB_TRACE_THREADS - 1) / SSB_TRACE_THREADS;
 		unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * blocks_per_sm, want);
-		SSB_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+		while (c->ev_pass.size() < 2 * (size_t)(passes + 1)) { cudaEvent_t e; SSB_CUDA(cudaEventCreate(&e)); c->ev_pass.push_back(e); }
+		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes], c->stream));
 		ssb_trace_kernel<<<grid, SSB_TRACE_THREADS, smem, c->stream>>>(P);
 		SSB_CUDA(cudaGetLastError());
-		SSB_CUDA(cudaEventRecord(c->ev_t1, c->stream));
+		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes + 1], c->stream));
 		unsigned agrid = (unsigned)((npix_rect + 127) / 128);
 		ssb_accumulate_kernel<<<agrid, 128, 0, c->stream>>>(c->d_samples, c->d_accum, o->width, o->x0, o->y0, rect_w, rect_h, ns);
 		SSB_CUDA(cudaGetLastError());
-		launches += 2;
-		if (nsamp_total > chunk) {  // multi-pass: collect per-pass trace time (single pass is read after the end event)
-			SSB_CUDA(cudaEventSynchronize(c->ev_t1));
-			float ms = 0; SSB_CUDA(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1)); trace_ms += ms;
-		}
+		launches += 2; passes += 1;
 	}
 	SSB_CUDA(cudaEventRecord(c->ev_end, c->stream));
-	SSB_CUDA(cudaEventSynchronize(c->ev_end));
-	float ms = 0;
-	SSB_CUDA(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
-	if (nsamp_total <= chunk) { float t = 0; SSB_CUDA(cudaEventElapsedTime(&t, c->ev_t0, c->ev_t1)); trace_ms = t; }
+	// asynchronous: the event times are read lazily by ssb_get_stats()
 	c->stats.samples = (uint64_t)npix_rect * nsamp_total;
-	c->stats.device_ms = ms;
-	c->stats.trace_ms = trace_ms;
 	c->stats.launches = launches;
+	c->passes = passes;
+	c->stats_pending = true;
 	return SSB_OK;
 }
 
@@ -485,7 +495,27 @@ int ssb_accum_device(ssb_ctx* c, double** dptr, size_t* count) {
 	return SSB_OK;
 }
 
+static int resolve_impl(ssb_ctx* c, const ssb_options* o, double* xyza_host, float* srgba_host, bool device_only);
+
 int ssb_resolve(ssb_ctx* c, const ssb_options* o, double* xyza_host, float* srgba_host) {
+	return resolve_impl(c, o, xyza_host, srgba_host, false);
+}
+int ssb_resolve_device(ssb_ctx* c, const ssb_options* o, double** xyza_dev, float** srgba_dev) {
+	int rc = resolve_impl(c, o, nullptr, nullptr, true);
+	if (rc != SSB_OK) return rc;
+	if (xyza_dev) *xyza_dev = c->d_xyza;
+	if (srgba_dev) *srgba_dev = reinterpret_cast<float*>(c->d_srgba);
+	return SSB_OK;
+}
+int ssb_set_stream(ssb_ctx* c, void* cuda_stream) {
+	if (!c) return fail(SSB_ERR_ARG, "ssb_set_stream: NULL context");
+	SSB_CUDA(cudaSetDevice(c->device));
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+	return SSB_OK;
+}
+
+static int resolve_impl(ssb_ctx* c, const ssb_options* o, double* xyza_host, float* srgba_host, bool device_only) {
 	if (!c || !o) return fail(SSB_ERR_ARG, "ssb_resolve: NULL argument");
 	if (!c->d_accum || c->accum_w != o->width || c->accum_h != o->height) return fail(SSB_ERR_ARG, "ssb_resolve: no accumulator for this resolution");
 	if (o->spp == 0) return fail(SSB_ERR_ARG, "ssb_resolve: spp must be positive");
@@ -500,11 +530,12 @@ int ssb_resolve(ssb_ctx* c, const ssb_options* o, double* xyza_host, float* srgb
 	const float* m = c->xyz_to_lrgb;
 	double scale = 1000.0 / (double)o->spp;  // renderer.cpp:296
 	unsigned grid = (unsigned)((npix + 127) / 128);
-	ssb_resolve_kernel<<<grid, 128, 0, c->stream>>>(c->d_accum, xyza_host ? c->d_xyza : nullptr, srgba_host ? c->d_srgba : nullptr,
+	ssb_resolve_kernel<<<grid, 128, 0, c->stream>>>(c->d_accum, (device_only || xyza_host) ? c->d_xyza : nullptr, (device_only || srgba_host) ? c->d_srgba : nullptr,
 	                                                (uint32_t)npix, scale, o->upsampling, c->d65_rad_Y,
 	                                                m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
 	SSB_CUDA(cudaGetLastError());
 	c->stats.launches += 1;
+	if (device_only) return SSB_OK;
 	if (xyza_host) SSB_CUDA(cudaMemcpyAsync(xyza_host, c->d_xyza, npix * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if (srgba_host) SSB_CUDA(cudaMemcpyAsync(srgba_host, c->d_srgba, npix * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
 	SSB_CUDA(cudaStreamSynchronize(c->stream));
@@ -517,15 +548,22 @@ int ssb_render_frame(ssb_ctx* c, const ssb_options* o, double* xyza_host, float*
 	full.sample_begin = 0; full.sample_end = 0;
 	int rc = ssb_render(c, &full);
 	if (rc != SSB_OK) return rc;
-	ssb_stats st = c->stats;
-	rc = ssb_resolve(c, &full, xyza_host, srgba_host);
-	st.launches += 1;
-	c->stats = st;
-	return rc;
+	return ssb_resolve(c, &full, xyza_host, srgba_host);
 }
 
 int ssb_get_stats(ssb_ctx* c, ssb_stats* out) {
 	if (!c || !out) return fail(SSB_ERR_ARG, "ssb_get_stats: NULL argument");
+	if (c->stats_pending) {
+		SSB_CUDA(cudaSetDevice(c->device));
+		SSB_CUDA(cudaEventSynchronize(c->ev_end));
+		float ms = 0;
+		SSB_CUDA(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
+		c->stats.device_ms = ms;
+		double trace = 0;
+		for (uint32_t p = 0; p < c->passes; ++p) { float t = 0; SSB_CUDA(cudaEventElapsedTime(&t, c->ev_pass[2 * p], c->ev_pass[2 * p + 1])); trace += t; }
+		c->stats.trace_ms = trace;
+		c->stats_pending = false;
+	}
 	*out = c->stats;
 	return SSB_OK;
 }
@@ -569,6 +607,7 @@ int ssb_debug_trace_samples(ssb_ctx* c, const ssb_options* o, uint32_t px, uint3
 	if (rc != SSB_OK) return rc;
 	uint32_t ns = s1 - begin;
 	if ((size_t)ns > kSampleBudget) return fail(SSB_ERR_UNSUPPORTED, "too many samples");
+	SSB_CUDA(cudaStreamSynchronize(c->stream));
 	SSB_CUDA(cudaMemcpy(out_host, c->d_samples, (size_t)ns * sizeof(float4), cudaMemcpyDeviceToHost));
 	if (had) rc = ssb_write_accum(c, saved.data());
 	return rc;

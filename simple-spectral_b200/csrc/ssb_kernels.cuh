@@ -821,6 +821,14 @@ __global__ void ssb_resolve_kernel(const double* __restrict__ accum, double* __r
 	}
 }
 
+// sRGB_ReflectanceTexture keeps RGB8 scanlines (material.hpp:20-21); the device copy is RGBA8 so that a texel is
+// one aligned 32-bit load
+__global__ void ssb_repack_rgb8_kernel(const unsigned char* __restrict__ rgb, uchar4* __restrict__ rgba, size_t n) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	rgba[i] = make_uchar4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 255);
+}
+
 __global__ void ssb_eval_math_kernel(uint32_t fn, const float* __restrict__ x, float arg, float* __restrict__ out, size_t n) {
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
