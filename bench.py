@@ -1,0 +1,362 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark: Mpath-samples/s of the spectral path-tracing hot path.
+
+A "step" = one frame of BASELINE.json configs[1]: cornell-srgb 512x512, spp 64, hero-wavelength (4 λ),
+RENDER_MODE_SPECTRAL_OURS, CIE 1931, explicit light sampling, MAX_DEPTH 10, per-sample seeding.
+  value : whole-job samples / time with scene, tables and texture already resident in HBM
+          (trace kernel + in-order f64 accumulation + resolve to XYZA/sRGBA, results left on the device)
+  e2e   : the same metric through the reference-facing C-ABI calls with HOST buffers — every step uploads
+          the scene (incl. the 48 MiB RGB8 texture) and colour tables from pinned host memory and reads the
+          XYZA + sRGBA framebuffers back (ssb_upload_scene + ssb_upload_color + ssb_render_frame)
+Multi-GPU (torchrun, one rank per GPU): weak scaling — every rank renders its own 64 samples per pixel of the
+same 512x512 frame (sample indices r*64..r*64+63), then ONE NCCL reduce(sum) of the f64 XYZA accumulators to
+rank 0, which resolves the spp = 64*N image.
+`--impl reference` times the reference's own multithreaded CPU renderer (oracle/_ref, built from /root/reference
+by oracle/build_ref.py) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpath-samples/s"
+SCENE, VARIANT = "cornell-srgb", "ours1931"
+# SURVEY.md §8(d) algorithmic HBM bytes per path sample (wavefront model the north star names):
+# 5.30 closest-hit stages x 192 B ray state read+write + 47 B texture sectors + 32 B f64 XYZA output
+ALGO_BYTES_PER_SAMPLE = {"cornell-srgb": 5.30 * 192 + 47 + 32, "cornell": 5.30 * 192 + 32, "plane-srgb": 2.0 * 192 + 64 + 32}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def data_root():
+    host = importlib.import_module("simple-spectral_b200.host")
+    return host.find_data_root()
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def ref_binary(variant=VARIANT):
+    p = os.path.join(ROOT, "oracle", "_ref", f"simple_spectral_{variant}")
+    if not os.path.exists(p):
+        raise SystemExit(f"{p} missing: run __graft_entry__.build() where /root/reference exists")
+    return p
+
+
+def run_reference_once(width, height, spp, threads=None, variant=VARIANT, scene=SCENE):
+    """Runs the UNMODIFIED reference renderer; returns its own 'Render completed in' time (excludes load)."""
+    env = dict(os.environ)
+    out = f"/tmp/ssb_ref_bench_{os.getpid()}.pfm"
+    r = subprocess.run([ref_binary(variant), f"--scene={scene}", f"-w={width}", f"-h={height}", f"-spp={spp}", f"--output={out}"],
+                       cwd=data_root(), env=env, capture_output=True, text=True)
+    try:
+        os.remove(out)
+    except OSError:
+        pass
+    m = re.findall(r"Render completed in (?:(\d+) days \+ )?(\d+):(\d+):([0-9.]+)", r.stdout)
+    if r.returncode != 0 or not m:
+        raise SystemExit("reference run failed: " + r.stderr[-500:])
+    d, h, mi, s = m[-1]
+    return (int(d or 0) * 86400) + int(h) * 3600 + int(mi) * 60 + float(s)
+
+
+def cpu_baseline(width, height, sample_spp):
+    cores = os.cpu_count() or 1
+    secs = run_reference_once(width, height, sample_spp)
+    n = width * height * sample_spp
+    return {"value": n / secs / 1e6, "unit": METRIC, "cores": cores, "kind": "reference",
+            "sample": f"{SCENE} {width}x{height} spp{sample_spp} ({n} samples, {secs:.2f} s by the reference's own timer; "
+                      f"unmodified reference sources, g++ -O3 -march=x86-64-v3, std::thread::hardware_concurrency()={cores} threads)"}
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    spp = args.ref_spp
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = run_reference_once(args.width, args.height, spp)
+        if i >= args.warmup:
+            times.append(t)
+    total = sum(times)
+    n = args.width * args.height * spp
+    value = n * len(times) / total / 1e6
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "reference scene (hard-coded geometry + shipped spectra/texture)",
+        "config": {"workload": f"{SCENE} {args.width}x{args.height} hero-wavelength OURS CIE1931; each step = one frame at spp{spp} "
+                               f"(bounded sample of the spp{args.spp} workload)", "timer": "reference's own 'Render completed in' (excludes scene load)"},
+        "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "reference",
+                         "sample": f"{args.steps} frames of {SCENE} {args.width}x{args.height} spp{spp}, {cores} threads"},
+        "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def main_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    ssb = importlib.import_module("simple-spectral_b200")
+    host = importlib.import_module("simple-spectral_b200.host")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    W, H, SPP = args.width, args.height, args.spp
+    color = host.Color(None, *host.VARIANTS[VARIANT])
+    scene = host.Scene(SCENE, color)
+    ctx = ssb.Context(local_rank)
+    ctx.upload_color(color.flat)
+    ctx.upload_scene(scene.flat)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    total_spp = SPP * world  # weak scaling: the job is the same frame at spp 64*N
+    opt = host.options_for(color, W, H, total_spp, seed=1, sample_begin=rank * SPP, sample_end=(rank + 1) * SPP)
+    npix = W * H
+
+    def device_accum_tensor():
+        ptr, count = ctx.accum_device()
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Arr(), device=f"cuda:{local_rank}")
+
+    def step_device():
+        ctx.clear()
+        ctx.render(opt)                     # trace + in-order accumulate, async on the torch stream
+        if world > 1:
+            dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)  # the single exchange step: f64 XYZA accumulators
+        if rank == 0:
+            ctx.resolve_device(opt)         # XYZA (f64) + sRGBA (f32) framebuffers, left on the device
+
+    # warm-up (also allocates the accumulator so that it can be wrapped as a tensor)
+    ctx.clear(); ctx.render(opt); ctx.synchronize()
+    accum_t = device_accum_tensor() if world > 1 else None
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    trace_ms, launches = 0.0, 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    # per-launch duration of the dominant kernel, CUDA events on the launching stream (one more, separately timed step)
+    trace_list = []
+    for _ in range(3):
+        ctx.clear(); ctx.render(opt)
+        st = ctx.stats()
+        trace_list.append(st.trace_ms)
+        launches_per_render = st.launches
+    trace_ms = sum(trace_list) / len(trace_list)
+    launches = (launches_per_render + (1 if rank == 0 else 0)) * args.steps
+
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    dev_ms, wall_ms = t.tolist()
+    samples_per_step = npix * SPP * world
+    value = samples_per_step * args.steps / (dev_ms * 1e-3) / 1e6
+
+    # ---------------- e2e: host buffers in, host buffers out, every step
+    tex_np = host.load_png_rgb8(os.path.join(color.data_root, "data", "scenes", "crystal-lizard-4096.png"))
+    pinned_tex = torch.empty(tex_np.shape, dtype=torch.uint8, pin_memory=True)
+    pinned_tex.numpy()[...] = tex_np
+    flat_scene = scene.flat
+    tex_desc = (ssb.ssb_texture * 1)()
+    tex_desc[0].rgb8 = C.cast(pinned_tex.data_ptr(), C.POINTER(C.c_uint8))
+    tex_desc[0].width, tex_desc[0].height = tex_np.shape[1], tex_np.shape[0]
+    e2e_scene = ssb.ssb_scene()
+    C.memmove(C.byref(e2e_scene), C.byref(flat_scene), C.sizeof(e2e_scene))
+    e2e_scene.textures = tex_desc
+    xyza_host = torch.empty((H, W, 4), dtype=torch.float64, pin_memory=True)
+    srgba_host = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
+    xyza_np, srgba_np = xyza_host.numpy(), srgba_host.numpy()
+    accum_host = torch.empty(npix * 4, dtype=torch.float64, pin_memory=True) if world > 1 else None
+    h2d = tex_np.nbytes + 16 * 1024  # texture + (scene blob + colour tables, < 16 KiB)
+    d2h = xyza_np.nbytes + srgba_np.nbytes
+
+    def step_e2e():
+        ctx.upload_color(color.flat)
+        ctx.upload_scene(e2e_scene)
+        if world == 1:
+            ctx.render_frame(opt, xyza=xyza_np, srgba=srgba_np)
+        else:
+            ctx.clear(); ctx.render(opt)
+            dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                ctx.resolve(opt, xyza=xyza_np, srgba=srgba_np)
+            else:
+                ctx.synchronize()
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e2e_steps = max(3, args.steps // 2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    tw = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_wall = (time.perf_counter() - tw) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall)  # host-side work (blob packing) is part of the call: use the larger
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item()
+    e2e_value = samples_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        algo_bytes = ALGO_BYTES_PER_SAMPLE[SCENE] * npix * SPP  # per trace-kernel launch (one rank's launch)
+        achieved = algo_bytes / (trace_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "reference scene (hard-coded cornell-srgb geometry, shipped spectra + 4096^2 sRGB texture); per-sample seeded RNG",
+            "config": {"workload": f"{SCENE} {W}x{H} spp{SPP} per GPU (job spp {total_spp}), hero-wavelength x4, OURS upsampling, CIE1931, "
+                                   f"ELS on, MAX_DEPTH 10", "parallelism": f"sample-sharded x{world}, one NCCL reduce of f64 XYZA" if world > 1 else "single GPU",
+                       "l2": "no flush needed: each step rewrites a 268 MB sample buffer (> 126 MB L2) and re-reads it",
+                       "timing": "CUDA events on the launching stream around K steps, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "calls": "ssb_upload_color + ssb_upload_scene (pinned RGB8 texture) + ssb_render_frame -> pinned XYZA f64 + sRGBA f32"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "ssb_trace_kernel", "kernel_ms": trace_ms,
+                         "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE[SCENE],
+                         "note": "HBM-model bytes of SURVEY.md §8(d) (wavefront ray-state traffic); the kernel keeps path state in registers, "
+                                 "so its real bound is fp32 issue — see DESIGN.md"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(W, H, args.cpu_spp)
+            except SystemExit as e:
+                line["cpu_baseline"] = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--height", type=int, default=512)
+    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded CPU-baseline sample")
+    ap.add_argument("--ref-spp", type=int, default=4, help="spp per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return main_reference(args, rank, world)
+    return main_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

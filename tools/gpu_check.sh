@@ -1,0 +1,19 @@
+#!/bin/bash
+# Run on the GPU box (via gpurun): GPU tests, bench, launch list and one full ncu capture of the trace kernel.
+# Usage: tools/gpu_check.sh <tag>       outputs -> gpurun_out/<tag>_*
+set -u
+TAG=${1:-run}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.txt 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest.txt
+tail -5 $OUT/${TAG}_pytest.txt
+timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
+if [ "${2:-}" != "noprof" ]; then
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/${TAG}_launches.csv \
+   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1; echo "ncu launches rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ssb_trace -s 2 -c 1 -f -o $OUT/${TAG}_trace \
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+ls -la $OUT | tail -12
+fi
