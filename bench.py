@@ -177,7 +177,11 @@ def main_ours(args, rank, local_rank, world):
     ctx = ssb.Context(local_rank)
     ctx.upload_color(color.flat)
     ctx.upload_scene(scene.flat)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the context issues every kernel/copy on it, and the timing events below are
+    # recorded on the same stream (handle 0 = "legacy default stream" would mean "use the context's own stream")
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     total_spp = SPP * world  # weak scaling: the job is the same frame at spp 64*N

@@ -5,6 +5,7 @@
 // computes fails with SSB_ERR_DATA when CUDA is unavailable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -170,6 +171,7 @@ int build_blob(ssb_ctx* c) {
 	hdr.off_lights = (uint32_t)off; off = align_up(off + c->lights.size() * sizeof(uint32_t), 16);
 	hdr.off_textures = (uint32_t)off; off = align_up(off + texs.size() * sizeof(DevTexture), 16);
 	hdr.off_pool = (uint32_t)off; off = align_up(off + pool.size() * sizeof(float), 16);
+	hdr.off_boxes = (uint32_t)off; off = align_up(off + c->quads.size() * 8 * sizeof(float), 16);
 	hdr.total_bytes = (uint32_t)off;
 	if (off > 160 * 1024) return fail(SSB_ERR_UNSUPPORTED, "scene tables (%zu bytes) exceed the shared-memory budget", off);
 
@@ -180,6 +182,25 @@ int build_blob(ssb_ctx* c) {
 	if (!c->lights.empty()) memcpy(blob.data() + hdr.off_lights, c->lights.data(), c->lights.size() * sizeof(uint32_t));
 	if (!texs.empty()) memcpy(blob.data() + hdr.off_textures, texs.data(), texs.size() * sizeof(DevTexture));
 	if (!pool.empty()) memcpy(blob.data() + hdr.off_pool, pool.data(), pool.size() * sizeof(float));
+	{
+		// conservative per-quad bounds for the culling phase of scene_intersect: the exact AABB of the quad's
+		// vertices expanded by 1e-4 of the scene diagonal (>> the rounding of the watertight test)
+		float slo[3] = { INFINITY, INFINITY, INFINITY }, shi[3] = { -INFINITY, -INFINITY, -INFINITY };
+		for (const ssb_quad& q : c->quads)
+			for (int t = 0; t < 2; ++t) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) {
+				slo[k] = std::min(slo[k], q.tri[t].v[v].pos[k]); shi[k] = std::max(shi[k], q.tri[t].v[v].pos[k]);
+			}
+		double diag = std::sqrt((double)(shi[0] - slo[0]) * (shi[0] - slo[0]) + (double)(shi[1] - slo[1]) * (shi[1] - slo[1]) + (double)(shi[2] - slo[2]) * (shi[2] - slo[2]));
+		float margin = (float)(1e-4 * diag) + 1e-6f;
+		float* boxes = reinterpret_cast<float*>(blob.data() + hdr.off_boxes);
+		for (size_t qi = 0; qi < c->quads.size(); ++qi) {
+			float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+			for (int t = 0; t < 2; ++t) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) {
+				lo[k] = std::min(lo[k], c->quads[qi].tri[t].v[v].pos[k]); hi[k] = std::max(hi[k], c->quads[qi].tri[t].v[v].pos[k]);
+			}
+			for (int k = 0; k < 3; ++k) { boxes[8 * qi + k] = lo[k] - margin; boxes[8 * qi + 4 + k] = hi[k] + margin; }
+		}
+	}
 
 	if (off > c->blob_capacity) {
 		if (c->d_blob) cudaFree(c->d_blob);

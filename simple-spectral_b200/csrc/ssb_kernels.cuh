@@ -51,7 +51,8 @@ struct DevHeader {
 	uint32_t nquads, nmaterials, nlights, ntextures;
 	uint32_t off_quads, off_materials, off_lights, off_textures, off_pool;  // byte offsets from blob start
 	uint32_t total_bytes;  // multiple of 16
-	uint32_t pad[2];
+	uint32_t off_boxes;    // per quad: float lo[3], pad, hi[3], pad — conservative (expanded) bounds for culling
+	uint32_t pad;
 	DevSpectrum xbar, ybar, zbar, basis_r, basis_g, basis_b;
 	float srgb_lut[256];  // Color::srgb_to_lrgb(v/255) for v = 0..255 (color.hpp:91-97), built with the host libm
 };
@@ -131,6 +132,12 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 	return z ^ (z >> 31);
 }
 
+// Single, non-inlined copies of the exact libm restatements: the trace kernel calls them from ~20 sites and its
+// instruction footprint must stay inside the instruction cache (ncu: `stalled_no_instruction` dominated v1).
+__device__ __noinline__ float acosf_x(float x) { return ssbm::acosf_exact(x); }
+__device__ __noinline__ float sinf_x(float x) { return ssbm::sinf_exact(x); }
+__device__ __noinline__ float cosf_x(float x) { return ssbm::cosf_exact(x); }
+
 // ------------------------------------------------------------------ shared-memory view of the blob
 struct SceneView {
 	const DevHeader* hdr;
@@ -139,6 +146,7 @@ struct SceneView {
 	const uint32_t* lights;
 	const DevTexture* textures;
 	const float* pool;
+	const float4* boxes;  // 2 x float4 per quad
 };
 
 // _Spectrum::_sample_linear / _sample_nearest (spectrum.cpp:29-60)
@@ -158,10 +166,19 @@ __device__ __forceinline__ float spec_sample(const float* pool, const DevSpectru
 	return val0 * (1.0f - frac) + val1 * frac;
 }
 // _Spectrum::operator[] (spectrum.cpp:61-67)
+__device__ __noinline__ float4 spec_hero4(const float* pool, const DevSpectrum* sp, float lambda_0, float step) {
+	const DevSpectrum s = *sp;
+	float4 h;
+	h.x = spec_sample(pool, s, lambda_0 + 0.0f * step);
+	h.y = spec_sample(pool, s, lambda_0 + 1.0f * step);
+	h.z = spec_sample(pool, s, lambda_0 + 2.0f * step);
+	h.w = spec_sample(pool, s, lambda_0 + 3.0f * step);
+	return h;
+}
 __device__ __forceinline__ Hero spec_hero(const float* pool, const DevSpectrum& s, float lambda_0, float step) {
+	float4 v = spec_hero4(pool, &s, lambda_0, step);
 	Hero h;
-#pragma unroll
-	for (int i = 0; i < 4; ++i) h.v[i] = spec_sample(pool, s, lambda_0 + (float)i * step);
+	h.v[0] = v.x; h.v[1] = v.y; h.v[2] = v.z; h.v[3] = v.w;
 	return h;
 }
 
@@ -363,17 +380,67 @@ __device__ __forceinline__ bool tri_intersect(const ssb_tri& t, const RayConst& 
 	return false;
 }
 
-// Scene::intersect (scene.cpp:433-445) + PrimQuad::intersect (geometry.cpp:128-139)
-__device__ __forceinline__ void scene_intersect(const SceneView& S, const RayConst& rc, float eps, int ignore, Hit& hit) {
+// Scene::intersect (scene.cpp:433-445) + PrimQuad::intersect (geometry.cpp:128-139).
+//
+// The reference scans every primitive with the full watertight test.  Here the scan is split in two
+// phases that give the SAME hit record:
+//   1. a slab test of the ray against each quad's bounding box — expanded by 1e-4 of the scene diagonal,
+//      orders of magnitude more than the watertight test's own rounding, so it can only reject quads the
+//      exact test would reject — run converged by all lanes (box data is a shared-memory broadcast),
+//      producing a per-lane bit mask of candidate quads;
+//   2. the exact test (tri0, then tri1) only for the lane's candidates, in list order (lowest bit first), so
+//      ties and the `ignore` rule resolve exactly as in the reference.  Lanes iterate over their own
+//      candidates in lock-step: the trip count is the max candidate count in the warp (~2-4), not 2x19.
+// The culling arithmetic (explicit fma, approximate reciprocals) is not part of the reference's arithmetic
+// and never touches the hit record.
+#ifndef SSB_CULL
+#define SSB_CULL 1
+#endif
+__device__ __forceinline__ void scene_intersect(const SceneView& S, const RayConst& rc, float eps, int ignore, Hit& hit,
+                                                float ox, float oy, float oz, float dx, float dy, float dz) {
 	hit.quad = -1; hit.tri = 0; hit.dist = __int_as_float(0x7f800000);
 	hit.bx = hit.by = hit.bz = 0.0f;
 	const int nq = (int)S.hdr->nquads;
+#if SSB_CULL
+	// per-ray reciprocal direction, clamped so that axis-parallel rays give finite slab distances
+	float ix = (fabsf(dx) < 1e-30f) ? copysignf(1e30f, dx) : __frcp_rn(dx);
+	float iy = (fabsf(dy) < 1e-30f) ? copysignf(1e30f, dy) : __frcp_rn(dy);
+	float iz = (fabsf(dz) < 1e-30f) ? copysignf(1e30f, dz) : __frcp_rn(dz);
+	float bx = -ox * ix, by = -oy * iy, bz = -oz * iz;
+	for (int base = 0; base < nq; base += 32) {
+		const int cnt = min(32, nq - base);
+		unsigned cand = 0u;
+		for (int j = 0; j < cnt; ++j) {
+			const float4 lo = S.boxes[2 * (base + j)], hi = S.boxes[2 * (base + j) + 1];
+			float t0x = __fmaf_rn(lo.x, ix, bx), t1x = __fmaf_rn(hi.x, ix, bx);
+			float t0y = __fmaf_rn(lo.y, iy, by), t1y = __fmaf_rn(hi.y, iy, by);
+			float t0z = __fmaf_rn(lo.z, iz, bz), t1z = __fmaf_rn(hi.z, iz, bz);
+			float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+			float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+			// keep unless the ray provably misses the expanded box or the box lies entirely behind the origin;
+			// any NaN (0*inf cannot occur with the clamp, but be safe) keeps the quad
+			bool miss = (tmin > tmax) || (tmax < 0.0f);
+			cand |= miss ? 0u : (1u << j);
+		}
+		if (ignore >= base && ignore < base + 32) cand &= ~(1u << (ignore - base));
+		while (cand) {
+			const int q = base + (__ffs(cand) - 1);
+			cand &= cand - 1u;
+			const ssb_quad& quad = S.quads[q];
+#pragma unroll 1
+			for (int tt = 0; tt < 2; ++tt) {  // tri0, then tri1 only if tri0 missed (geometry.cpp:131-133)
+				if (tri_intersect(quad.tri[tt], rc, eps, hit)) { hit.quad = q; hit.tri = tt; break; }
+			}
+		}
+	}
+#else
 	for (int q = 0; q < nq; ++q) {
 		if (q == ignore) continue;
 		const ssb_quad& quad = S.quads[q];
 		if (tri_intersect(quad.tri[0], rc, eps, hit)) { hit.quad = q; hit.tri = 0; }
 		else if (tri_intersect(quad.tri[1], rc, eps, hit)) { hit.quad = q; hit.tri = 1; }
 	}
+#endif
 }
 
 // ------------------------------------------------------------------ light sampling
@@ -404,10 +471,10 @@ __device__ __noinline__ void sample_spherical_triangle(const ssb_tri& t, float p
 	float cos_a = glm_clamp(dot3(Bx, By, Bz, Cx, Cy, Cz), -1.0f, 1.0f);
 	float cos_b = glm_clamp(dot3(Ax, Ay, Az, Cx, Cy, Cz), -1.0f, 1.0f);
 	float cos_c = glm_clamp(dot3(Ax, Ay, Az, Bx, By, Bz), -1.0f, 1.0f);
-	float a = glm_clamp(ssbm::acosf_exact(cos_a), 0.0f, underestimate_pi());
-	float b = glm_clamp(ssbm::acosf_exact(cos_b), 0.0f, underestimate_pi());
-	float c = glm_clamp(ssbm::acosf_exact(cos_c), 0.0f, underestimate_pi());
-	float sin_a = ssbm::sinf_exact(a), sin_b = ssbm::sinf_exact(b), sin_c = ssbm::sinf_exact(c);
+	float a = glm_clamp(acosf_x(cos_a), 0.0f, underestimate_pi());
+	float b = glm_clamp(acosf_x(cos_b), 0.0f, underestimate_pi());
+	float c = glm_clamp(acosf_x(cos_c), 0.0f, underestimate_pi());
+	float sin_a = sinf_x(a), sin_b = sinf_x(b), sin_c = sinf_x(c);
 	float numer0 = cos_a - cos_b * cos_c;
 	float numer1 = cos_b - cos_c * cos_a;
 	float numer2 = cos_c - cos_a * cos_b;
@@ -418,9 +485,9 @@ __device__ __noinline__ void sample_spherical_triangle(const ssb_tri& t, float p
 		cos_alpha = glm_clamp(numer0 / denom0, -1.0f, 1.0f);
 		float cos_beta = glm_clamp(numer1 / denom1, -1.0f, 1.0f);
 		float cos_gamma = glm_clamp(numer2 / denom2, -1.0f, 1.0f);
-		alpha = glm_clamp(ssbm::acosf_exact(cos_alpha), 0.0f, underestimate_pi());
-		float beta = glm_clamp(ssbm::acosf_exact(cos_beta), 0.0f, underestimate_pi());
-		float gamma = glm_clamp(ssbm::acosf_exact(cos_gamma), 0.0f, underestimate_pi());
+		alpha = glm_clamp(acosf_x(cos_alpha), 0.0f, underestimate_pi());
+		float beta = glm_clamp(acosf_x(cos_beta), 0.0f, underestimate_pi());
+		float gamma = glm_clamp(acosf_x(cos_gamma), 0.0f, underestimate_pi());
 		surface_area = ((alpha + beta) + gamma) - SSB_PI_F;
 		if (!(surface_area >= 0)) surface_area = 0;
 	} else {
@@ -435,19 +502,19 @@ __device__ __noinline__ void sample_spherical_triangle(const ssb_tri& t, float p
 				else { alpha = cos_alpha = nan; }
 			}
 		} else {
-			if (sin_b > 0 && sin_c > 0) { cos_alpha = glm_clamp(numer0 / denom0, -1.0f, 1.0f); alpha = ssbm::acosf_exact(cos_alpha); }
+			if (sin_b > 0 && sin_c > 0) { cos_alpha = glm_clamp(numer0 / denom0, -1.0f, 1.0f); alpha = acosf_x(cos_alpha); }
 			else { alpha = cos_alpha = nan; }
 		}
 	}
 	pdf = 1.0f / surface_area;  // geometry.cpp:115 (inf when the area is 0)
 
 	// Arvo sampling (random.cpp:101-154)
-	float sin_alpha = ssbm::sinf_exact(alpha);
+	float sin_alpha = sinf_x(alpha);
 	float q;
 	if (sin_alpha > 0) {
 		float random_area = r0 * surface_area;
 		float phi = random_area - alpha;
-		float s = ssbm::sinf_exact(phi), tt = ssbm::cosf_exact(phi);
+		float s = sinf_x(phi), tt = cosf_x(phi);
 		float u = tt - cos_alpha;
 		float v = s + sin_alpha * cos_c;
 		float denom = (v * s + u * tt) * sin_alpha;
@@ -526,6 +593,7 @@ ssb_trace_kernel(const __grid_constant__ KParams P) {
 	S.lights = reinterpret_cast<const uint32_t*>(smem_raw + S.hdr->off_lights);
 	S.textures = reinterpret_cast<const DevTexture*>(smem_raw + S.hdr->off_textures);
 	S.pool = reinterpret_cast<const float*>(smem_raw + S.hdr->off_pool);
+	S.boxes = reinterpret_cast<const float4*>(smem_raw + S.hdr->off_boxes);
 
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -609,8 +677,10 @@ ssb_trace_kernel(const __grid_constant__ KParams P) {
 		Hit hit;
 		hit.quad = -1; hit.tri = 0; hit.dist = 0; hit.bx = hit.by = hit.bz = 0;
 		if (alive) {
-			RayConst rc = (state == ST_SHADOW) ? ray_setup(ox, oy, oz, sx, sy, sz) : ray_setup(ox, oy, oz, dx, dy, dz);
-			scene_intersect(S, rc, eps, (state == ST_SHADOW) ? cur_quad : ignore, hit);
+			const bool sh = state == ST_SHADOW;
+			const float rdx = sh ? sx : dx, rdy = sh ? sy : dy, rdz = sh ? sz : dz;
+			RayConst rc = ray_setup(ox, oy, oz, rdx, rdy, rdz);
+			scene_intersect(S, rc, eps, sh ? cur_quad : ignore, hit, ox, oy, oz, rdx, rdy, rdz);
 		}
 
 		bool do_bsdf = false, finish = false;
@@ -691,7 +761,7 @@ ssb_trace_kernel(const __grid_constant__ KParams P) {
 				float hx, hy, hz;
 				do {
 					float angle = rand_1f(rng) * (2.0f * SSB_PI_F);
-					float co = ssbm::cosf_exact(angle), si = ssbm::sinf_exact(angle);
+					float co = cosf_x(angle), si = sinf_x(angle);
 					float radius_sq = rand_1f(rng);
 					float radius = sqrtf(radius_sq);
 					hx = radius * co; hy = sqrtf(1.0f - radius_sq); hz = radius * si;
