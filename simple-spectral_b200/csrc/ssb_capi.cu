@@ -104,9 +104,13 @@ struct ssb_ctx {
 	float* d_meng_points = nullptr;
 	double* d_accum = nullptr;
 	uint32_t accum_w = 0, accum_h = 0;
-	float4* d_samples = nullptr;
-	size_t samples_capacity = 0;  // in float4
-	unsigned long long* d_counter = nullptr;
+	// wavefront buffers of one pass (see KParams)
+	unsigned char* d_wave = nullptr;
+	size_t wave_bytes = 0;
+	float4* d_samples = nullptr;      // per-sample outputs, only allocated for ssb_debug_trace_samples
+	size_t samples_capacity = 0;      // in float4
+	bool want_samples = false;
+	uint32_t* d_counts = nullptr;     // queue lengths per depth
 	double* d_xyza = nullptr;
 	float4* d_srgba = nullptr;
 	size_t resolve_capacity = 0;  // pixels
@@ -237,7 +241,7 @@ int validate_options(const ssb_options* o, uint32_t& x1, uint32_t& y1, uint32_t&
 	return SSB_OK;
 }
 
-const size_t kSampleBudget = (size_t)64 << 20;  // float4 slots per pass (1 GiB)
+const size_t kWaveBudgetBytes = (size_t)12 << 30;  // device memory for the path state + fold records of one pass
 
 }  // namespace
 
@@ -280,7 +284,7 @@ int ssb_create(int device, ssb_ctx** out) {
 	SSB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
 	SSB_CUDA(cudaEventCreate(&c->ev_begin)); SSB_CUDA(cudaEventCreate(&c->ev_end));
-	SSB_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
+	SSB_CUDA(cudaMalloc(&c->d_counts, (SSB_MAX_DEPTH + 2) * sizeof(uint32_t)));
 	*out = c;
 	return SSB_OK;
 }
@@ -291,7 +295,7 @@ void ssb_destroy(ssb_ctx* c) {
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	free_textures(c);
 	cudaFree(c->d_blob); cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points);
-	cudaFree(c->d_accum); cudaFree(c->d_samples); cudaFree(c->d_counter); cudaFree(c->d_xyza); cudaFree(c->d_srgba);
+	cudaFree(c->d_accum); cudaFree(c->d_samples); cudaFree(c->d_counts); cudaFree(c->d_wave); cudaFree(c->d_xyza); cudaFree(c->d_srgba);
 	cudaFree(c->d_rgb_staging);
 	if (c->ev_begin) cudaEventDestroy(c->ev_begin);
 	if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -425,20 +429,53 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	const uint32_t nsamp_total = s1 - o->sample_begin;
 	c->stats = ssb_stats{}; c->stats_pending = false; c->passes = 0;
 	if (npix_rect == 0 || nsamp_total == 0) return SSB_OK;
-	if (npix_rect > kSampleBudget) return fail(SSB_ERR_UNSUPPORTED, "pixel rectangle too large for one pass");
-	uint32_t chunk = (uint32_t)std::min<size_t>(nsamp_total, std::max<size_t>(1, kSampleBudget / npix_rect));
-	size_t need = npix_rect * chunk;
-	if (need > c->samples_capacity) {
+
+	// ---- size one pass: N = npix_rect * chunk samples share the wavefront buffers
+	const uint32_t nrec_depths = o->max_depth > 1 ? o->max_depth - 1 : 1;
+	const size_t bytes_per_sample = 2 * (16 + 16 + 16 + 4) + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4;
+	const size_t max_samples = std::min<size_t>(kWaveBudgetBytes / bytes_per_sample, (size_t)1 << 31);
+	if (npix_rect > max_samples) return fail(SSB_ERR_UNSUPPORTED, "pixel rectangle too large for one pass");
+	const uint32_t chunk = (uint32_t)std::min<size_t>(nsamp_total, std::max<size_t>(1, max_samples / npix_rect));
+	const size_t N = npix_rect * chunk;
+	auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+	size_t off = 0;
+	const size_t o_od0 = off; off += up(N * 16); const size_t o_od1 = off; off += up(N * 16);
+	const size_t o_dl0 = off; off += up(N * 16); const size_t o_dl1 = off; off += up(N * 16);
+	const size_t o_rng0 = off; off += up(N * 16); const size_t o_rng1 = off; off += up(N * 16);
+	const size_t o_id0 = off; off += up(N * 4); const size_t o_id1 = off; off += up(N * 4);
+	const size_t o_sl = off; off += up(N * nrec_depths * 16);
+	const size_t o_sf = off; off += up(N * nrec_depths * 16);
+	const size_t o_sn = off; off += up(N * nrec_depths * 8);
+	const size_t o_leaf = off; off += up(N * 16);
+	const size_t o_meta = off; off += up(N * 8);
+	const size_t o_ff = off; off += up(N * 4);
+	if (off > c->wave_bytes) {
+		if (c->d_wave) cudaFree(c->d_wave);
+		c->d_wave = nullptr; c->wave_bytes = 0;
+		SSB_CUDA(cudaMalloc(&c->d_wave, off));
+		c->wave_bytes = off;
+	}
+	if (c->want_samples && N > c->samples_capacity) {
 		if (c->d_samples) cudaFree(c->d_samples);
 		c->d_samples = nullptr; c->samples_capacity = 0;
-		SSB_CUDA(cudaMalloc(&c->d_samples, need * sizeof(float4)));
-		c->samples_capacity = need;
+		SSB_CUDA(cudaMalloc(&c->d_samples, N * sizeof(float4)));
+		c->samples_capacity = N;
 	}
 
 	KParams P{};
 	P.blob = c->d_blob;
-	P.samples = c->d_samples;
-	P.work_counter = c->d_counter;
+	unsigned char* wv = c->d_wave;
+	P.st_od[0] = reinterpret_cast<float4*>(wv + o_od0); P.st_od[1] = reinterpret_cast<float4*>(wv + o_od1);
+	P.st_dl[0] = reinterpret_cast<float4*>(wv + o_dl0); P.st_dl[1] = reinterpret_cast<float4*>(wv + o_dl1);
+	P.st_rng[0] = reinterpret_cast<uint4*>(wv + o_rng0); P.st_rng[1] = reinterpret_cast<uint4*>(wv + o_rng1);
+	P.st_id[0] = reinterpret_cast<uint32_t*>(wv + o_id0); P.st_id[1] = reinterpret_cast<uint32_t*>(wv + o_id1);
+	P.stk_local = reinterpret_cast<float4*>(wv + o_sl); P.stk_f = reinterpret_cast<float4*>(wv + o_sf);
+	P.stk_np = reinterpret_cast<float2*>(wv + o_sn);
+	P.leaf = reinterpret_cast<float4*>(wv + o_leaf); P.meta = reinterpret_cast<float2*>(wv + o_meta);
+	P.ff = reinterpret_cast<float*>(wv + o_ff);
+	P.counts = c->d_counts;
+	P.samples = c->want_samples ? c->d_samples : nullptr;
+	P.accum = c->d_accum;
 	P.width = o->width; P.height = o->height; P.x0 = o->x0; P.y0 = o->y0; P.rect_w = rect_w; P.rect_h = rect_h;
 	P.indirect_only = o->indirect_only; P.upsampling = o->upsampling; P.max_depth = o->max_depth;
 	P.els = o->explicit_light_sampling; P.flat_field = o->flat_field_correction;
@@ -455,31 +492,48 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.meng_sample_min = c->meng.sample_min; P.meng_sample_max = c->meng.sample_max;
 
 	const size_t smem = c->blob_bytes;
-	SSB_CUDA(cudaFuncSetAttribute(ssb_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int blocks_per_sm = 0;
-	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ssb_trace_kernel, SSB_TRACE_THREADS, smem));
-	if (blocks_per_sm < 1) return fail(SSB_ERR_UNSUPPORTED, "trace kernel does not fit on an SM with %zu bytes of tables", smem);
+	typedef void (*bounce_fn)(const KParams);
+	bounce_fn k_first = nullptr, k_next = nullptr;
+	switch (o->upsampling) {  // one instantiation per upsampling mode keeps the instruction footprint small
+		case SSB_UPSAMPLE_OURS: k_first = ssb_bounce_kernel<true, SSB_UPSAMPLE_OURS>; k_next = ssb_bounce_kernel<false, SSB_UPSAMPLE_OURS>; break;
+		case SSB_UPSAMPLE_JH: k_first = ssb_bounce_kernel<true, SSB_UPSAMPLE_JH>; k_next = ssb_bounce_kernel<false, SSB_UPSAMPLE_JH>; break;
+		default: k_first = ssb_bounce_kernel<true, SSB_UPSAMPLE_MENG>; k_next = ssb_bounce_kernel<false, SSB_UPSAMPLE_MENG>; break;
+	}
+	SSB_CUDA(cudaFuncSetAttribute(k_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	SSB_CUDA(cudaFuncSetAttribute(k_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int occ_first = 0, occ_next = 0;
+	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_first, k_first, SSB_BOUNCE_THREADS, smem));
+	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_next, k_next, SSB_BOUNCE_THREADS, smem));
+	if (occ_first < 1 || occ_next < 1) return fail(SSB_ERR_UNSUPPORTED, "bounce kernel does not fit on an SM with %zu bytes of tables", smem);
 
 	SSB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
 	uint32_t launches = 0, passes = 0;
 	for (uint32_t k0 = 0; k0 < nsamp_total; k0 += chunk) {
-		uint32_t ns = std::min(chunk, nsamp_total - k0);
+		const uint32_t ns = std::min(chunk, nsamp_total - k0);
 		P.sample_begin = o->sample_begin + k0;
 		P.nsamp = ns;
 		P.total_work = (unsigned long long)npix_rect * ns;
-		SSB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
-		// persistent grid: SMs x resident CTAs, never more CTAs than there is work for
-		unsigned long long want = (P.total_work + SSB_TRACE_THREADS - 1) / SSB_TRACE_THREADS;
-		unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * blocks_per_sm, want);
+		SSB_CUDA(cudaMemsetAsync(c->d_counts, 0, (SSB_MAX_DEPTH + 2) * sizeof(uint32_t), c->stream));
 		while (c->ev_pass.size() < 2 * (size_t)(passes + 1)) { cudaEvent_t e; SSB_CUDA(cudaEventCreate(&e)); c->ev_pass.push_back(e); }
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes], c->stream));
-		ssb_trace_kernel<<<grid, SSB_TRACE_THREADS, smem, c->stream>>>(P);
-		SSB_CUDA(cudaGetLastError());
+		// one launch per path depth; persistent grids (SMs x resident CTAs), never more CTAs than the first queue needs
+		const unsigned long long want = (P.total_work + SSB_BOUNCE_THREADS - 1) / SSB_BOUNCE_THREADS;
+		for (uint32_t d = 0; d < o->max_depth; ++d) {
+			// with explicit light sampling the last depth is never entered (dead-work skip in the bounce kernel)
+			if (d > 0 && o->explicit_light_sampling && d + 1 >= o->max_depth) break;
+			P.depth = d;
+			const int occ = d == 0 ? occ_first : occ_next;
+			const unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * occ, want);
+			if (d == 0) k_first<<<grid, SSB_BOUNCE_THREADS, smem, c->stream>>>(P);
+			else k_next<<<grid, SSB_BOUNCE_THREADS, smem, c->stream>>>(P);
+			SSB_CUDA(cudaGetLastError());
+			launches += 1;
+		}
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes + 1], c->stream));
-		unsigned agrid = (unsigned)((npix_rect + 127) / 128);
-		ssb_accumulate_kernel<<<agrid, 128, 0, c->stream>>>(c->d_samples, c->d_accum, o->width, o->x0, o->y0, rect_w, rect_h, ns);
+		const unsigned fgrid = (unsigned)((npix_rect + 127) / 128);
+		ssb_finalize_kernel<<<fgrid, 128, 0, c->stream>>>(P);
 		SSB_CUDA(cudaGetLastError());
-		launches += 2; passes += 1;
+		launches += 1; passes += 1;
 	}
 	SSB_CUDA(cudaEventRecord(c->ev_end, c->stream));
 	// asynchronous: the event times are read lazily by ssb_get_stats()
@@ -623,11 +677,12 @@ int ssb_debug_trace_samples(ssb_ctx* c, const ssb_options* o, uint32_t px, uint3
 	bool had = c->d_accum && c->accum_w == o->width && c->accum_h == o->height;
 	if (had) { saved.resize((size_t)o->width * o->height * 4); if ((rc = ssb_read_accum(c, saved.data())) != SSB_OK) return rc; }
 	uint32_t begin = one.sample_begin;
-	if (begin == 0) one.sample_begin = 0;
+	c->want_samples = true;
 	rc = ssb_render(c, &one);
+	c->want_samples = false;
 	if (rc != SSB_OK) return rc;
 	uint32_t ns = s1 - begin;
-	if ((size_t)ns > kSampleBudget) return fail(SSB_ERR_UNSUPPORTED, "too many samples");
+	if ((size_t)ns > c->samples_capacity) return fail(SSB_ERR_UNSUPPORTED, "too many samples for one pass");
 	SSB_CUDA(cudaStreamSynchronize(c->stream));
 	SSB_CUDA(cudaMemcpy(out_host, c->d_samples, (size_t)ns * sizeof(float4), cudaMemcpyDeviceToHost));
 	if (had) rc = ssb_write_accum(c, saved.data());

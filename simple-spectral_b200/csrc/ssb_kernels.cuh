@@ -5,23 +5,24 @@
 // islands the reference has: camera ray, zero-barycentric fallback, accumulation), compiled with
 // -fmad=false so that no multiply-add is contracted: operation order is the reference's.
 //
-// Design (B200-first, not a translation of the reference's recursive std::function):
-//   * ssb_trace_kernel — persistent kernel, one CTA set per SM, grid = SMs x resident CTAs.
-//     One lane = one path.  The recursion L() is turned into a per-lane state machine in which
-//     EVERY loop iteration performs exactly one ray query (closest-hit or shadow) for every lane,
-//     so the dominant cost (the linear scan over the quad list, scene.cpp:433-445) always runs
-//     converged; lanes whose path ended regenerate a new path in place (warp-ballot compaction of
-//     the work queue: one atomic per warp per chunk), so lanes do not idle while the longest path
-//     of the warp finishes.
-//   * the scene, materials, spectra, observer/basis tables and the sRGB LUT are one contiguous
-//     "blob" that each CTA pulls into shared memory with a single TMA bulk copy
-//     (cp.async.bulk.shared::cluster.global + mbarrier).
-//   * the reference folds radiance on the way back UP the recursion (renderer.cpp:216,248); to keep
-//     that exact rounding, each lane keeps a small per-depth stack (local memory, L1-resident) and
-//     folds it backwards when its path ends.
-//   * each sample's float4 (X,Y,Z,hit) goes to a [sample][pixel] buffer; ssb_accumulate_kernel then
-//     adds sample*0.001f to the double XYZA accumulator in sample order — the reference's exact
-//     summation order (renderer.cpp:292-295), deterministic run to run (no float/double atomics).
+// Design (B200-first, not a translation of the reference's recursive std::function): a WAVEFRONT.
+//   * One launch of ssb_bounce_kernel per path depth.  A thread owns one live path for exactly one bounce:
+//     closest-hit query -> emission / albedo -> light sample -> shadow query -> BSDF sample -> next ray.  Every
+//     lane of every warp is a live path (ncu on the first, megakernel version of this file showed 9.8 of 32
+//     lanes active on average and the instruction cache thrashing on a 131 KB kernel; see profiles/).
+//   * Path state lives in HBM as dense, coalesced float4/uint4 SoA arrays (origin+ignore, direction+lambda0, PCG32
+//     state, sample id), ping-ponged between depths.  Surviving paths are stream-compacted on write with a
+//     warp ballot + one atomic per warp, so the next depth's launch is dense again.
+//   * The depth-0 instantiation generates the camera ray, seeds the RNG and draws the hero wavelength in-kernel.
+//   * The kernels are persistent (grid = SMs x resident CTAs, grid-stride over the queue whose length is read
+//     from device memory: no host round-trip between depths).
+//   * the scene, materials, spectra, observer/basis tables and the sRGB LUT are one contiguous "blob" that each
+//     CTA pulls into shared memory with a single TMA bulk copy (cp.async.bulk.shared::cluster.global + mbarrier).
+//   * the reference folds radiance on the way back UP the recursion (renderer.cpp:216,248); to keep that exact
+//     rounding every bounce writes its (local radiance, f_s, n.l, pdf) record to a per-depth array, and
+//     ssb_finalize_kernel folds them backwards per sample, converts to XYZ and adds sample*0.001f to the double
+//     XYZA accumulator in sample order — the reference's exact summation order (renderer.cpp:292-295),
+//     deterministic run to run (no float/double atomics).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -59,11 +60,26 @@ struct DevHeader {
 
 struct KParams {
 	const unsigned char* blob;
-	float4* samples;               // [nsamp][npix_rect]
-	unsigned long long* work_counter;
+	// path state, ping-pong [2]: dense arrays indexed by queue position
+	float4* st_od[2];   // origin.xyz, ignore (int bits)
+	float4* st_dl[2];   // direction.xyz, lambda_0
+	uint4* st_rng[2];   // PCG32 state, inc
+	uint32_t* st_id[2]; // sample id within the pass
+	// per-depth records for the backward fold, indexed [depth][sample id]
+	float4* stk_local;
+	float4* stk_f;
+	float2* stk_np;     // n.l, pdf
+	// per-sample end of path
+	float4* leaf;       // value returned by the deepest L() call
+	float2* meta;       // lambda_0, (#records | hit<<16) as int bits
+	float* ff;          // dot(camera ray, camera dir), only when FLAT_FIELD_CORRECTION is off (renderer.cpp:265)
+	uint32_t* counts;   // queue length per depth; counts[0] = samples in the pass
+	float4* samples;    // optional [nsamp][npix_rect] per-sample output (debug), may be null
+	double* accum;
 	unsigned long long total_work;  // npix_rect * nsamp
 	uint32_t width, height, x0, y0, rect_w, rect_h, sample_begin, nsamp;
 	uint32_t indirect_only, upsampling, max_depth, els, flat_field;
+	uint32_t depth;     // depth processed by this launch
 	float eps, lambda_min, lambda_step;
 	unsigned long long seed;
 	double pv_inv[16];
@@ -88,6 +104,11 @@ __device__ __forceinline__ float glm_max(float a, float b) { return (a < b) ? b 
 __device__ __forceinline__ float glm_clamp(float x, float lo, float hi) { return glm_min(glm_max(x, lo), hi); }
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
 	return (ax * bx + ay * by) + az * bz;
+}
+__device__ __forceinline__ float rcp_approx(float x) {  // 1 ulp MUFU.RCP: culling only, never reference arithmetic
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
 }
 __device__ __forceinline__ float sel3(float x, float y, float z, int i) { return i == 0 ? x : (i == 1 ? y : z); }
 
@@ -288,6 +309,7 @@ __device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, f
 
 // material albedo at (st, lambda_0): constant spectrum or sRGB texture + upsampling
 // (material.cpp:45-97,120-143; color.cpp:166-232)
+template <int UPS>
 __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneView& S, const DevMaterial& m,
                                                 float st_x, float st_y, float lambda_0) {
 	if (m.albedo_mode == SSB_ALBEDO_CONSTANT) return spec_hero(S.pool, m.albedo, lambda_0, P.lambda_step);
@@ -299,7 +321,7 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 	j = max(j, 0); j = min(j, (int)tex.height - 1);
 	uchar4 px = __ldg(tex.rgba + ((size_t)j * tex.width + (size_t)i));
 	float r = S.hdr->srgb_lut[px.x], g = S.hdr->srgb_lut[px.y], b = S.hdr->srgb_lut[px.z];
-	if (P.upsampling == SSB_UPSAMPLE_OURS) {
+	if (UPS == SSB_UPSAMPLE_OURS) {
 		Hero br = spec_hero(S.pool, S.hdr->basis_r, lambda_0, P.lambda_step);
 		Hero bg = spec_hero(S.pool, S.hdr->basis_g, lambda_0, P.lambda_step);
 		Hero bb = spec_hero(S.pool, S.hdr->basis_b, lambda_0, P.lambda_step);
@@ -307,10 +329,11 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 #pragma unroll
 		for (int k = 0; k < 4; ++k) h.v[k] = (r * br.v[k] + g * bg.v[k]) + b * bb.v[k];
 		return h;
-	} else if (P.upsampling == SSB_UPSAMPLE_JH) {
+	} else if (UPS == SSB_UPSAMPLE_JH) {
 		return jh_upsample(P, r, g, b, lambda_0);
+	} else {
+		return meng_upsample(P, r, g, b, lambda_0);
 	}
-	return meng_upsample(P, r, g, b, lambda_0);
 }
 
 // ------------------------------------------------------------------ ray / scene intersection
@@ -396,16 +419,17 @@ __device__ __forceinline__ bool tri_intersect(const ssb_tri& t, const RayConst& 
 #ifndef SSB_CULL
 #define SSB_CULL 1
 #endif
-__device__ __forceinline__ void scene_intersect(const SceneView& S, const RayConst& rc, float eps, int ignore, Hit& hit,
-                                                float ox, float oy, float oz, float dx, float dy, float dz) {
+__device__ __noinline__ void scene_intersect(const SceneView& S, float eps, int ignore, Hit& hit,
+                                             float ox, float oy, float oz, float dx, float dy, float dz) {
+	const RayConst rc = ray_setup(ox, oy, oz, dx, dy, dz);
 	hit.quad = -1; hit.tri = 0; hit.dist = __int_as_float(0x7f800000);
 	hit.bx = hit.by = hit.bz = 0.0f;
 	const int nq = (int)S.hdr->nquads;
 #if SSB_CULL
 	// per-ray reciprocal direction, clamped so that axis-parallel rays give finite slab distances
-	float ix = (fabsf(dx) < 1e-30f) ? copysignf(1e30f, dx) : __frcp_rn(dx);
-	float iy = (fabsf(dy) < 1e-30f) ? copysignf(1e30f, dy) : __frcp_rn(dy);
-	float iz = (fabsf(dz) < 1e-30f) ? copysignf(1e30f, dz) : __frcp_rn(dz);
+	float ix = (fabsf(dx) < 1e-30f) ? copysignf(1e30f, dx) : rcp_approx(dx);
+	float iy = (fabsf(dy) < 1e-30f) ? copysignf(1e30f, dy) : rcp_approx(dy);
+	float iz = (fabsf(dz) < 1e-30f) ? copysignf(1e30f, dz) : rcp_approx(dz);
 	float bx = -ox * ix, by = -oy * iy, bz = -oz * iz;
 	for (int base = 0; base < nq; base += 32) {
 		const int cnt = min(32, nq - base);
@@ -457,6 +481,8 @@ __device__ __forceinline__ void func_bar(float xx, float xy, float xz, float yx,
 	float inv = 1.0f / sqrtf(lensq);
 	ox = dx * inv; oy = dy * inv; oz = dz * inv;
 }
+
+__device__ __noinline__ float cos_double_cold(float x) { return (float)cos((double)x); }  // degenerate triangles only
 
 __device__ __noinline__ void sample_spherical_triangle(const ssb_tri& t, float px, float py, float pz, float r0, float r1,
                                                        float& wx, float& wy, float& wz, float& pdf) {
@@ -521,7 +547,7 @@ __device__ __noinline__ void sample_spherical_triangle(const ssb_tri& t, float p
 		if (denom != 0.0f) q = ((v * tt - u * s) * cos_alpha - v) / denom;
 		else q = cos_c;
 	} else {
-		q = (float)cos((double)(b * r0));  // ::cos(double), random.cpp:135
+		q = cos_double_cold(b * r0);  // ::cos(double), random.cpp:135
 	}
 	q = glm_clamp(q, -1.0f, 1.0f);
 	float fx, fy, fz;
@@ -534,11 +560,6 @@ __device__ __noinline__ void sample_spherical_triangle(const ssb_tri& t, float p
 	float sz = sqrtf(1.0f - z * z);
 	wx = z * Bx + sz * fx; wy = z * By + sz * fy; wz = z * Bz + sz * fz;
 }
-
-// ------------------------------------------------------------------ per-lane path state
-#define SSB_STACK_FLOATS 10  // local[4], f[4], n_dot_l, pdf
-
-enum : int { ST_CLOSEST = 0, ST_SHADOW = 1 };
 
 // ------------------------------------------------------------------ TMA bulk copy of the blob into shared memory
 __device__ __forceinline__ void stage_blob(unsigned char* smem, const unsigned char* gmem, uint32_t bytes,
@@ -570,16 +591,18 @@ __device__ __forceinline__ void stage_blob(unsigned char* smem, const unsigned c
 	}
 }
 
-#ifndef SSB_TRACE_THREADS
-#define SSB_TRACE_THREADS 128
+#ifndef SSB_BOUNCE_THREADS
+#define SSB_BOUNCE_THREADS 128
 #endif
-#ifndef SSB_TRACE_MIN_BLOCKS
-#define SSB_TRACE_MIN_BLOCKS 4
+#ifndef SSB_BOUNCE_MIN_BLOCKS
+#define SSB_BOUNCE_MIN_BLOCKS 4
 #endif
-#define SSB_WORK_CHUNK 128u  // work items a warp reserves per atomic
 
-__global__ void __launch_bounds__(SSB_TRACE_THREADS, SSB_TRACE_MIN_BLOCKS)
-ssb_trace_kernel(const __grid_constant__ KParams P) {
+// One bounce of every live path at depth P.depth: the body of the reference's lambda L (renderer.cpp:147-255).
+// FIRST: depth 0 — the path is created here (Renderer::_render_sample prologue, renderer.cpp:103-138).
+template <bool FIRST, int UPS>
+__global__ void __launch_bounds__(SSB_BOUNCE_THREADS, SSB_BOUNCE_MIN_BLOCKS)
+ssb_bounce_kernel(const __grid_constant__ KParams P) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long blob_bar;
 	{
@@ -600,44 +623,28 @@ ssb_trace_kernel(const __grid_constant__ KParams P) {
 	const uint32_t npix_rect = P.rect_w * P.rect_h;
 	const float eps = P.eps;
 	const bool els = P.els != 0;
+	const int depth = (int)P.depth;
+	const uint32_t n_in = FIRST ? (uint32_t)P.total_work : P.counts[depth];
+	const int pin = depth & 1, pout = pin ^ 1;
+	const uint32_t nthreads = gridDim.x * blockDim.x;
+	// warps iterate together: the loop bound is rounded up to a warp multiple so that ballots stay converged
+	const uint32_t n_round = (n_in + 31u) & ~31u;
 
-	// warp-uniform work queue
-	unsigned long long wq_next = 0, wq_end = 0;
-	bool exhausted = false;
-
-	// per-lane path state
-	bool alive = false;
-	int state = ST_CLOSEST;
-	Rng rng; rng.state = 0; rng.inc = 1;
-	unsigned long long out_index = 0;
-	float ox = 0, oy = 0, oz = 0;     // ray origin (becomes the hit point once something was hit)
-	float dx = 0, dy = 0, dz = 1;     // path direction
-	float sx = 0, sy = 0, sz = 1;     // shadow-ray direction (ST_SHADOW)
-	float nx = 0, ny = 0, nz = 0;     // geometric normal at the current vertex
-	float lambda_0 = 0, ff_scale = 1.0f;
-	Hero f_s, local;                  // BSDF value and radiance gathered at the current vertex
-	f_s.v[0] = f_s.v[1] = f_s.v[2] = f_s.v[3] = 0; local = f_s;
-	float l_ndl = 0, l_pdf = 1;       // light sample: n.l and pdf
-	int depth = 0, ignore = -1, cur_quad = -1, light_quad = -1;
-	bool last_was_delta = true, hit_anything = false;
-	float stk[SSB_MAX_DEPTH * SSB_STACK_FLOATS];
-
-	while (true) {
-		// ---------------------------------------------------------------- regeneration
-		bool need = !alive && !exhausted;
-		unsigned need_mask = __ballot_sync(full, need);
-		while (need_mask) {
-			unsigned long long avail = wq_end - wq_next;
-			unsigned rank = __popc(need_mask & ((1u << lane) - 1u));
-			unsigned cnt = __popc(need_mask);
-			if (need && rank < avail) {
-				// -------- start a new path: Renderer::_render_sample prologue (renderer.cpp:103-138)
-				unsigned long long work = wq_next + rank;
-				uint32_t kk = (uint32_t)(work / npix_rect);
-				uint32_t pr = (uint32_t)(work - (unsigned long long)kk * npix_rect);
+	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += nthreads) {
+		const bool valid = item < n_in;
+		bool cont = false;  // path continues to depth+1
+		float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, lambda_0 = 0;
+		float ff_scale = 1.0f;
+		int ignore = -1;
+		uint32_t id = 0;
+		Rng rng; rng.state = 0; rng.inc = 1;
+		if (valid) {
+			if (FIRST) {
+				id = item;
+				uint32_t kk = id / npix_rect;
+				uint32_t pr = id - kk * npix_rect;
 				uint32_t pi = P.x0 + pr % P.rect_w, pj = P.y0 + pr / P.rect_w;
 				uint32_t k = P.sample_begin + kk;
-				out_index = work;
 				unsigned long long sample_index = (unsigned long long)k * ((unsigned long long)P.width * P.height) +
 				                                  ((unsigned long long)pj * P.width + pi);
 				rng.state = mix64(P.seed ^ mix64(sample_index));
@@ -658,200 +665,209 @@ ssb_trace_kernel(const __grid_constant__ KParams P) {
 				dx = (float)(ddx * inv); dy = (float)(ddy * inv); dz = (float)(ddz * inv);
 				lambda_0 = P.lambda_min + rand_1f(rng) * P.lambda_step;
 				if (!P.flat_field) ff_scale = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
-				depth = 0; ignore = -1; last_was_delta = true; hit_anything = false; state = ST_CLOSEST;
-				alive = true; need = false;
-			}
-			wq_next += (cnt < avail) ? cnt : avail;
-			need_mask = __ballot_sync(full, need);
-			if (!need_mask) break;
-			unsigned long long base = 0;
-			if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)SSB_WORK_CHUNK);
-			base = __shfl_sync(full, base, 0);
-			if (base >= P.total_work) { exhausted = true; break; }
-			wq_next = base;
-			wq_end = (base + SSB_WORK_CHUNK < P.total_work) ? base + SSB_WORK_CHUNK : P.total_work;
-		}
-		if (!__any_sync(full, alive)) break;
-
-		// ---------------------------------------------------------------- one ray query for every live lane
-		Hit hit;
-		hit.quad = -1; hit.tri = 0; hit.dist = 0; hit.bx = hit.by = hit.bz = 0;
-		if (alive) {
-			const bool sh = state == ST_SHADOW;
-			const float rdx = sh ? sx : dx, rdy = sh ? sy : dy, rdz = sh ? sz : dz;
-			RayConst rc = ray_setup(ox, oy, oz, rdx, rdy, rdz);
-			scene_intersect(S, rc, eps, sh ? cur_quad : ignore, hit, ox, oy, oz, rdx, rdy, rdz);
-		}
-
-		bool do_bsdf = false, finish = false;
-		Hero rad;  // value returned by the deepest L() call when the path ends
-		rad.v[0] = rad.v[1] = rad.v[2] = rad.v[3] = 0.0f;
-
-		if (alive && state == ST_SHADOW) {
-			// ---- shadow ray came back (renderer.cpp:196-218)
-			if (hit.quad == light_quad) {
-				const DevMaterial& lm = S.materials[S.quads[light_quad].material];
-				Hero emitted = spec_hero(S.pool, lm.emission, lambda_0, P.lambda_step);
-				const DevMaterial& m = S.materials[S.quads[cur_quad].material];
-#pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					float fe = (m.kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;  // MaterialMirror::evaluate_bsdf = 0
-					local.v[c] = local.v[c] + ((emitted.v[c] * l_ndl) * fe) / l_pdf;
-				}
-			}
-			do_bsdf = true;
-		} else if (alive) {
-			// ---- closest hit of the path ray: body of L() (renderer.cpp:147-255)
-			if (hit.quad < 0) {
-				finish = true;  // miss: L() returns 0
 			} else {
+				const float4 a = P.st_od[pin][item], b = P.st_dl[pin][item];
+				const uint4 r = P.st_rng[pin][item];
+				id = P.st_id[pin][item];
+				ox = a.x; oy = a.y; oz = a.z; ignore = __float_as_int(a.w);
+				dx = b.x; dy = b.y; dz = b.z; lambda_0 = b.w;
+				rng.state = ((unsigned long long)r.y << 32) | r.x;
+				rng.inc = ((unsigned long long)r.w << 32) | r.z;
+			}
+
+			// ---- closest hit (renderer.cpp:163)
+			Hit hit;
+			scene_intersect(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+			Hero rad;  // value this L() call returns if the path ends here
+			rad.v[0] = rad.v[1] = rad.v[2] = rad.v[3] = 0.0f;
+			int nrec = depth;            // fold records written by shallower depths
+			bool hit_anything = !FIRST;  // depth > 0 implies an earlier hit
+			if (hit.quad >= 0) {
 				hit_anything = true;
-				cur_quad = hit.quad;
-				const ssb_quad& quad = S.quads[hit.quad];
+				const int cur_quad = hit.quad;
+				const ssb_quad& quad = S.quads[cur_quad];
 				const ssb_tri& tri = quad.tri[hit.tri];
 				const DevMaterial& m = S.materials[quad.material];
-				nx = tri.normal[0]; ny = tri.normal[1]; nz = tri.normal[2];
-				float st_x = (hit.bx * tri.v[0].st[0] + hit.by * tri.v[1].st[0]) + hit.bz * tri.v[2].st[0];
-				float st_y = (hit.bx * tri.v[0].st[1] + hit.by * tri.v[1].st[1]) + hit.bz * tri.v[2].st[1];
+				const float nx = tri.normal[0], ny = tri.normal[1], nz = tri.normal[2];
+				const float st_x = (hit.bx * tri.v[0].st[0] + hit.by * tri.v[1].st[0]) + hit.bz * tri.v[2].st[0];
+				const float st_y = (hit.bx * tri.v[0].st[1] + hit.by * tri.v[1].st[1]) + hit.bz * tri.v[2].st[1];
+				Hero local;
 				local.v[0] = local.v[1] = local.v[2] = local.v[3] = 0.0f;
-				if (!els || (last_was_delta && (!P.indirect_only || depth > 0))) {
+				// emission: last_was_delta is true only for the camera ray (the reference recurses with `false`, :248)
+				if (!els || (FIRST && !P.indirect_only)) {
 					Hero e = spec_hero(S.pool, m.emission, lambda_0, P.lambda_step);
 #pragma unroll
 					for (int c = 0; c < 4; ++c) local.v[c] = local.v[c] + e.v[c];
 				}
 				if ((uint32_t)depth + 1u < P.max_depth) {
-					// hit position (Ray::at): becomes the origin of the shadow ray and of the next path ray
-					float d_ = hit.dist;
-					ox = ox + d_ * dx; oy = oy + d_ * dy; oz = oz + d_ * dz;
-					// albedo lookup (the reference does it twice with identical arguments:
-					// evaluate_bsdf + interact_bsdf, material.cpp:120-143)
-					Hero alb = material_albedo(P, S, m, st_x, st_y, lambda_0);
+					// hit position (Ray::at): origin of the shadow ray and of the next path ray
+					const float d_ = hit.dist;
+					const float hx = ox + d_ * dx, hy = oy + d_ * dy, hz = oz + d_ * dz;
+					// albedo lookup (the reference does it twice with identical arguments, material.cpp:120-143)
+					Hero f_s = material_albedo<UPS>(P, S, m, st_x, st_y, lambda_0);
+					if (m.kind == SSB_MATERIAL_LAMBERT) {
 #pragma unroll
-					for (int c = 0; c < 4; ++c) f_s.v[c] = (m.kind == SSB_MATERIAL_LAMBERT) ? alb.v[c] / SSB_PI_F : alb.v[c];
-					do_bsdf = true;
-					if (els && (!P.indirect_only || depth > 0)) {
-						// Scene::get_rand_toward_light (scene.cpp:417-431)
+						for (int c = 0; c < 4; ++c) f_s.v[c] = f_s.v[c] / SSB_PI_F;
+					}
+					if (els && (!P.indirect_only || !FIRST)) {
+						// ---- direct lighting (renderer.cpp:182-220; Scene::get_rand_toward_light, scene.cpp:417-431)
 						uint32_t li = rand_choice(rng, S.hdr->nlights);
-						light_quad = (int)S.lights[li];
+						const int light_quad = (int)S.lights[li];
 						const ssb_quad& lq = S.quads[light_quad];
 						const ssb_tri& lt = (rand_1f(rng) <= 0.5f) ? lq.tri[0] : lq.tri[1];
 						float r0 = rand_1f(rng);
 						float r1 = rand_1f(rng);
-						float pdf;
-						sample_spherical_triangle(lt, ox, oy, oz, r0, r1, sx, sy, sz, pdf);
+						float sx, sy, sz, pdf;
+						sample_spherical_triangle(lt, hx, hy, hz, r0, r1, sx, sy, sz, pdf);
 						pdf *= 0.5f;
 						pdf /= (float)S.hdr->nlights;
-						l_pdf = pdf;
-						l_ndl = dot3(sx, sy, sz, nx, ny, nz);
-						if (l_ndl > 0.0f) { state = ST_SHADOW; do_bsdf = false; }
+						const float l_ndl = dot3(sx, sy, sz, nx, ny, nz);
+						if (l_ndl > 0.0f) {
+							Hit hs;
+							scene_intersect(S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
+							if (hs.quad == light_quad) {
+								const DevMaterial& lm = S.materials[lq.material];
+								Hero emitted = spec_hero(S.pool, lm.emission, lambda_0, P.lambda_step);
+#pragma unroll
+								for (int c = 0; c < 4; ++c) {
+									float fe = (m.kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;  // MaterialMirror::evaluate_bsdf = 0
+									local.v[c] = local.v[c] + ((emitted.v[c] * l_ndl) * fe) / pdf;
+								}
+							}
+						}
+					}
+					// ---- interact_bsdf + recursion decision (renderer.cpp:222-251)
+					float wix, wiy, wiz, pdf_w_i;
+					if (m.kind == SSB_MATERIAL_LAMBERT) {
+						float cx, cy, cz;  // Math::rand_coshemi (random.cpp:29-49)
+						do {
+							float angle = rand_1f(rng) * (2.0f * SSB_PI_F);
+							float co = cosf_x(angle), si = sinf_x(angle);
+							float radius_sq = rand_1f(rng);
+							float radius = sqrtf(radius_sq);
+							cx = radius * co; cy = sqrtf(1.0f - radius_sq); cz = radius * si;
+							pdf_w_i = cy;
+						} while (pdf_w_i <= eps);
+						pdf_w_i *= 1.0f / SSB_PI_F;
+						// Math::get_rotated_to / get_basis (math-helpers.hpp:14-38)
+						float sign = copysignf(1.0f, nz);
+						float a = -1.0f / (sign + nz);
+						float b = nx * ny * a;
+						float bxx = 1.0f + sign * nx * nx * a, bxy = sign * b, bxz = -sign * nx;
+						float bzx = b, bzy = sign + ny * ny * a, bzz = -ny;
+						wix = (cx * bxx + cy * nx) + cz * bzx;
+						wiy = (cx * bxy + cy * ny) + cz * bzy;
+						wiz = (cx * bxz + cy * nz) + cz * bzz;
+					} else {
+						// MaterialMirror::interact_bsdf (material.cpp:154-167): reflect(w_o = -ray.dir, N)
+						float vx = -dx, vy = -dy, vz = -dz;
+						float d2 = 2.0f * dot3(vx, vy, vz, nx, ny, nz);
+						wix = -vx + d2 * nx; wiy = -vy + d2 * ny; wiz = -vz + d2 * nz;
+						pdf_w_i = __int_as_float(0x7f800000);
+					}
+					bool recurse = false;
+					float n_dot_l = 0.0f;
+					float ff = (f_s.v[0] * f_s.v[0] + f_s.v[1] * f_s.v[1]) + (f_s.v[2] * f_s.v[2] + f_s.v[3] * f_s.v[3]);
+					if (ff > 0.0f) {
+						if (isfinite(pdf_w_i)) n_dot_l = dot3(wix, wiy, wiz, nx, ny, nz);
+						else { n_dot_l = 1.0f; pdf_w_i = 1.0f; }
+						recurse = n_dot_l > 0.0f;
+					}
+					if (recurse) {
+						const size_t rec = (size_t)depth * P.total_work + id;
+						P.stk_local[rec] = make_float4(local.v[0], local.v[1], local.v[2], local.v[3]);
+						P.stk_f[rec] = make_float4(f_s.v[0], f_s.v[1], f_s.v[2], f_s.v[3]);
+						P.stk_np[rec] = make_float2(n_dot_l, pdf_w_i);
+						nrec = depth + 1;
+						// Dead-work skip (result-identical): with explicit light sampling the L() call at the last depth
+						// can add neither emission (last_was_delta == false) nor children: it returns 0, hit_anything is
+						// already set and no random numbers are drawn there.  rad stays 0.
+						if (!(els && (uint32_t)depth + 2u >= P.max_depth)) {
+							cont = true;
+							ox = hx; oy = hy; oz = hz; dx = wix; dy = wiy; dz = wiz; ignore = cur_quad;
+						}
+					} else {
+						rad = local;
 					}
 				} else {
-					rad = local; finish = true;
+					rad = local;
 				}
 			}
+			// ---- the path ends here: the deepest L() call returns `rad`, `nrec` records wait to be folded
+			if (!cont) {
+				P.leaf[id] = make_float4(rad.v[0], rad.v[1], rad.v[2], rad.v[3]);
+				P.meta[id] = make_float2(lambda_0, __int_as_float(nrec | (hit_anything ? (1 << 16) : 0)));
+			}
+			if (FIRST && !P.flat_field) P.ff[id] = ff_scale;
 		}
 
-		if (do_bsdf) {
-			// ---- interact_bsdf + recursion decision (renderer.cpp:222-251)
-			state = ST_CLOSEST;
-			const DevMaterial& m = S.materials[S.quads[cur_quad].material];
-			float wix, wiy, wiz, pdf_w_i;
-			if (m.kind == SSB_MATERIAL_LAMBERT) {
-				// Math::rand_coshemi (random.cpp:29-49)
-				float hx, hy, hz;
-				do {
-					float angle = rand_1f(rng) * (2.0f * SSB_PI_F);
-					float co = cosf_x(angle), si = sinf_x(angle);
-					float radius_sq = rand_1f(rng);
-					float radius = sqrtf(radius_sq);
-					hx = radius * co; hy = sqrtf(1.0f - radius_sq); hz = radius * si;
-					pdf_w_i = hy;
-				} while (pdf_w_i <= eps);
-				pdf_w_i *= 1.0f / SSB_PI_F;
-				// Math::get_rotated_to / get_basis (math-helpers.hpp:14-38)
-				float sign = copysignf(1.0f, nz);
-				float a = -1.0f / (sign + nz);
-				float b = nx * ny * a;
-				float bxx = 1.0f + sign * nx * nx * a, bxy = sign * b, bxz = -sign * nx;
-				float bzx = b, bzy = sign + ny * ny * a, bzz = -ny;
-				wix = (hx * bxx + hy * nx) + hz * bzx;
-				wiy = (hx * bxy + hy * ny) + hz * bzy;
-				wiz = (hx * bxz + hy * nz) + hz * bzz;
-			} else {
-				// MaterialMirror::interact_bsdf (material.cpp:154-167): reflect(w_o = -ray.dir, N)
-				float vx = -dx, vy = -dy, vz = -dz;
-				float d2 = 2.0f * dot3(vx, vy, vz, nx, ny, nz);
-				wix = -vx + d2 * nx; wiy = -vy + d2 * ny; wiz = -vz + d2 * nz;
-				pdf_w_i = __int_as_float(0x7f800000);
+		// ---- compaction: surviving paths go to dense positions of the next depth's queue
+		const unsigned mask = __ballot_sync(full, cont);
+		if (mask) {
+			unsigned base = 0;
+			const int leader = __ffs(mask) - 1;
+			if (lane == leader) base = atomicAdd(&P.counts[depth + 1], (uint32_t)__popc(mask));
+			base = __shfl_sync(full, base, leader);
+			if (cont) {
+				const uint32_t o = base + __popc(mask & ((1u << lane) - 1u));
+				P.st_od[pout][o] = make_float4(ox, oy, oz, __int_as_float(ignore));
+				P.st_dl[pout][o] = make_float4(dx, dy, dz, lambda_0);
+				P.st_rng[pout][o] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
+				P.st_id[pout][o] = id;
 			}
-			bool recurse = false;
-			float n_dot_l = 0.0f;
-			float ff = (f_s.v[0] * f_s.v[0] + f_s.v[1] * f_s.v[1]) + (f_s.v[2] * f_s.v[2] + f_s.v[3] * f_s.v[3]);
-			if (ff > 0.0f) {
-				if (isfinite(pdf_w_i)) n_dot_l = dot3(wix, wiy, wiz, nx, ny, nz);
-				else { n_dot_l = 1.0f; pdf_w_i = 1.0f; }
-				recurse = n_dot_l > 0.0f;
-			}
-			if (recurse) {
-				float* e = stk + depth * SSB_STACK_FLOATS;
-#pragma unroll
-				for (int c = 0; c < 4; ++c) { e[c] = local.v[c]; e[4 + c] = f_s.v[c]; }
-				e[8] = n_dot_l; e[9] = pdf_w_i;
-				dx = wix; dy = wiy; dz = wiz;
-				ignore = cur_quad;
-				last_was_delta = false;  // the reference passes `false` unconditionally (renderer.cpp:248)
-				depth += 1;
-				// Dead-work skip (result-identical): with explicit light sampling the L() call at the last
-				// depth can add neither emission (last_was_delta == false) nor children: it returns 0 and
-				// hit_anything is already set.  No random numbers are drawn there either.
-				if (els && (uint32_t)depth + 1u >= P.max_depth) finish = true;  // rad = 0
-			} else {
-				rad = local; finish = true;
-			}
-		}
-
-		if (finish) {
-			// ---- unwind the recursion: radiance = local + ((child * n.l) * f_s) / pdf (renderer.cpp:248)
-			for (int d = depth - 1; d >= 0; --d) {
-				const float* e = stk + d * SSB_STACK_FLOATS;
-#pragma unroll
-				for (int c = 0; c < 4; ++c) rad.v[c] = e[c] + ((rad.v[c] * e[8]) * e[4 + c]) / e[9];
-			}
-			if (!P.flat_field) {
-#pragma unroll
-				for (int c = 0; c < 4; ++c) rad.v[c] = rad.v[c] * ff_scale;
-			}
-			// Color::specradflux_to_ciexyz (color.hpp:115-139)
-			Hero xb = spec_hero(S.pool, S.hdr->xbar, lambda_0, P.lambda_step);
-			Hero yb = spec_hero(S.pool, S.hdr->ybar, lambda_0, P.lambda_step);
-			Hero zb = spec_hero(S.pool, S.hdr->zbar, lambda_0, P.lambda_step);
-			float X = 0.0f, Y = 0.0f, Z = 0.0f;
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				X += (xb.v[c] * rad.v[c]) * P.lambda_step;
-				Y += (yb.v[c] * rad.v[c]) * P.lambda_step;
-				Z += (zb.v[c] * rad.v[c]) * P.lambda_step;
-			}
-			P.samples[out_index] = make_float4(X, Y, Z, hit_anything ? 1.0f : 0.0f);
-			alive = false;
 		}
 	}
 }
 
-// avg += double4(sample * 0.001f), in sample order (renderer.cpp:292-295)
-__global__ void ssb_accumulate_kernel(const float4* __restrict__ samples, double* __restrict__ accum,
-                                      uint32_t width, uint32_t x0, uint32_t y0, uint32_t rect_w, uint32_t rect_h,
-                                      uint32_t nsamp) {
-	uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t npix_rect = rect_w * rect_h;
+// Unwind the recursion of every sample of a pixel, convert to XYZ and accumulate, in sample order:
+//   radiance = local + ((child * n.l) * f_s) / pdf        (renderer.cpp:216,248)
+//   XYZ = specradflux_to_ciexyz(radiance, lambda_0)        (color.hpp:115-139)
+//   avg += double4(float4(XYZ, hit) * 0.001f)              (renderer.cpp:292-295)
+// One thread per pixel of the pass rectangle; lanes = neighbouring pixels, so every record array is read coalesced.
+__global__ void __launch_bounds__(128) ssb_finalize_kernel(const __grid_constant__ KParams P) {
+	const uint32_t npix_rect = P.rect_w * P.rect_h;
+	const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
 	if (pr >= npix_rect) return;
-	uint32_t pi = x0 + pr % rect_w, pj = y0 + pr / rect_w;
-	double* a = accum + 4 * ((size_t)pj * width + pi);
+	const DevHeader* hdr = reinterpret_cast<const DevHeader*>(P.blob);
+	const float* pool = reinterpret_cast<const float*>(P.blob + hdr->off_pool);
+	const DevSpectrum sx = hdr->xbar, sy = hdr->ybar, sz = hdr->zbar;
+	const uint32_t pi = P.x0 + pr % P.rect_w, pj = P.y0 + pr / P.rect_w;
+	double* a = P.accum + 4 * ((size_t)pj * P.width + pi);
 	double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
-	for (uint32_t k = 0; k < nsamp; ++k) {
-		float4 s = samples[(size_t)k * npix_rect + pr];
-		a0 += (double)(s.x * 0.001f); a1 += (double)(s.y * 0.001f);
-		a2 += (double)(s.z * 0.001f); a3 += (double)(s.w * 0.001f);
+	for (uint32_t kk = 0; kk < P.nsamp; ++kk) {
+		const size_t id = (size_t)kk * npix_rect + pr;
+		const float4 lf = P.leaf[id];
+		const float2 mt = P.meta[id];
+		const float lambda_0 = mt.x;
+		const int info = __float_as_int(mt.y);
+		const int nrec = info & 0xffff;
+		float r0 = lf.x, r1 = lf.y, r2 = lf.z, r3 = lf.w;
+		for (int d = nrec - 1; d >= 0; --d) {
+			const size_t rec = (size_t)d * P.total_work + id;
+			const float4 lo = P.stk_local[rec], f = P.stk_f[rec];
+			const float2 np = P.stk_np[rec];
+			r0 = lo.x + ((r0 * np.x) * f.x) / np.y;
+			r1 = lo.y + ((r1 * np.x) * f.y) / np.y;
+			r2 = lo.z + ((r2 * np.x) * f.z) / np.y;
+			r3 = lo.w + ((r3 * np.x) * f.w) / np.y;
+		}
+		if (!P.flat_field) {
+			const float s = P.ff[id];
+			r0 *= s; r1 *= s; r2 *= s; r3 *= s;
+		}
+		float rad[4] = { r0, r1, r2, r3 };
+		float X = 0.0f, Y = 0.0f, Z = 0.0f;
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			const float lambda = lambda_0 + (float)c * P.lambda_step;
+			X += (spec_sample(pool, sx, lambda) * rad[c]) * P.lambda_step;
+			Y += (spec_sample(pool, sy, lambda) * rad[c]) * P.lambda_step;
+			Z += (spec_sample(pool, sz, lambda) * rad[c]) * P.lambda_step;
+		}
+		const float hitf = (info >> 16) ? 1.0f : 0.0f;
+		if (P.samples) P.samples[id] = make_float4(X, Y, Z, hitf);
+		a0 += (double)(X * 0.001f); a1 += (double)(Y * 0.001f);
+		a2 += (double)(Z * 0.001f); a3 += (double)(hitf * 0.001f);
 	}
 	a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
 }

@@ -13,7 +13,8 @@ cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
 if [ "${2:-}" != "noprof" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/${TAG}_launches.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ssb_trace -s 2 -c 1 -f -o $OUT/${TAG}_trace \
+# one whole frame of bounce launches (depths 0..8) + its finalize, after two warm frames
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"ssb_bounce|ssb_finalize" -s 20 -c 10 -f -o $OUT/${TAG}_trace \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT | tail -12
 fi
