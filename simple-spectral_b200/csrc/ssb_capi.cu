@@ -175,7 +175,7 @@ int build_blob(ssb_ctx* c) {
 	hdr.off_lights = (uint32_t)off; off = align_up(off + c->lights.size() * sizeof(uint32_t), 16);
 	hdr.off_textures = (uint32_t)off; off = align_up(off + texs.size() * sizeof(DevTexture), 16);
 	hdr.off_pool = (uint32_t)off; off = align_up(off + pool.size() * sizeof(float), 16);
-	hdr.off_boxes = (uint32_t)off; off = align_up(off + c->quads.size() * 8 * sizeof(float), 16);
+	hdr.off_boxes = (uint32_t)off; off = align_up(off + c->quads.size() * 12 * sizeof(float), 16);
 	hdr.total_bytes = (uint32_t)off;
 	if (off > 160 * 1024) return fail(SSB_ERR_UNSUPPORTED, "scene tables (%zu bytes) exceed the shared-memory budget", off);
 
@@ -187,22 +187,48 @@ int build_blob(ssb_ctx* c) {
 	if (!texs.empty()) memcpy(blob.data() + hdr.off_textures, texs.data(), texs.size() * sizeof(DevTexture));
 	if (!pool.empty()) memcpy(blob.data() + hdr.off_pool, pool.data(), pool.size() * sizeof(float));
 	{
-		// conservative per-quad bounds for the culling phase of scene_intersect: the exact AABB of the quad's
-		// vertices expanded by 1e-4 of the scene diagonal (>> the rounding of the watertight test)
+		// conservative per-quad bounds for the filter phase of scene_intersect: the plane of the quad and its
+		// bounding rectangle in two in-plane axes, enlarged by 1e-4 of the scene diagonal (>> any rounding of the
+		// watertight test).  Non-planar or degenerate quads get an all-zero record, which the filter always passes.
 		float slo[3] = { INFINITY, INFINITY, INFINITY }, shi[3] = { -INFINITY, -INFINITY, -INFINITY };
 		for (const ssb_quad& q : c->quads)
 			for (int t = 0; t < 2; ++t) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) {
 				slo[k] = std::min(slo[k], q.tri[t].v[v].pos[k]); shi[k] = std::max(shi[k], q.tri[t].v[v].pos[k]);
 			}
-		double diag = std::sqrt((double)(shi[0] - slo[0]) * (shi[0] - slo[0]) + (double)(shi[1] - slo[1]) * (shi[1] - slo[1]) + (double)(shi[2] - slo[2]) * (shi[2] - slo[2]));
-		float margin = (float)(1e-4 * diag) + 1e-6f;
-		float* boxes = reinterpret_cast<float*>(blob.data() + hdr.off_boxes);
+		const double diag = std::sqrt((double)(shi[0] - slo[0]) * (shi[0] - slo[0]) + (double)(shi[1] - slo[1]) * (shi[1] - slo[1]) + (double)(shi[2] - slo[2]) * (shi[2] - slo[2]));
+		const double margin = 1e-4 * diag + 1e-6;
+		DevHeader* h = reinterpret_cast<DevHeader*>(blob.data());
+		h->cull_margin = (float)margin;
+		float* rec = reinterpret_cast<float*>(blob.data() + hdr.off_boxes);
 		for (size_t qi = 0; qi < c->quads.size(); ++qi) {
-			float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-			for (int t = 0; t < 2; ++t) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) {
-				lo[k] = std::min(lo[k], c->quads[qi].tri[t].v[v].pos[k]); hi[k] = std::max(hi[k], c->quads[qi].tri[t].v[v].pos[k]);
+			const ssb_quad& q = c->quads[qi];
+			double P[6][3];
+			for (int t = 0; t < 2; ++t) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) P[t * 3 + v][k] = q.tri[t].v[v].pos[k];
+			float* r = rec + 12 * qi;
+			for (int k = 0; k < 12; ++k) r[k] = 0.0f;
+			// plane through tri0 (double precision, from the vertices — not from the stored float normal)
+			double e1[3], e2[3], n[3];
+			for (int k = 0; k < 3; ++k) { e1[k] = P[1][k] - P[0][k]; e2[k] = P[2][k] - P[0][k]; }
+			n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+			double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), e1l = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+			if (!(nl > 1e-12 * diag * diag) || !(e1l > 0)) continue;  // degenerate: always a candidate
+			for (int k = 0; k < 3; ++k) n[k] /= nl;
+			double w = n[0] * P[0][0] + n[1] * P[0][1] + n[2] * P[0][2];
+			bool planar = true;
+			for (int v = 0; v < 6; ++v) if (std::fabs(n[0] * P[v][0] + n[1] * P[v][1] + n[2] * P[v][2] - w) > 1e-6 * diag) planar = false;
+			if (!planar) continue;
+			double a[3], b[3];
+			for (int k = 0; k < 3; ++k) a[k] = e1[k] / e1l;
+			b[0] = n[1] * a[2] - n[2] * a[1]; b[1] = n[2] * a[0] - n[0] * a[2]; b[2] = n[0] * a[1] - n[1] * a[0];
+			double ulo = INFINITY, uhi = -INFINITY, vlo = INFINITY, vhi = -INFINITY;
+			for (int v = 0; v < 6; ++v) {
+				double u = a[0] * P[v][0] + a[1] * P[v][1] + a[2] * P[v][2], vv = b[0] * P[v][0] + b[1] * P[v][1] + b[2] * P[v][2];
+				ulo = std::min(ulo, u); uhi = std::max(uhi, u); vlo = std::min(vlo, vv); vhi = std::max(vhi, vv);
 			}
-			for (int k = 0; k < 3; ++k) { boxes[8 * qi + k] = lo[k] - margin; boxes[8 * qi + 4 + k] = hi[k] + margin; }
+			double hu = 0.5 * (uhi - ulo) + margin, hv = 0.5 * (vhi - vlo) + margin, cu = 0.5 * (uhi + ulo), cv = 0.5 * (vhi + vlo);
+			r[0] = (float)n[0]; r[1] = (float)n[1]; r[2] = (float)n[2]; r[3] = (float)w;
+			r[4] = (float)(a[0] / hu); r[5] = (float)(a[1] / hu); r[6] = (float)(a[2] / hu); r[7] = (float)(cu / hu);
+			r[8] = (float)(b[0] / hv); r[9] = (float)(b[1] / hv); r[10] = (float)(b[2] / hv); r[11] = (float)(cv / hv);
 		}
 	}
 

@@ -52,8 +52,8 @@ struct DevHeader {
 	uint32_t nquads, nmaterials, nlights, ntextures;
 	uint32_t off_quads, off_materials, off_lights, off_textures, off_pool;  // byte offsets from blob start
 	uint32_t total_bytes;  // multiple of 16
-	uint32_t off_boxes;    // per quad: float lo[3], pad, hi[3], pad — conservative (expanded) bounds for culling
-	uint32_t pad;
+	uint32_t off_boxes;    // per quad: 3 x float4 conservative oriented bounds for culling (see scene_intersect)
+	float cull_margin;     // 1e-4 x scene diagonal
 	DevSpectrum xbar, ybar, zbar, basis_r, basis_g, basis_b;
 	float srgb_lut[256];  // Color::srgb_to_lrgb(v/255) for v = 0..255 (color.hpp:91-97), built with the host libm
 };
@@ -167,7 +167,7 @@ struct SceneView {
 	const uint32_t* lights;
 	const DevTexture* textures;
 	const float* pool;
-	const float4* boxes;  // 2 x float4 per quad
+	const float4* boxes;  // 3 x float4 per quad: plane (n,w), scaled in-plane axes (a,ca), (b,cb)
 };
 
 // _Spectrum::_sample_linear / _sample_nearest (spectrum.cpp:29-60)
@@ -407,15 +407,16 @@ __device__ __forceinline__ bool tri_intersect(const ssb_tri& t, const RayConst& 
 //
 // The reference scans every primitive with the full watertight test.  Here the scan is split in two
 // phases that give the SAME hit record:
-//   1. a slab test of the ray against each quad's bounding box — expanded by 1e-4 of the scene diagonal,
-//      orders of magnitude more than the watertight test's own rounding, so it can only reject quads the
-//      exact test would reject — run converged by all lanes (box data is a shared-memory broadcast),
-//      producing a per-lane bit mask of candidate quads;
+//   1. a conservative filter per quad, run converged by all lanes (quad data is a shared-memory broadcast):
+//      intersect the ray with the quad's plane, and test the plane point against the quad's bounding rectangle
+//      in the plane's own axes, enlarged by 1e-4 of the scene diagonal — orders of magnitude more than the
+//      rounding of the watertight test or of this filter, so it can only reject quads the exact test would
+//      reject.  Rays (nearly) parallel to the plane and non-planar quads always pass.  The result is a per-lane
+//      bit mask of candidate quads: almost always just the quad that is hit.
 //   2. the exact test (tri0, then tri1) only for the lane's candidates, in list order (lowest bit first), so
-//      ties and the `ignore` rule resolve exactly as in the reference.  Lanes iterate over their own
-//      candidates in lock-step: the trip count is the max candidate count in the warp (~2-4), not 2x19.
-// The culling arithmetic (explicit fma, approximate reciprocals) is not part of the reference's arithmetic
-// and never touches the hit record.
+//      ties and the `ignore` rule resolve exactly as in the reference.
+// The filter arithmetic (explicit fma, approximate reciprocal) is not part of the reference's arithmetic and
+// never touches the hit record.
 #ifndef SSB_CULL
 #define SSB_CULL 1
 #endif
@@ -426,25 +427,21 @@ __device__ __noinline__ void scene_intersect(const SceneView& S, float eps, int 
 	hit.bx = hit.by = hit.bz = 0.0f;
 	const int nq = (int)S.hdr->nquads;
 #if SSB_CULL
-	// per-ray reciprocal direction, clamped so that axis-parallel rays give finite slab distances
-	float ix = (fabsf(dx) < 1e-30f) ? copysignf(1e30f, dx) : rcp_approx(dx);
-	float iy = (fabsf(dy) < 1e-30f) ? copysignf(1e30f, dy) : rcp_approx(dy);
-	float iz = (fabsf(dz) < 1e-30f) ? copysignf(1e30f, dz) : rcp_approx(dz);
-	float bx = -ox * ix, by = -oy * iy, bz = -oz * iz;
+	const float tmargin = S.hdr->cull_margin;
 	for (int base = 0; base < nq; base += 32) {
 		const int cnt = min(32, nq - base);
 		unsigned cand = 0u;
 		for (int j = 0; j < cnt; ++j) {
-			const float4 lo = S.boxes[2 * (base + j)], hi = S.boxes[2 * (base + j) + 1];
-			float t0x = __fmaf_rn(lo.x, ix, bx), t1x = __fmaf_rn(hi.x, ix, bx);
-			float t0y = __fmaf_rn(lo.y, iy, by), t1y = __fmaf_rn(hi.y, iy, by);
-			float t0z = __fmaf_rn(lo.z, iz, bz), t1z = __fmaf_rn(hi.z, iz, bz);
-			float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
-			float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-			// keep unless the ray provably misses the expanded box or the box lies entirely behind the origin;
-			// any NaN (0*inf cannot occur with the clamp, but be safe) keeps the quad
-			bool miss = (tmin > tmax) || (tmax < 0.0f);
-			cand |= miss ? 0u : (1u << j);
+			const float4 pl = S.boxes[3 * (base + j)], ua = S.boxes[3 * (base + j) + 1], vb = S.boxes[3 * (base + j) + 2];
+			const float nd = __fmaf_rn(pl.x, dx, __fmaf_rn(pl.y, dy, pl.z * dz));
+			const float no = __fmaf_rn(pl.x, ox, __fmaf_rn(pl.y, oy, pl.z * oz));
+			const float tp = (pl.w - no) * rcp_approx(nd);
+			const float px = __fmaf_rn(tp, dx, ox), py = __fmaf_rn(tp, dy, oy), pz = __fmaf_rn(tp, dz, oz);
+			const float u = __fmaf_rn(ua.x, px, __fmaf_rn(ua.y, py, __fmaf_rn(ua.z, pz, -ua.w)));
+			const float v = __fmaf_rn(vb.x, px, __fmaf_rn(vb.y, py, __fmaf_rn(vb.z, pz, -vb.w)));
+			// written so that any NaN keeps the quad (comparisons with NaN are false -> `reject` stays false)
+			const bool reject = (fabsf(nd) >= 1e-6f) && ((tp < -tmargin) || (fabsf(u) > 1.0f) || (fabsf(v) > 1.0f));
+			cand |= reject ? 0u : (1u << j);
 		}
 		if (ignore >= base && ignore < base + 32) cand &= ~(1u << (ignore - base));
 		while (cand) {

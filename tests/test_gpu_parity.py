@@ -124,3 +124,16 @@ def test_gpu_full_size_properties():
     ref_mean = np.array(json.load(open(os.path.join(pu.GOLDEN, "golden_index.json")))["cornell-srgb_ours1931_128x128_spp16_seed1"]["mean"])
     got_mean = xg.mean(axis=(0, 1))
     assert np.allclose(got_mean, ref_mean, rtol=0.02), (got_mean, ref_mean)
+
+
+def test_gpu_config2_bit_exact_vs_oracle():
+    """BASELINE.json configs[1] at full size: cornell-srgb 512x512 spp64 (16.8 M samples) — the CUDA accumulators equal
+    the oracle's bit for bit (the oracle runs multi-threaded on the box's host cores)."""
+    _skip_if_no_assets("cornell-srgb", "ours1931")
+    flat = pu.load_flat("cornell-srgb", "ours1931")
+    opt = pu.options("ours1931", 512, 512, 64, seed=1)
+    with pu.gpu_context(flat) as ctx:
+        ctx.render(opt)
+        acc_g = ctx.read_accum(512, 512)
+    acc_o, _, _ = pu.oracle_render(flat, opt)
+    assert pu.bits_equal(acc_g, acc_o), f"max rel {pu.rel_err(acc_g, acc_o).max()}"

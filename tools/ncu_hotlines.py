@@ -7,7 +7,13 @@ from collections import defaultdict
 
 src_csv, nvd, kern = sys.argv[1:4]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-rows = list(csv.reader(open(src_csv)))
+rows_all = list(csv.reader(open(src_csv)))
+# the page may hold several launches ("Kernel Name" row starts each); pick one with SSB_LAUNCH (default 0)
+starts = [i for i, r in enumerate(rows_all) if r and r[0] == "Kernel Name"]
+which = int(__import__("os").environ.get("SSB_LAUNCH", "0"))
+lo = starts[which]; hi = starts[which + 1] if which + 1 < len(starts) else len(rows_all)
+rows = rows_all[lo:hi]
+print("launch", which, "of", len(starts), ":", rows[0][1])
 hdr = rows[1]
 ia, ie, it, ins = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 ino = hdr.index("stall_no_inst") if "stall_no_inst" in hdr else None
