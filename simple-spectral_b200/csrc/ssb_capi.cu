@@ -175,7 +175,7 @@ int build_blob(ssb_ctx* c) {
 	hdr.off_lights = (uint32_t)off; off = align_up(off + c->lights.size() * sizeof(uint32_t), 16);
 	hdr.off_textures = (uint32_t)off; off = align_up(off + texs.size() * sizeof(DevTexture), 16);
 	hdr.off_pool = (uint32_t)off; off = align_up(off + pool.size() * sizeof(float), 16);
-	hdr.off_boxes = (uint32_t)off; off = align_up(off + c->quads.size() * 12 * sizeof(float), 16);
+	hdr.off_boxes = (uint32_t)off; off = align_up(off + c->quads.size() * 16 * sizeof(float), 16);
 	hdr.total_bytes = (uint32_t)off;
 	if (off > 160 * 1024) return fail(SSB_ERR_UNSUPPORTED, "scene tables (%zu bytes) exceed the shared-memory budget", off);
 
@@ -204,8 +204,8 @@ int build_blob(ssb_ctx* c) {
 			const ssb_quad& q = c->quads[qi];
 			double P[6][3];
 			for (int t = 0; t < 2; ++t) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) P[t * 3 + v][k] = q.tri[t].v[v].pos[k];
-			float* r = rec + 12 * qi;
-			for (int k = 0; k < 12; ++k) r[k] = 0.0f;
+			float* r = rec + 16 * qi;
+			for (int k = 0; k < 16; ++k) r[k] = 0.0f;
 			// plane through tri0 (double precision, from the vertices — not from the stored float normal)
 			double e1[3], e2[3], n[3];
 			for (int k = 0; k < 3; ++k) { e1[k] = P[1][k] - P[0][k]; e2[k] = P[2][k] - P[0][k]; }
@@ -229,6 +229,24 @@ int build_blob(ssb_ctx* c) {
 			r[0] = (float)n[0]; r[1] = (float)n[1]; r[2] = (float)n[2]; r[3] = (float)w;
 			r[4] = (float)(a[0] / hu); r[5] = (float)(a[1] / hu); r[6] = (float)(a[2] / hu); r[7] = (float)(cu / hu);
 			r[8] = (float)(b[0] / hv); r[9] = (float)(b[1] / hv); r[10] = (float)(b[2] / hv); r[11] = (float)(cv / hv);
+			// which triangle: signed distance to the shared diagonal v00-v11 (tri0 = v00,v10,v11; tri1 = v00,v11,v01), in units
+			// of the margin, as a function of the scaled (u,v).  Only when the two triangles really share that diagonal and lie
+			// on opposite sides of it; otherwise the record stays 0 and both triangles are always tested.
+			bool shared = true;
+			for (int k = 0; k < 3; ++k) shared = shared && q.tri[1].v[0].pos[k] == q.tri[0].v[0].pos[k] && q.tri[1].v[1].pos[k] == q.tri[0].v[2].pos[k];
+			auto uv = [&](int v, double& U, double& V) { U = a[0] * P[v][0] + a[1] * P[v][1] + a[2] * P[v][2]; V = b[0] * P[v][0] + b[1] * P[v][1] + b[2] * P[v][2]; };
+			double u00, v00, u10, v10, u11, v11, u01, v01;
+			uv(0, u00, v00); uv(1, u10, v10); uv(2, u11, v11); uv(5, u01, v01);
+			double ex = u11 - u00, ey = v11 - v00, el = std::sqrt(ex * ex + ey * ey);
+			if (shared && el > 0) {
+				double nx2 = ey / el, ny2 = -ex / el;  // unit normal of the diagonal
+				double d10 = nx2 * (u10 - u00) + ny2 * (v10 - v00), d01 = nx2 * (u01 - u00) + ny2 * (v01 - v00);
+				if (d10 < 0) { nx2 = -nx2; ny2 = -ny2; d10 = -d10; d01 = -d01; }
+				if (d10 > margin && d01 < -margin) {
+					r[12] = (float)(nx2 * hu / margin); r[13] = (float)(ny2 * hv / margin);
+					r[14] = (float)((nx2 * (cu - u00) + ny2 * (cv - v00)) / margin);
+				}
+			}
 		}
 	}
 

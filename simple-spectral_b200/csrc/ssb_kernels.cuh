@@ -52,7 +52,7 @@ struct DevHeader {
 	uint32_t nquads, nmaterials, nlights, ntextures;
 	uint32_t off_quads, off_materials, off_lights, off_textures, off_pool;  // byte offsets from blob start
 	uint32_t total_bytes;  // multiple of 16
-	uint32_t off_boxes;    // per quad: 3 x float4 conservative oriented bounds for culling (see scene_intersect)
+	uint32_t off_boxes;    // per quad: 4 x float4 — plane (n,w), scaled in-plane axes (a,ca), (b,cb), diagonal (A,B,C,0)
 	float cull_margin;     // 1e-4 x scene diagonal
 	DevSpectrum xbar, ybar, zbar, basis_r, basis_g, basis_b;
 	float srgb_lut[256];  // Color::srgb_to_lrgb(v/255) for v = 0..255 (color.hpp:91-97), built with the host libm
@@ -160,14 +160,19 @@ __device__ __noinline__ float sinf_x(float x) { return ssbm::sinf_exact(x); }
 __device__ __noinline__ float cosf_x(float x) { return ssbm::cosf_exact(x); }
 
 // ------------------------------------------------------------------ shared-memory view of the blob
+// The blob lives in dynamic shared memory.  It is declared at namespace scope and reached through these accessors
+// (not through generic pointers carried in a struct) so that every load — also inside the non-inlined helpers —
+// is a shared-memory load (LDS) rather than a generic one (ncu on the first wavefront build: LD.E.128 + R2UR
+// in the intersection scan).
+extern __shared__ __align__(128) unsigned char ssb_smem[];
 struct SceneView {
-	const DevHeader* hdr;
-	const ssb_quad* quads;
-	const DevMaterial* materials;
-	const uint32_t* lights;
-	const DevTexture* textures;
-	const float* pool;
-	const float4* boxes;  // 3 x float4 per quad: plane (n,w), scaled in-plane axes (a,ca), (b,cb)
+	__device__ __forceinline__ const DevHeader* hdr() const { return reinterpret_cast<const DevHeader*>(ssb_smem); }
+	__device__ __forceinline__ const ssb_quad* quads() const { return reinterpret_cast<const ssb_quad*>(ssb_smem + hdr()->off_quads); }
+	__device__ __forceinline__ const DevMaterial* materials() const { return reinterpret_cast<const DevMaterial*>(ssb_smem + hdr()->off_materials); }
+	__device__ __forceinline__ const uint32_t* lights() const { return reinterpret_cast<const uint32_t*>(ssb_smem + hdr()->off_lights); }
+	__device__ __forceinline__ const DevTexture* textures() const { return reinterpret_cast<const DevTexture*>(ssb_smem + hdr()->off_textures); }
+	__device__ __forceinline__ const float* pool() const { return reinterpret_cast<const float*>(ssb_smem + hdr()->off_pool); }
+	__device__ __forceinline__ const float4* boxes() const { return reinterpret_cast<const float4*>(ssb_smem + hdr()->off_boxes); }
 };
 
 // _Spectrum::_sample_linear / _sample_nearest (spectrum.cpp:29-60)
@@ -187,8 +192,8 @@ __device__ __forceinline__ float spec_sample(const float* pool, const DevSpectru
 	return val0 * (1.0f - frac) + val1 * frac;
 }
 // _Spectrum::operator[] (spectrum.cpp:61-67)
-__device__ __noinline__ float4 spec_hero4(const float* pool, const DevSpectrum* sp, float lambda_0, float step) {
-	const DevSpectrum s = *sp;
+__device__ __noinline__ float4 spec_hero4(DevSpectrum s, float lambda_0, float step) {
+	const float* pool = SceneView().pool();
 	float4 h;
 	h.x = spec_sample(pool, s, lambda_0 + 0.0f * step);
 	h.y = spec_sample(pool, s, lambda_0 + 1.0f * step);
@@ -196,8 +201,8 @@ __device__ __noinline__ float4 spec_hero4(const float* pool, const DevSpectrum* 
 	h.w = spec_sample(pool, s, lambda_0 + 3.0f * step);
 	return h;
 }
-__device__ __forceinline__ Hero spec_hero(const float* pool, const DevSpectrum& s, float lambda_0, float step) {
-	float4 v = spec_hero4(pool, &s, lambda_0, step);
+__device__ __forceinline__ Hero spec_hero(const float*, const DevSpectrum& s, float lambda_0, float step) {
+	float4 v = spec_hero4(s, lambda_0, step);
 	Hero h;
 	h.v[0] = v.x; h.v[1] = v.y; h.v[2] = v.z; h.v[3] = v.w;
 	return h;
@@ -312,19 +317,19 @@ __device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, f
 template <int UPS>
 __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneView& S, const DevMaterial& m,
                                                 float st_x, float st_y, float lambda_0) {
-	if (m.albedo_mode == SSB_ALBEDO_CONSTANT) return spec_hero(S.pool, m.albedo, lambda_0, P.lambda_step);
-	const DevTexture tex = S.textures[m.texture];
+	if (m.albedo_mode == SSB_ALBEDO_CONSTANT) return spec_hero(S.pool(), m.albedo, lambda_0, P.lambda_step);
+	const DevTexture tex = S.textures()[m.texture];
 	float index_x = st_x * (float)tex.width;
 	float index_y = (float)tex.height - st_y * (float)tex.height;
 	int i = (int)floorf(index_x), j = (int)floorf(index_y);
 	i = max(i, 0); i = min(i, (int)tex.width - 1);
 	j = max(j, 0); j = min(j, (int)tex.height - 1);
 	uchar4 px = __ldg(tex.rgba + ((size_t)j * tex.width + (size_t)i));
-	float r = S.hdr->srgb_lut[px.x], g = S.hdr->srgb_lut[px.y], b = S.hdr->srgb_lut[px.z];
+	float r = S.hdr()->srgb_lut[px.x], g = S.hdr()->srgb_lut[px.y], b = S.hdr()->srgb_lut[px.z];
 	if (UPS == SSB_UPSAMPLE_OURS) {
-		Hero br = spec_hero(S.pool, S.hdr->basis_r, lambda_0, P.lambda_step);
-		Hero bg = spec_hero(S.pool, S.hdr->basis_g, lambda_0, P.lambda_step);
-		Hero bb = spec_hero(S.pool, S.hdr->basis_b, lambda_0, P.lambda_step);
+		Hero br = spec_hero(S.pool(), S.hdr()->basis_r, lambda_0, P.lambda_step);
+		Hero bg = spec_hero(S.pool(), S.hdr()->basis_g, lambda_0, P.lambda_step);
+		Hero bb = spec_hero(S.pool(), S.hdr()->basis_b, lambda_0, P.lambda_step);
 		Hero h;
 #pragma unroll
 		for (int k = 0; k < 4; ++k) h.v[k] = (r * br.v[k] + g * bg.v[k]) + b * bb.v[k];
@@ -411,8 +416,9 @@ __device__ __forceinline__ bool tri_intersect(const ssb_tri& t, const RayConst& 
 //      intersect the ray with the quad's plane, and test the plane point against the quad's bounding rectangle
 //      in the plane's own axes, enlarged by 1e-4 of the scene diagonal — orders of magnitude more than the
 //      rounding of the watertight test or of this filter, so it can only reject quads the exact test would
-//      reject.  Rays (nearly) parallel to the plane and non-planar quads always pass.  The result is a per-lane
-//      bit mask of candidate quads: almost always just the quad that is hit.
+//      reject.  The side of the quad's diagonal (again with that margin) tells which of its two triangles can be
+//      hit.  Rays (nearly) parallel to the plane and non-planar quads always pass.  The result is a per-lane bit
+//      mask of candidate triangles: almost always just the one that is hit.
 //   2. the exact test (tri0, then tri1) only for the lane's candidates, in list order (lowest bit first), so
 //      ties and the `ignore` rule resolve exactly as in the reference.
 // The filter arithmetic (explicit fma, approximate reciprocal) is not part of the reference's arithmetic and
@@ -425,39 +431,46 @@ __device__ __noinline__ void scene_intersect(const SceneView& S, float eps, int 
 	const RayConst rc = ray_setup(ox, oy, oz, dx, dy, dz);
 	hit.quad = -1; hit.tri = 0; hit.dist = __int_as_float(0x7f800000);
 	hit.bx = hit.by = hit.bz = 0.0f;
-	const int nq = (int)S.hdr->nquads;
+	const int nq = (int)S.hdr()->nquads;
 #if SSB_CULL
-	const float tmargin = S.hdr->cull_margin;
+	const float tmargin = S.hdr()->cull_margin;
 	for (int base = 0; base < nq; base += 32) {
 		const int cnt = min(32, nq - base);
-		unsigned cand = 0u;
+		unsigned cand0 = 0u, cand1 = 0u;  // quads whose tri0 / tri1 may be hit
 		for (int j = 0; j < cnt; ++j) {
-			const float4 pl = S.boxes[3 * (base + j)], ua = S.boxes[3 * (base + j) + 1], vb = S.boxes[3 * (base + j) + 2];
+			const float4* rec = S.boxes() + 4 * (base + j);
+			const float4 pl = rec[0], ua = rec[1], vb = rec[2], dg = rec[3];
 			const float nd = __fmaf_rn(pl.x, dx, __fmaf_rn(pl.y, dy, pl.z * dz));
 			const float no = __fmaf_rn(pl.x, ox, __fmaf_rn(pl.y, oy, pl.z * oz));
 			const float tp = (pl.w - no) * rcp_approx(nd);
 			const float px = __fmaf_rn(tp, dx, ox), py = __fmaf_rn(tp, dy, oy), pz = __fmaf_rn(tp, dz, oz);
 			const float u = __fmaf_rn(ua.x, px, __fmaf_rn(ua.y, py, __fmaf_rn(ua.z, pz, -ua.w)));
 			const float v = __fmaf_rn(vb.x, px, __fmaf_rn(vb.y, py, __fmaf_rn(vb.z, pz, -vb.w)));
-			// written so that any NaN keeps the quad (comparisons with NaN are false -> `reject` stays false)
-			const bool reject = (fabsf(nd) >= 1e-6f) && ((tp < -tmargin) || (fabsf(u) > 1.0f) || (fabsf(v) > 1.0f));
-			cand |= reject ? 0u : (1u << j);
+			const float sd = __fmaf_rn(dg.x, u, __fmaf_rn(dg.y, v, dg.z));  // signed distance to the diagonal / margin
+			// written so that any NaN keeps the quad (comparisons with NaN are false)
+			const bool par = !(fabsf(nd) >= 1e-6f);  // (nearly) parallel to the plane, or all-zero record: keep both
+			const bool out = (tp < -tmargin) | (fabsf(u) > 1.0f) | (fabsf(v) > 1.0f);
+			const bool keep0 = par | (!out & !(sd < -1.0f));  // tri0 lies on the sd >= 0 side of the diagonal
+			const bool keep1 = par | (!out & !(sd > 1.0f));
+			cand0 |= keep0 ? (1u << j) : 0u;
+			cand1 |= keep1 ? (1u << j) : 0u;
 		}
-		if (ignore >= base && ignore < base + 32) cand &= ~(1u << (ignore - base));
-		while (cand) {
-			const int q = base + (__ffs(cand) - 1);
-			cand &= cand - 1u;
-			const ssb_quad& quad = S.quads[q];
-#pragma unroll 1
-			for (int tt = 0; tt < 2; ++tt) {  // tri0, then tri1 only if tri0 missed (geometry.cpp:131-133)
-				if (tri_intersect(quad.tri[tt], rc, eps, hit)) { hit.quad = q; hit.tri = tt; break; }
-			}
+		if (ignore >= base && ignore < base + 32) { cand0 &= ~(1u << (ignore - base)); cand1 &= ~(1u << (ignore - base)); }
+		// one exact triangle test per iteration: (quad, tri0) before (quad, tri1), quads in list order; tri1 is skipped when
+		// tri0 was hit (PrimQuad::intersect, geometry.cpp:131-133)
+		while (cand0 | cand1) {
+			const unsigned bit = (cand0 | cand1) & (0u - (cand0 | cand1));
+			const int q = base + (__ffs(bit) - 1);
+			const int tt = (cand0 & bit) ? 0 : 1;
+			cand0 &= ~bit;
+			if (tt == 1) cand1 &= ~bit;
+			if (tri_intersect(S.quads()[q].tri[tt], rc, eps, hit)) { hit.quad = q; hit.tri = tt; cand1 &= ~bit; }
 		}
 	}
 #else
 	for (int q = 0; q < nq; ++q) {
 		if (q == ignore) continue;
-		const ssb_quad& quad = S.quads[q];
+		const ssb_quad& quad = S.quads()[q];
 		if (tri_intersect(quad.tri[0], rc, eps, hit)) { hit.quad = q; hit.tri = 0; }
 		else if (tri_intersect(quad.tri[1], rc, eps, hit)) { hit.quad = q; hit.tri = 1; }
 	}
@@ -481,8 +494,9 @@ __device__ __forceinline__ void func_bar(float xx, float xy, float xz, float yx,
 
 __device__ __noinline__ float cos_double_cold(float x) { return (float)cos((double)x); }  // degenerate triangles only
 
-__device__ __noinline__ void sample_spherical_triangle(const ssb_tri& t, float px, float py, float pz, float r0, float r1,
+__device__ __noinline__ void sample_spherical_triangle(int light_quad, int light_tri, float px, float py, float pz, float r0, float r1,
                                                        float& wx, float& wy, float& wz, float& pdf) {
+	const ssb_tri& t = SceneView().quads()[light_quad].tri[light_tri];
 	// unit vectors toward the vertices: glm::normalize(v - from) = v * (1/sqrt(dot))
 	float Ax = t.v[0].pos[0] - px, Ay = t.v[0].pos[1] - py, Az = t.v[0].pos[2] - pz;
 	float Bx = t.v[1].pos[0] - px, By = t.v[1].pos[1] - py, Bz = t.v[1].pos[2] - pz;
@@ -600,20 +614,12 @@ __device__ __forceinline__ void stage_blob(unsigned char* smem, const unsigned c
 template <bool FIRST, int UPS>
 __global__ void __launch_bounds__(SSB_BOUNCE_THREADS, SSB_BOUNCE_MIN_BLOCKS)
 ssb_bounce_kernel(const __grid_constant__ KParams P) {
-	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long blob_bar;
 	{
 		const DevHeader* gh = reinterpret_cast<const DevHeader*>(P.blob);
-		stage_blob(smem_raw, P.blob, __ldg(&gh->total_bytes), &blob_bar);
+		stage_blob(ssb_smem, P.blob, __ldg(&gh->total_bytes), &blob_bar);
 	}
-	SceneView S;
-	S.hdr = reinterpret_cast<const DevHeader*>(smem_raw);
-	S.quads = reinterpret_cast<const ssb_quad*>(smem_raw + S.hdr->off_quads);
-	S.materials = reinterpret_cast<const DevMaterial*>(smem_raw + S.hdr->off_materials);
-	S.lights = reinterpret_cast<const uint32_t*>(smem_raw + S.hdr->off_lights);
-	S.textures = reinterpret_cast<const DevTexture*>(smem_raw + S.hdr->off_textures);
-	S.pool = reinterpret_cast<const float*>(smem_raw + S.hdr->off_pool);
-	S.boxes = reinterpret_cast<const float4*>(smem_raw + S.hdr->off_boxes);
+	const SceneView S;
 
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -682,9 +688,9 @@ ssb_bounce_kernel(const __grid_constant__ KParams P) {
 			if (hit.quad >= 0) {
 				hit_anything = true;
 				const int cur_quad = hit.quad;
-				const ssb_quad& quad = S.quads[cur_quad];
+				const ssb_quad& quad = S.quads()[cur_quad];
 				const ssb_tri& tri = quad.tri[hit.tri];
-				const DevMaterial& m = S.materials[quad.material];
+				const DevMaterial& m = S.materials()[quad.material];
 				const float nx = tri.normal[0], ny = tri.normal[1], nz = tri.normal[2];
 				const float st_x = (hit.bx * tri.v[0].st[0] + hit.by * tri.v[1].st[0]) + hit.bz * tri.v[2].st[0];
 				const float st_y = (hit.bx * tri.v[0].st[1] + hit.by * tri.v[1].st[1]) + hit.bz * tri.v[2].st[1];
@@ -692,7 +698,7 @@ ssb_bounce_kernel(const __grid_constant__ KParams P) {
 				local.v[0] = local.v[1] = local.v[2] = local.v[3] = 0.0f;
 				// emission: last_was_delta is true only for the camera ray (the reference recurses with `false`, :248)
 				if (!els || (FIRST && !P.indirect_only)) {
-					Hero e = spec_hero(S.pool, m.emission, lambda_0, P.lambda_step);
+					Hero e = spec_hero(S.pool(), m.emission, lambda_0, P.lambda_step);
 #pragma unroll
 					for (int c = 0; c < 4; ++c) local.v[c] = local.v[c] + e.v[c];
 				}
@@ -708,23 +714,23 @@ ssb_bounce_kernel(const __grid_constant__ KParams P) {
 					}
 					if (els && (!P.indirect_only || !FIRST)) {
 						// ---- direct lighting (renderer.cpp:182-220; Scene::get_rand_toward_light, scene.cpp:417-431)
-						uint32_t li = rand_choice(rng, S.hdr->nlights);
-						const int light_quad = (int)S.lights[li];
-						const ssb_quad& lq = S.quads[light_quad];
-						const ssb_tri& lt = (rand_1f(rng) <= 0.5f) ? lq.tri[0] : lq.tri[1];
+						uint32_t li = rand_choice(rng, S.hdr()->nlights);
+						const int light_quad = (int)S.lights()[li];
+						const ssb_quad& lq = S.quads()[light_quad];
+						const int lt = (rand_1f(rng) <= 0.5f) ? 0 : 1;
 						float r0 = rand_1f(rng);
 						float r1 = rand_1f(rng);
 						float sx, sy, sz, pdf;
-						sample_spherical_triangle(lt, hx, hy, hz, r0, r1, sx, sy, sz, pdf);
+						sample_spherical_triangle(light_quad, lt, hx, hy, hz, r0, r1, sx, sy, sz, pdf);
 						pdf *= 0.5f;
-						pdf /= (float)S.hdr->nlights;
+						pdf /= (float)S.hdr()->nlights;
 						const float l_ndl = dot3(sx, sy, sz, nx, ny, nz);
 						if (l_ndl > 0.0f) {
 							Hit hs;
 							scene_intersect(S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
 							if (hs.quad == light_quad) {
-								const DevMaterial& lm = S.materials[lq.material];
-								Hero emitted = spec_hero(S.pool, lm.emission, lambda_0, P.lambda_step);
+								const DevMaterial& lm = S.materials()[lq.material];
+								Hero emitted = spec_hero(S.pool(), lm.emission, lambda_0, P.lambda_step);
 #pragma unroll
 								for (int c = 0; c < 4; ++c) {
 									float fe = (m.kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;  // MaterialMirror::evaluate_bsdf = 0
