@@ -602,11 +602,12 @@ __device__ __forceinline__ void stage_blob(unsigned char* smem, const unsigned c
 	}
 }
 
+// 256 threads x 3 CTAs = 24 warps/SM at 80 registers: best of the on-box sweep (profiles/r1f_tune.txt)
 #ifndef SSB_BOUNCE_THREADS
-#define SSB_BOUNCE_THREADS 128
+#define SSB_BOUNCE_THREADS 256
 #endif
 #ifndef SSB_BOUNCE_MIN_BLOCKS
-#define SSB_BOUNCE_MIN_BLOCKS 4
+#define SSB_BOUNCE_MIN_BLOCKS 3
 #endif
 
 // One bounce of every live path at depth P.depth: the body of the reference's lambda L (renderer.cpp:147-255).
@@ -849,6 +850,17 @@ __global__ void __launch_bounds__(128) ssb_finalize_kernel(const __grid_constant
 			const size_t rec = (size_t)d * P.total_work + id;
 			const float4 lo = P.stk_local[rec], f = P.stk_f[rec];
 			const float2 np = P.stk_np[rec];
+			// Exact shortcut: the child radiance is +0 in all four channels (miss / skipped last depth — the common
+			// case at the deepest record) and n.l, pdf are positive finite, f_s non-negative finite: then
+			// ((+0*n.l)*f_s)/pdf is +0 and local + (+0) == local bit for bit (local is never -0: it is a sum that
+			// starts at +0).  Saves four IEEE divisions that would take the zero-numerator slow path.
+			if (__float_as_uint(r0) == 0u && __float_as_uint(r1) == 0u && __float_as_uint(r2) == 0u && __float_as_uint(r3) == 0u &&
+			    np.x > 0.0f && np.x < __int_as_float(0x7f800000) && np.y > 0.0f && np.y < __int_as_float(0x7f800000) &&
+			    f.x >= 0.0f && f.y >= 0.0f && f.z >= 0.0f && f.w >= 0.0f &&
+			    f.x < __int_as_float(0x7f800000) && f.y < __int_as_float(0x7f800000) && f.z < __int_as_float(0x7f800000) && f.w < __int_as_float(0x7f800000)) {
+				r0 = lo.x; r1 = lo.y; r2 = lo.z; r3 = lo.w;
+				continue;
+			}
 			r0 = lo.x + ((r0 * np.x) * f.x) / np.y;
 			r1 = lo.y + ((r1 * np.x) * f.y) / np.y;
 			r2 = lo.z + ((r2 * np.x) * f.z) / np.y;

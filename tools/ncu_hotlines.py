@@ -67,7 +67,12 @@ if reg:
         name, r = item.split(":"); lo, hi = r.split("-"); regs.append((name, int(lo), int(hi)))
     out = defaultdict(lambda: [0, 0, 0])
     for (f, l), a in agg.items():
-        name = f if f != "ssb_kernels.cuh" else next((n for n, lo, hi in regs if lo <= l <= hi), "other")
+        # nvdisasm's file attribution is unreliable for inlined device functions (it often names the wrong one of our
+        # two headers); line numbers are right.  SSB_LINES_ONLY=1: classify by line number alone.
+        if os.environ.get("SSB_LINES_ONLY") and f in ("ssb_kernels.cuh", "ssb_math.cuh"):
+            name = next((n for n, lo, hi in regs if lo <= l <= hi), "other")
+        else:
+            name = f if f != "ssb_kernels.cuh" else next((n for n, lo, hi in regs if lo <= l <= hi), "other")
         o = out[name]; o[0] += a[0]; o[1] += a[1]; o[2] += a[2]
     print("\nregions:")
     for name, o in sorted(out.items(), key=lambda kv: -kv[1][0]):
