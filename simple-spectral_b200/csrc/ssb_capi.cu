@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -286,6 +287,10 @@ int validate_options(const ssb_options* o, uint32_t& x1, uint32_t& y1, uint32_t&
 }
 
 const size_t kWaveBudgetBytes = (size_t)12 << 30;  // device memory for the path state + fold records of one pass
+// counters, cleared once per pass: queue lengths [D+2] | hits per depth [D] | per-depth per-quad counts and cursors
+const size_t kCountsOff = 0, kNhitsOff = SSB_MAX_DEPTH + 2, kBinCountOff = kNhitsOff + SSB_MAX_DEPTH,
+             kBinCursorOff = kBinCountOff + (size_t)SSB_MAX_DEPTH * SSB_MAX_QUADS,
+             kCounterWords = kBinCursorOff + (size_t)SSB_MAX_DEPTH * SSB_MAX_QUADS;
 
 }  // namespace
 
@@ -328,7 +333,7 @@ int ssb_create(int device, ssb_ctx** out) {
 	SSB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
 	SSB_CUDA(cudaEventCreate(&c->ev_begin)); SSB_CUDA(cudaEventCreate(&c->ev_end));
-	SSB_CUDA(cudaMalloc(&c->d_counts, (SSB_MAX_DEPTH + 2) * sizeof(uint32_t)));
+	SSB_CUDA(cudaMalloc(&c->d_counts, kCounterWords * sizeof(uint32_t)));
 	*out = c;
 	return SSB_OK;
 }
@@ -476,7 +481,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 
 	// ---- size one pass: N = npix_rect * chunk samples share the wavefront buffers
 	const uint32_t nrec_depths = o->max_depth > 1 ? o->max_depth - 1 : 1;
-	const size_t bytes_per_sample = 2 * (16 + 16 + 16 + 4) + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4;
+	const size_t bytes_per_sample = 2 * (16 + 16 + 16 + 4) + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (16 + 4 + 4);
 	const size_t max_samples = std::min<size_t>(kWaveBudgetBytes / bytes_per_sample, (size_t)1 << 31);
 	if (npix_rect > max_samples) return fail(SSB_ERR_UNSUPPORTED, "pixel rectangle too large for one pass");
 	const uint32_t chunk = (uint32_t)std::min<size_t>(nsamp_total, std::max<size_t>(1, max_samples / npix_rect));
@@ -493,6 +498,9 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	const size_t o_leaf = off; off += up(N * 16);
 	const size_t o_meta = off; off += up(N * 8);
 	const size_t o_ff = off; off += up(N * 4);
+	const size_t o_ha = off; off += up(N * 16);
+	const size_t o_hq = off; off += up(N * 4);
+	const size_t o_ord = off; off += up(N * 4);
 	if (off > c->wave_bytes) {
 		if (c->d_wave) cudaFree(c->d_wave);
 		c->d_wave = nullptr; c->wave_bytes = 0;
@@ -517,7 +525,12 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.stk_np = reinterpret_cast<float2*>(wv + o_sn);
 	P.leaf = reinterpret_cast<float4*>(wv + o_leaf); P.meta = reinterpret_cast<float2*>(wv + o_meta);
 	P.ff = reinterpret_cast<float*>(wv + o_ff);
-	P.counts = c->d_counts;
+	P.counts = c->d_counts + kCountsOff;
+	P.nhits = c->d_counts + kNhitsOff;
+	P.bin_count = c->d_counts + kBinCountOff;
+	P.bin_cursor = c->d_counts + kBinCursorOff;
+	P.hit_a = reinterpret_cast<float4*>(wv + o_ha); P.hit_q = reinterpret_cast<uint32_t*>(wv + o_hq);
+	P.order = reinterpret_cast<uint32_t*>(wv + o_ord);
 	P.samples = c->want_samples ? c->d_samples : nullptr;
 	P.accum = c->d_accum;
 	P.width = o->width; P.height = o->height; P.x0 = o->x0; P.y0 = o->y0; P.rect_w = rect_w; P.rect_h = rect_h;
@@ -536,19 +549,23 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.meng_sample_min = c->meng.sample_min; P.meng_sample_max = c->meng.sample_max;
 
 	const size_t smem = c->blob_bytes;
-	typedef void (*bounce_fn)(const KParams);
-	bounce_fn k_first = nullptr, k_next = nullptr;
+	typedef void (*kfn)(const KParams);
+	kfn k_shade_first = nullptr, k_shade_next = nullptr;
 	switch (o->upsampling) {  // one instantiation per upsampling mode keeps the instruction footprint small
-		case SSB_UPSAMPLE_OURS: k_first = ssb_bounce_kernel<true, SSB_UPSAMPLE_OURS>; k_next = ssb_bounce_kernel<false, SSB_UPSAMPLE_OURS>; break;
-		case SSB_UPSAMPLE_JH: k_first = ssb_bounce_kernel<true, SSB_UPSAMPLE_JH>; k_next = ssb_bounce_kernel<false, SSB_UPSAMPLE_JH>; break;
-		default: k_first = ssb_bounce_kernel<true, SSB_UPSAMPLE_MENG>; k_next = ssb_bounce_kernel<false, SSB_UPSAMPLE_MENG>; break;
+		case SSB_UPSAMPLE_OURS: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_OURS>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_OURS>; break;
+		case SSB_UPSAMPLE_JH: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_JH>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_JH>; break;
+		default: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_MENG>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_MENG>; break;
 	}
-	SSB_CUDA(cudaFuncSetAttribute(k_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	SSB_CUDA(cudaFuncSetAttribute(k_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int occ_first = 0, occ_next = 0;
-	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_first, k_first, SSB_BOUNCE_THREADS, smem));
-	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_next, k_next, SSB_BOUNCE_THREADS, smem));
-	if (occ_first < 1 || occ_next < 1) return fail(SSB_ERR_UNSUPPORTED, "bounce kernel does not fit on an SM with %zu bytes of tables", smem);
+	kfn k_isect_first = ssb_intersect_kernel<true>, k_isect_next = ssb_intersect_kernel<false>;
+	int occ_sf = 0, occ_sn = 0, occ_if = 0, occ_in = 0;
+	for (kfn k : { k_shade_first, k_shade_next, k_isect_first, k_isect_next })
+		SSB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sf, k_shade_first, SSB_SHADE_THREADS, smem));
+	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, k_shade_next, SSB_SHADE_THREADS, smem));
+	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_if, k_isect_first, SSB_INTERSECT_THREADS, smem));
+	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_in, k_isect_next, SSB_INTERSECT_THREADS, smem));
+	if (occ_sf < 1 || occ_sn < 1 || occ_if < 1 || occ_in < 1) return fail(SSB_ERR_UNSUPPORTED, "kernels do not fit on an SM with %zu bytes of tables", smem);
+	const uint32_t nquads = (uint32_t)c->quads.size();
 
 	SSB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
 	uint32_t launches = 0, passes = 0;
@@ -557,21 +574,29 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 		P.sample_begin = o->sample_begin + k0;
 		P.nsamp = ns;
 		P.total_work = (unsigned long long)npix_rect * ns;
-		SSB_CUDA(cudaMemsetAsync(c->d_counts, 0, (SSB_MAX_DEPTH + 2) * sizeof(uint32_t), c->stream));
+		SSB_CUDA(cudaMemsetAsync(c->d_counts, 0, kCounterWords * sizeof(uint32_t), c->stream));
 		while (c->ev_pass.size() < 2 * (size_t)(passes + 1)) { cudaEvent_t e; SSB_CUDA(cudaEventCreate(&e)); c->ev_pass.push_back(e); }
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes], c->stream));
-		// one launch per path depth; persistent grids (SMs x resident CTAs), never more CTAs than the first queue needs
-		const unsigned long long want = (P.total_work + SSB_BOUNCE_THREADS - 1) / SSB_BOUNCE_THREADS;
+		// per path depth: closest-hit queries -> counting sort by hit quad -> shading; persistent grids (SMs x resident
+		// CTAs, queue lengths are read on the device), never more CTAs than the first queue needs
 		for (uint32_t d = 0; d < o->max_depth; ++d) {
-			// with explicit light sampling the last depth is never entered (dead-work skip in the bounce kernel)
+			// with explicit light sampling the last depth is never entered (dead-work skip in the shade kernel)
 			if (d > 0 && o->explicit_light_sampling && d + 1 >= o->max_depth) break;
 			P.depth = d;
-			const int occ = d == 0 ? occ_first : occ_next;
-			const unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * occ, want);
-			if (d == 0) k_first<<<grid, SSB_BOUNCE_THREADS, smem, c->stream>>>(P);
-			else k_next<<<grid, SSB_BOUNCE_THREADS, smem, c->stream>>>(P);
+			const unsigned long long want_i = (P.total_work + SSB_INTERSECT_THREADS - 1) / SSB_INTERSECT_THREADS;
+			const unsigned long long want_s = (P.total_work + SSB_SHADE_THREADS - 1) / SSB_SHADE_THREADS;
+			const unsigned grid_i = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_if : occ_in), want_i);
+			const unsigned grid_s = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_sf : occ_sn), want_s);
+			(d == 0 ? k_isect_first : k_isect_next)<<<grid_i, SSB_INTERSECT_THREADS, smem, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
-			launches += 1;
+			ssb_bin_scan_kernel<<<1, 32, 0, c->stream>>>(P, nquads);
+			SSB_CUDA(cudaGetLastError());
+			const unsigned grid_b = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * 8, (P.total_work + 255) / 256);
+			ssb_bin_scatter_kernel<<<grid_b, 256, 0, c->stream>>>(P, d == 0 ? 1u : 0u);
+			SSB_CUDA(cudaGetLastError());
+			(d == 0 ? k_shade_first : k_shade_next)<<<grid_s, SSB_SHADE_THREADS, smem, c->stream>>>(P);
+			SSB_CUDA(cudaGetLastError());
+			launches += 4;
 		}
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes + 1], c->stream));
 		const unsigned fgrid = (unsigned)((npix_rect + 127) / 128);

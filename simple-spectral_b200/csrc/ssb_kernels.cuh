@@ -74,6 +74,13 @@ struct KParams {
 	float2* meta;       // lambda_0, (#records | hit<<16) as int bits
 	float* ff;          // dot(camera ray, camera dir), only when FLAT_FIELD_CORRECTION is off (renderer.cpp:265)
 	uint32_t* counts;   // queue length per depth; counts[0] = samples in the pass
+	// closest-hit records of the current depth (indexed like the input queue) and the sort-by-quad machinery
+	float4* hit_a;      // dist, barycentrics
+	uint32_t* hit_q;    // quad | tri << 31, or 0xffffffff for a miss
+	uint32_t* order;    // queue positions of the paths that hit something, grouped by hit quad
+	uint32_t* bin_count;   // [max_depth][SSB_MAX_QUADS] paths per hit quad
+	uint32_t* bin_cursor;  // [max_depth][SSB_MAX_QUADS] scatter cursors (start at the bin offset)
+	uint32_t* nhits;       // [max_depth] total hits (= length of `order`)
 	float4* samples;    // optional [nsamp][npix_rect] per-sample output (debug), may be null
 	double* accum;
 	unsigned long long total_work;  // npix_rect * nsamp
@@ -602,55 +609,58 @@ __device__ __forceinline__ void stage_blob(unsigned char* smem, const unsigned c
 	}
 }
 
-// 256 threads x 3 CTAs = 24 warps/SM at 80 registers: best of the on-box sweep (profiles/r1f_tune.txt)
-#ifndef SSB_BOUNCE_THREADS
-#define SSB_BOUNCE_THREADS 256
+#ifndef SSB_INTERSECT_THREADS
+#define SSB_INTERSECT_THREADS 256
 #endif
-#ifndef SSB_BOUNCE_MIN_BLOCKS
-#define SSB_BOUNCE_MIN_BLOCKS 3
+#ifndef SSB_INTERSECT_MIN_BLOCKS
+#define SSB_INTERSECT_MIN_BLOCKS 4
+#endif
+#ifndef SSB_SHADE_THREADS
+#define SSB_SHADE_THREADS 256
+#endif
+#ifndef SSB_SHADE_MIN_BLOCKS
+#define SSB_SHADE_MIN_BLOCKS 3
 #endif
 
-// One bounce of every live path at depth P.depth: the body of the reference's lambda L (renderer.cpp:147-255).
-// FIRST: depth 0 — the path is created here (Renderer::_render_sample prologue, renderer.cpp:103-138).
-template <bool FIRST, int UPS>
-__global__ void __launch_bounds__(SSB_BOUNCE_THREADS, SSB_BOUNCE_MIN_BLOCKS)
-ssb_bounce_kernel(const __grid_constant__ KParams P) {
+__device__ __forceinline__ void stage_scene(const KParams& P, unsigned long long* bar) {
+	const DevHeader* gh = reinterpret_cast<const DevHeader*>(P.blob);
+	stage_blob(ssb_smem, P.blob, __ldg(&gh->total_bytes), bar);
+}
+
+// ---- stage 1 of a bounce: the closest-hit query of every live path at depth P.depth (renderer.cpp:163).
+// FIRST: depth 0 — the path is created here (Renderer::_render_sample prologue, renderer.cpp:103-138) and its state
+// written.  A miss ends the path (L() returns 0).  Hits are recorded and counted per hit quad, so that the shading
+// stage can run with all lanes of a warp on the same quad / material.
+template <bool FIRST>
+__global__ void __launch_bounds__(SSB_INTERSECT_THREADS, SSB_INTERSECT_MIN_BLOCKS)
+ssb_intersect_kernel(const __grid_constant__ KParams P) {
 	__shared__ __align__(8) unsigned long long blob_bar;
-	{
-		const DevHeader* gh = reinterpret_cast<const DevHeader*>(P.blob);
-		stage_blob(ssb_smem, P.blob, __ldg(&gh->total_bytes), &blob_bar);
-	}
+	stage_scene(P, &blob_bar);
 	const SceneView S;
-
 	const unsigned full = 0xffffffffu;
-	const int lane = threadIdx.x & 31;
 	const uint32_t npix_rect = P.rect_w * P.rect_h;
-	const float eps = P.eps;
-	const bool els = P.els != 0;
 	const int depth = (int)P.depth;
 	const uint32_t n_in = FIRST ? (uint32_t)P.total_work : P.counts[depth];
-	const int pin = depth & 1, pout = pin ^ 1;
+	const int pin = depth & 1;
 	const uint32_t nthreads = gridDim.x * blockDim.x;
-	// warps iterate together: the loop bound is rounded up to a warp multiple so that ballots stay converged
-	const uint32_t n_round = (n_in + 31u) & ~31u;
+	const uint32_t n_round = (n_in + 31u) & ~31u;  // warps iterate together (match/ballot below)
+	uint32_t* bins = P.bin_count + (size_t)depth * SSB_MAX_QUADS;
 
 	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += nthreads) {
 		const bool valid = item < n_in;
-		bool cont = false;  // path continues to depth+1
-		float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, lambda_0 = 0;
-		float ff_scale = 1.0f;
-		int ignore = -1;
-		uint32_t id = 0;
-		Rng rng; rng.state = 0; rng.inc = 1;
+		uint32_t hq = 0xffffffffu;
 		if (valid) {
+			float ox, oy, oz, dx, dy, dz;
+			int ignore = -1;
 			if (FIRST) {
-				id = item;
+				const uint32_t id = item;
 				uint32_t kk = id / npix_rect;
 				uint32_t pr = id - kk * npix_rect;
 				uint32_t pi = P.x0 + pr % P.rect_w, pj = P.y0 + pr / P.rect_w;
 				uint32_t k = P.sample_begin + kk;
 				unsigned long long sample_index = (unsigned long long)k * ((unsigned long long)P.width * P.height) +
 				                                  ((unsigned long long)pj * P.width + pi);
+				Rng rng;
 				rng.state = mix64(P.seed ^ mix64(sample_index));
 				rng.inc = mix64(rng.state) | 1ull;
 				double sub_y = rand_1d(rng);  // g++ evaluates dvec2(rand_1d(),rand_1d()) right-to-left
@@ -667,27 +677,124 @@ ssb_bounce_kernel(const __grid_constant__ KParams P) {
 				double inv = 1.0 / sqrt((ddx * ddx + ddy * ddy) + ddz * ddz);
 				ox = P.cam_pos[0]; oy = P.cam_pos[1]; oz = P.cam_pos[2];
 				dx = (float)(ddx * inv); dy = (float)(ddy * inv); dz = (float)(ddz * inv);
-				lambda_0 = P.lambda_min + rand_1f(rng) * P.lambda_step;
-				if (!P.flat_field) ff_scale = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
+				const float lambda_0 = P.lambda_min + rand_1f(rng) * P.lambda_step;
+				if (!P.flat_field) P.ff[id] = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
+				P.st_od[0][item] = make_float4(ox, oy, oz, __int_as_float(-1));
+				P.st_dl[0][item] = make_float4(dx, dy, dz, lambda_0);
+				P.st_rng[0][item] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
+				P.st_id[0][item] = id;
 			} else {
+				const float4 a = P.st_od[pin][item], b = P.st_dl[pin][item];
+				ox = a.x; oy = a.y; oz = a.z; ignore = __float_as_int(a.w);
+				dx = b.x; dy = b.y; dz = b.z;
+			}
+			Hit hit;
+			scene_intersect(S, P.eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+			if (hit.quad >= 0) {
+				hq = (uint32_t)hit.quad | ((uint32_t)hit.tri << 31);
+				P.hit_a[item] = make_float4(hit.dist, hit.bx, hit.by, hit.bz);
+			} else {
+				// miss: L() returns 0 (renderer.cpp:161-163 with no hit); hit_anything only if an earlier depth hit
+				const uint32_t id = FIRST ? item : P.st_id[pin][item];
+				const float lambda_0 = FIRST ? P.st_dl[0][item].w : P.st_dl[pin][item].w;
+				P.leaf[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+				P.meta[id] = make_float2(lambda_0, __int_as_float(depth | (FIRST ? 0 : (1 << 16))));
+			}
+			P.hit_q[item] = hq;
+		}
+		// count hits per quad: one atomic per distinct quad per warp
+		const bool is_hit = hq != 0xffffffffu;
+		const unsigned hmask = __ballot_sync(full, is_hit);
+		if (is_hit) {
+			const uint32_t q = hq & 0x7fffffffu;
+			const unsigned peers = __match_any_sync(hmask, q);
+			if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&bins[q], (uint32_t)__popc(peers));
+		}
+	}
+}
+
+// ---- exclusive prefix sum of the per-quad hit counts of depth P.depth -> scatter cursors; one small CTA
+__global__ void ssb_bin_scan_kernel(const __grid_constant__ KParams P, uint32_t nquads) {
+	if (threadIdx.x != 0) return;
+	const uint32_t* cnt = P.bin_count + (size_t)P.depth * SSB_MAX_QUADS;
+	uint32_t* cur = P.bin_cursor + (size_t)P.depth * SSB_MAX_QUADS;
+	uint32_t acc = 0;
+	for (uint32_t q = 0; q < nquads; ++q) { cur[q] = acc; acc += cnt[q]; }
+	P.nhits[P.depth] = acc;
+}
+
+// ---- counting-sort scatter: order[] = queue positions of the hit paths, grouped by hit quad
+__global__ void __launch_bounds__(256) ssb_bin_scatter_kernel(const __grid_constant__ KParams P, uint32_t first_depth) {
+	const unsigned full = 0xffffffffu;
+	const int depth = (int)P.depth;
+	const uint32_t n_in = first_depth ? (uint32_t)P.total_work : P.counts[depth];
+	const uint32_t nthreads = gridDim.x * blockDim.x;
+	const uint32_t n_round = (n_in + 31u) & ~31u;
+	uint32_t* cur = P.bin_cursor + (size_t)depth * SSB_MAX_QUADS;
+	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += nthreads) {
+		const uint32_t hq = item < n_in ? P.hit_q[item] : 0xffffffffu;
+		const bool is_hit = hq != 0xffffffffu;
+		const unsigned hmask = __ballot_sync(full, is_hit);
+		if (is_hit) {
+			const uint32_t q = hq & 0x7fffffffu;
+			const unsigned peers = __match_any_sync(hmask, q);
+			const int leader = __ffs(peers) - 1;
+			uint32_t base = 0;
+			if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cur[q], (uint32_t)__popc(peers));
+			base = __shfl_sync(peers, base, leader);
+			P.order[base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = item;
+		}
+	}
+}
+
+// ---- stage 2 of a bounce: everything the reference's lambda L does after the closest hit (renderer.cpp:165-251)
+// for the paths that hit something, visited grouped by hit quad: emission, albedo, light sample + shadow query,
+// BSDF sample, fold record, and the compacted state of the continuing paths.
+template <bool FIRST, int UPS>
+__global__ void __launch_bounds__(SSB_SHADE_THREADS, SSB_SHADE_MIN_BLOCKS)
+ssb_shade_kernel(const __grid_constant__ KParams P) {
+	__shared__ __align__(8) unsigned long long blob_bar;
+	stage_scene(P, &blob_bar);
+	const SceneView S;
+
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const float eps = P.eps;
+	const bool els = P.els != 0;
+	const int depth = (int)P.depth;
+	const uint32_t n_in = P.nhits[depth];
+	const int pin = depth & 1, pout = pin ^ 1;
+	const uint32_t nthreads = gridDim.x * blockDim.x;
+	const uint32_t n_round = (n_in + 31u) & ~31u;
+
+	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += nthreads) {
+		const bool valid = slot < n_in;
+		bool cont = false;  // path continues to depth+1
+		float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, lambda_0 = 0;
+		int ignore = -1;
+		uint32_t id = 0;
+		Rng rng; rng.state = 0; rng.inc = 1;
+		if (valid) {
+			const uint32_t item = P.order[slot];
+			{
 				const float4 a = P.st_od[pin][item], b = P.st_dl[pin][item];
 				const uint4 r = P.st_rng[pin][item];
 				id = P.st_id[pin][item];
-				ox = a.x; oy = a.y; oz = a.z; ignore = __float_as_int(a.w);
+				ox = a.x; oy = a.y; oz = a.z;
 				dx = b.x; dy = b.y; dz = b.z; lambda_0 = b.w;
 				rng.state = ((unsigned long long)r.y << 32) | r.x;
 				rng.inc = ((unsigned long long)r.w << 32) | r.z;
 			}
-
-			// ---- closest hit (renderer.cpp:163)
+			const float4 ha = P.hit_a[item];
+			const uint32_t hq = P.hit_q[item];
 			Hit hit;
-			scene_intersect(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+			hit.quad = (int)(hq & 0x7fffffffu); hit.tri = (int)(hq >> 31);
+			hit.dist = ha.x; hit.bx = ha.y; hit.by = ha.z; hit.bz = ha.w;
+
 			Hero rad;  // value this L() call returns if the path ends here
 			rad.v[0] = rad.v[1] = rad.v[2] = rad.v[3] = 0.0f;
 			int nrec = depth;            // fold records written by shallower depths
-			bool hit_anything = !FIRST;  // depth > 0 implies an earlier hit
-			if (hit.quad >= 0) {
-				hit_anything = true;
+			{
 				const int cur_quad = hit.quad;
 				const ssb_quad& quad = S.quads()[cur_quad];
 				const ssb_tri& tri = quad.tri[hit.tri];
@@ -800,9 +907,8 @@ ssb_bounce_kernel(const __grid_constant__ KParams P) {
 			// ---- the path ends here: the deepest L() call returns `rad`, `nrec` records wait to be folded
 			if (!cont) {
 				P.leaf[id] = make_float4(rad.v[0], rad.v[1], rad.v[2], rad.v[3]);
-				P.meta[id] = make_float2(lambda_0, __int_as_float(nrec | (hit_anything ? (1 << 16) : 0)));
+				P.meta[id] = make_float2(lambda_0, __int_as_float(nrec | (1 << 16)));
 			}
-			if (FIRST && !P.flat_field) P.ff[id] = ff_scale;
 		}
 
 		// ---- compaction: surviving paths go to dense positions of the next depth's queue

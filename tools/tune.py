@@ -50,7 +50,7 @@ def main():
                 print(f"{v or 'default':60s} RUN FAILED: {out.stderr[-300:]}")
                 continue
             ms, tr = map(float, res[0].split()[1:3])
-            print(f"{v or 'default':60s} frame {ms:8.3f} ms  bounce {tr:8.3f} ms  {512*512*64/ms/1e3:8.1f} Msamples/s  (build {time.time()-t0:.0f}s)", flush=True)
+            print(f"{v or chr(100)+"efault":60s} frame {ms:8.3f} ms  bounce {tr:8.3f} ms  {512*512*64/ms/1e3:8.1f} Msamples/s  (build {time.time()-t0:.0f}s)", flush=True)
     finally:
         shutil.copyfile(backup, LIB)
         os.remove(backup)
