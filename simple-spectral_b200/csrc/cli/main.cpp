@@ -1,0 +1,112 @@
+// main.cpp — command-line front end with the reference's own flags (reference src/main.cpp:33-162,164-361):
+//   --scene=<name>/-s  --width=<w>/-w  --height=<h>/-h  --samples=<n>/-spp  --output=<path>/-o  [--indirect-only/-io]
+// so that `simple_spectral_b200 --scene=cornell-srgb -w=512 -h=512 -spp=64 --output=out.png` is a drop-in for the
+// reference binary, rendering on the GPU through the Renderer façade.  The reference's compile-time variants are
+// extra, optional flags here: --variant=ours1931|ours2006|meng|jh  --seed=<n>  --device=<n>  --data-root=<dir>
+// (default data root: the current directory, like the reference's cwd-relative "data/..." paths).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../host/ssb_host.hpp"
+
+namespace {
+
+void print_usage() {
+	std::printf(
+		"simple_spectral_b200: the simple-spectral renderer's hot path on a B200\n"
+		"  Required arguments:\n"
+		"    --scene=<name>/-s=<name>            cornell | cornell-srgb | plane-srgb\n"
+		"    --width=<w>/-w=<w>  --height=<h>/-h=<h>  --samples=<n>/-spp=<n>\n"
+		"    --output=<path>/-o=<path>           .png / .pfm / .hdr / .csv by extension\n"
+		"  Optional arguments:\n"
+		"    --indirect-only/-io\n"
+		"    --variant=ours1931|ours2006|meng|jh   (the reference's compile-time modes)\n"
+		"    --seed=<n>  --device=<n>  --data-root=<dir containing data/>\n");
+}
+
+struct Args {
+	std::vector<std::string> rest;
+	// main.cpp:61-79: "name=value" or bare "name"; throws -2 when absent
+	std::string get(std::string const& name, std::string const& shortname) {
+		for (auto it = rest.begin(); it != rest.end(); ++it) {
+			size_t eq = it->find('=');
+			if (eq != std::string::npos) {
+				std::string key = it->substr(0, eq);
+				if (key == name || key == shortname) { std::string v = it->substr(eq + 1); rest.erase(it); return v; }
+			} else if (*it == name || *it == shortname) { rest.erase(it); return name; }
+		}
+		throw -2;
+	}
+	std::string req(std::string const& name, std::string const& shortname) {
+		try { return get(name, shortname); }
+		catch (int) { std::fprintf(stderr, "Required argument `%s`/`%s` not found!\n", name.c_str(), shortname.c_str()); throw; }
+	}
+};
+
+unsigned to_pos(std::string const& s) {  // util/string.hpp:55-59
+	size_t i = 0;
+	int v = std::stoi(s, &i);
+	if (i != s.size()) throw -1;
+	if (v <= 0) throw -2;
+	return static_cast<unsigned>(v);
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+	ssbh::RendererOptions o;
+	try {
+		Args a;
+		for (int i = 1; i < argc; ++i) a.rest.emplace_back(argv[i]);
+		o.scene_name = a.req("--scene", "-s");
+		if (o.scene_name != "cornell" && o.scene_name != "cornell-srgb" && o.scene_name != "plane-srgb") {
+			std::fprintf(stderr, "Unrecognized scene \"%s\"!  (Supported scenes: \"cornell\", \"cornell-srgb\", \"plane-srgb\")\n", o.scene_name.c_str());
+			throw -3;
+		}
+		try { o.res[0] = to_pos(a.req("--width", "-w")); o.res[1] = to_pos(a.req("--height", "-h")); }
+		catch (int) { std::fprintf(stderr, "Invalid width or height!\n"); throw; }
+		catch (std::exception const&) { std::fprintf(stderr, "Invalid width or height!\n"); throw -1; }
+		try { o.spp = to_pos(a.req("--samples", "-spp")); }
+		catch (int) { std::fprintf(stderr, "Invalid number of samples!\n"); throw; }
+		catch (std::exception const&) { std::fprintf(stderr, "Invalid number of samples!\n"); throw -1; }
+		try {
+			std::string v = a.get("--indirect-only", "-io");
+			if (v != "--indirect-only") { std::fprintf(stderr, "`--indirect-only`/`-io` does not take a value!\n"); throw -1; }
+			o.indirect_only = true;
+		} catch (int code) { if (code != -2) throw; o.indirect_only = false; }
+		o.output_path = a.req("--output", "-o");
+		try {
+			std::string v = a.get("--variant", "--variant");
+			if (v == "ours1931") { o.observer = 1931; o.upsampling = SSB_UPSAMPLE_OURS; }
+			else if (v == "ours2006") { o.observer = 2006; o.upsampling = SSB_UPSAMPLE_OURS; }
+			else if (v == "meng") { o.observer = 1931; o.upsampling = SSB_UPSAMPLE_MENG; }
+			else if (v == "jh") { o.observer = 1931; o.upsampling = SSB_UPSAMPLE_JH; }
+			else { std::fprintf(stderr, "Unknown variant \"%s\"\n", v.c_str()); throw -3; }
+		} catch (int code) { if (code != -2) throw; }
+		try { o.seed = std::strtoull(a.get("--seed", "--seed").c_str(), nullptr, 10); } catch (int code) { if (code != -2) throw; }
+		try { o.device = std::atoi(a.get("--device", "--device").c_str()); } catch (int code) { if (code != -2) throw; }
+		try { o.data_root = a.get("--data-root", "--data-root"); } catch (int code) { if (code != -2) throw; }
+		if (!a.rest.empty()) {
+			std::fprintf(stderr, "Warning: ignoring extraneous argument(s):\n");
+			for (auto const& s : a.rest) std::fprintf(stderr, "  \"%s\"\n", s.c_str());
+		}
+	} catch (int) {
+		print_usage();
+		return -1;
+	}
+	try {
+		ssbh::Renderer renderer(o);
+		renderer.render_start();
+		renderer.render_wait();
+		std::printf("%.3f Mpath-samples/s on the device (%llu samples, %.3f ms)\n",
+		            renderer.last_stats.samples / renderer.last_stats.device_ms / 1e3,
+		            (unsigned long long)renderer.last_stats.samples, renderer.last_stats.device_ms);
+	} catch (ssbh::Error const& e) {
+		std::fprintf(stderr, "%s\n", e.message.c_str());
+		return e.code;
+	}
+	return 0;
+}

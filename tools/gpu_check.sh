@@ -14,7 +14,7 @@ if [ "${2:-}" != "noprof" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/${TAG}_launches.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1; echo "ncu launches rc=$?"
 # one whole frame of bounce launches (depths 0..8) + its finalize, after two warm frames
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"ssb_intersect|ssb_shade|ssb_bin|ssb_finalize" -s 74 -c 37 -f -o $OUT/${TAG}_trace \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"ssb_intersect|ssb_shade|ssb_bin|ssb_finalize" -s 78 -c 4 -f -o $OUT/${TAG}_trace \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT | tail -12
 fi
