@@ -481,24 +481,22 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 
 	// ---- size one pass: N = npix_rect * chunk samples share the wavefront buffers
 	const uint32_t nrec_depths = o->max_depth > 1 ? o->max_depth - 1 : 1;
-	const size_t bytes_per_sample = 2 * (16 + 16 + 16 + 4) + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (16 + 4 + 4);
+	const size_t bytes_per_sample = 2 * (32 + 32) + 32 + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (4 + 4);
 	const size_t max_samples = std::min<size_t>(kWaveBudgetBytes / bytes_per_sample, (size_t)1 << 31);
 	if (npix_rect > max_samples) return fail(SSB_ERR_UNSUPPORTED, "pixel rectangle too large for one pass");
 	const uint32_t chunk = (uint32_t)std::min<size_t>(nsamp_total, std::max<size_t>(1, max_samples / npix_rect));
 	const size_t N = npix_rect * chunk;
 	auto up = [](size_t v) { return (v + 255) / 256 * 256; };
 	size_t off = 0;
-	const size_t o_od0 = off; off += up(N * 16); const size_t o_od1 = off; off += up(N * 16);
-	const size_t o_dl0 = off; off += up(N * 16); const size_t o_dl1 = off; off += up(N * 16);
-	const size_t o_rng0 = off; off += up(N * 16); const size_t o_rng1 = off; off += up(N * 16);
-	const size_t o_id0 = off; off += up(N * 4); const size_t o_id1 = off; off += up(N * 4);
+	const size_t o_a0 = off; off += up(N * 32); const size_t o_a1 = off; off += up(N * 32);
+	const size_t o_r0 = off; off += up(N * 32); const size_t o_r1 = off; off += up(N * 32);
+	const size_t o_h = off; off += up(N * 32);
 	const size_t o_sl = off; off += up(N * nrec_depths * 16);
 	const size_t o_sf = off; off += up(N * nrec_depths * 16);
 	const size_t o_sn = off; off += up(N * nrec_depths * 8);
 	const size_t o_leaf = off; off += up(N * 16);
 	const size_t o_meta = off; off += up(N * 8);
 	const size_t o_ff = off; off += up(N * 4);
-	const size_t o_ha = off; off += up(N * 16);
 	const size_t o_hq = off; off += up(N * 4);
 	const size_t o_ord = off; off += up(N * 4);
 	if (off > c->wave_bytes) {
@@ -517,10 +515,9 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	KParams P{};
 	P.blob = c->d_blob;
 	unsigned char* wv = c->d_wave;
-	P.st_od[0] = reinterpret_cast<float4*>(wv + o_od0); P.st_od[1] = reinterpret_cast<float4*>(wv + o_od1);
-	P.st_dl[0] = reinterpret_cast<float4*>(wv + o_dl0); P.st_dl[1] = reinterpret_cast<float4*>(wv + o_dl1);
-	P.st_rng[0] = reinterpret_cast<uint4*>(wv + o_rng0); P.st_rng[1] = reinterpret_cast<uint4*>(wv + o_rng1);
-	P.st_id[0] = reinterpret_cast<uint32_t*>(wv + o_id0); P.st_id[1] = reinterpret_cast<uint32_t*>(wv + o_id1);
+	P.recA[0] = reinterpret_cast<float4*>(wv + o_a0); P.recA[1] = reinterpret_cast<float4*>(wv + o_a1);
+	P.recR[0] = reinterpret_cast<float4*>(wv + o_r0); P.recR[1] = reinterpret_cast<float4*>(wv + o_r1);
+	P.recH = reinterpret_cast<float4*>(wv + o_h);
 	P.stk_local = reinterpret_cast<float4*>(wv + o_sl); P.stk_f = reinterpret_cast<float4*>(wv + o_sf);
 	P.stk_np = reinterpret_cast<float2*>(wv + o_sn);
 	P.leaf = reinterpret_cast<float4*>(wv + o_leaf); P.meta = reinterpret_cast<float2*>(wv + o_meta);
@@ -529,7 +526,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.nhits = c->d_counts + kNhitsOff;
 	P.bin_count = c->d_counts + kBinCountOff;
 	P.bin_cursor = c->d_counts + kBinCursorOff;
-	P.hit_a = reinterpret_cast<float4*>(wv + o_ha); P.hit_q = reinterpret_cast<uint32_t*>(wv + o_hq);
+	P.hit_q = reinterpret_cast<uint32_t*>(wv + o_hq);
 	P.order = reinterpret_cast<uint32_t*>(wv + o_ord);
 	P.samples = c->want_samples ? c->d_samples : nullptr;
 	P.accum = c->d_accum;
@@ -591,8 +588,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			SSB_CUDA(cudaGetLastError());
 			ssb_bin_scan_kernel<<<1, 32, 0, c->stream>>>(P, nquads);
 			SSB_CUDA(cudaGetLastError());
-			const unsigned grid_b = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * 8, (P.total_work + 255) / 256);
-			ssb_bin_scatter_kernel<<<grid_b, 256, 0, c->stream>>>(P, d == 0 ? 1u : 0u);
+			const unsigned grid_b = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * 8, (P.total_work + 1023) / 1024);
+			ssb_bin_scatter_kernel<<<grid_b, 256, 0, c->stream>>>(P, d == 0 ? 1u : 0u, nquads);
 			SSB_CUDA(cudaGetLastError());
 			(d == 0 ? k_shade_first : k_shade_next)<<<grid_s, SSB_SHADE_THREADS, smem, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());

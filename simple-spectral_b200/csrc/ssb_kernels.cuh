@@ -5,24 +5,28 @@
 // islands the reference has: camera ray, zero-barycentric fallback, accumulation), compiled with
 // -fmad=false so that no multiply-add is contracted: operation order is the reference's.
 //
-// Design (B200-first, not a translation of the reference's recursive std::function): a WAVEFRONT.
-//   * One launch of ssb_bounce_kernel per path depth.  A thread owns one live path for exactly one bounce:
-//     closest-hit query -> emission / albedo -> light sample -> shadow query -> BSDF sample -> next ray.  Every
-//     lane of every warp is a live path (ncu on the first, megakernel version of this file showed 9.8 of 32
-//     lanes active on average and the instruction cache thrashing on a 131 KB kernel; see profiles/).
-//   * Path state lives in HBM as dense, coalesced float4/uint4 SoA arrays (origin+ignore, direction+lambda0, PCG32
-//     state, sample id), ping-ponged between depths.  Surviving paths are stream-compacted on write with a
-//     warp ballot + one atomic per warp, so the next depth's launch is dense again.
-//   * The depth-0 instantiation generates the camera ray, seeds the RNG and draws the hero wavelength in-kernel.
-//   * The kernels are persistent (grid = SMs x resident CTAs, grid-stride over the queue whose length is read
-//     from device memory: no host round-trip between depths).
-//   * the scene, materials, spectra, observer/basis tables and the sRGB LUT are one contiguous "blob" that each
-//     CTA pulls into shared memory with a single TMA bulk copy (cp.async.bulk.shared::cluster.global + mbarrier).
-//   * the reference folds radiance on the way back UP the recursion (renderer.cpp:216,248); to keep that exact
-//     rounding every bounce writes its (local radiance, f_s, n.l, pdf) record to a per-depth array, and
-//     ssb_finalize_kernel folds them backwards per sample, converts to XYZ and adds sample*0.001f to the double
-//     XYZA accumulator in sample order — the reference's exact summation order (renderer.cpp:292-295),
-//     deterministic run to run (no float/double atomics).
+// Design (B200-first, not a translation of the reference's recursive std::function): a sorted WAVEFRONT.
+// Per path depth, four launches on one stream (queue lengths stay on the device, no host round trip):
+//   1. ssb_intersect_kernel  — the closest-hit query of every live path (depth 0: also creates the path: camera
+//      ray, per-sample PCG32 seed, hero wavelength).  Small (15 KB of SASS, 64 registers, 32 warps/SM): the
+//      linear scan over the quad list is a conservative plane/rectangle filter run converged by all lanes plus the
+//      exact watertight test on the few surviving candidates.  Writes the hit record, ends paths that miss, and
+//      counts hits per quad (shared-memory histogram, one global atomic per quad per CTA).
+//   2. ssb_bin_scan_kernel + 3. ssb_bin_scatter_kernel — counting sort of the hit paths by hit quad.
+//   4. ssb_shade_kernel — everything the reference's lambda L does after the hit (emission, albedo / sRGB texture
+//      upsampling, light sample, shadow query, BSDF sample, fold record), visiting paths grouped by hit quad so
+//      that a warp shares material, light-sampling geometry class and branch behaviour; surviving paths are
+//      stream-compacted (warp ballot + one atomic per warp) into dense records for the next depth.
+// then ssb_finalize_kernel folds the per-depth records backwards per sample (the reference folds radiance on the
+// way back UP its recursion, renderer.cpp:216,248 — kept exact), converts to XYZ and adds sample*0.001f to the
+// double XYZA accumulator in sample order (renderer.cpp:292-295): deterministic, no float/double atomics.
+// History (profiles/): a register-resident megakernel reached 154-222 Msamples/s with 9.8 of 32 lanes active
+// and instruction-cache thrash on 131 KB of SASS; the wavefront forms reach 500-600+.
+// Path state lives in HBM as 32-byte (one sector) records: recA {origin, ignore | direction, lambda0} feeds the
+// intersect stage, recH {hit point, quad | barycentrics} goes intersect -> shade, recR {PCG32 | sample id} feeds
+// the shade stage.  The scene, materials, spectra, observer/basis tables, filter records and the sRGB LUT are one
+// contiguous "blob" that each CTA pulls into shared memory with a single TMA bulk copy
+// (cp.async.bulk.shared::cluster.global + mbarrier).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -60,11 +64,14 @@ struct DevHeader {
 
 struct KParams {
 	const unsigned char* blob;
-	// path state, ping-pong [2]: dense arrays indexed by queue position
-	float4* st_od[2];   // origin.xyz, ignore (int bits)
-	float4* st_dl[2];   // direction.xyz, lambda_0
-	uint4* st_rng[2];   // PCG32 state, inc
-	uint32_t* st_id[2]; // sample id within the pass
+	// Path state in HBM, one 32-byte sector per record so that every access moves whole sectors:
+	//   recA[2] (ping-pong): ray        {origin.xyz, ignore (int bits)} {direction.xyz, lambda_0}   read by the intersect stage
+	//   recR[2] (ping-pong): the rest   {PCG32 state, inc}              {sample id, lambda_0, -, -}  read by the shade stage
+	//   recH               : closest hit {hit point.xyz, quad|tri<<31}  {barycentrics, -}            intersect -> shade
+	// recA/recR are written densely (compacted) by the stage that creates the next ray; recH is indexed like the queue.
+	float4* recA[2];
+	float4* recR[2];
+	float4* recH;
 	// per-depth records for the backward fold, indexed [depth][sample id]
 	float4* stk_local;
 	float4* stk_f;
@@ -75,8 +82,7 @@ struct KParams {
 	float* ff;          // dot(camera ray, camera dir), only when FLAT_FIELD_CORRECTION is off (renderer.cpp:265)
 	uint32_t* counts;   // queue length per depth; counts[0] = samples in the pass
 	// closest-hit records of the current depth (indexed like the input queue) and the sort-by-quad machinery
-	float4* hit_a;      // dist, barycentrics
-	uint32_t* hit_q;    // quad | tri << 31, or 0xffffffff for a miss
+	uint32_t* hit_q;    // quad | tri << 31, or 0xffffffff for a miss (dense copy of recH[].w for the counting sort)
 	uint32_t* order;    // queue positions of the paths that hit something, grouped by hit quad
 	uint32_t* bin_count;   // [max_depth][SSB_MAX_QUADS] paths per hit quad
 	uint32_t* bin_cursor;  // [max_depth][SSB_MAX_QUADS] scatter cursors (start at the bin offset)
@@ -645,6 +651,11 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 	const uint32_t nthreads = gridDim.x * blockDim.x;
 	const uint32_t n_round = (n_in + 31u) & ~31u;  // warps iterate together (match/ballot below)
 	uint32_t* bins = P.bin_count + (size_t)depth * SSB_MAX_QUADS;
+	// hits per quad are counted in shared memory and flushed once per CTA: the global counters are only a handful of
+	// addresses (ncu on the first split build: the scatter kernel spent 0.77 ms waiting on 19 contended atomics)
+	__shared__ uint32_t s_bins[SSB_MAX_QUADS];
+	for (uint32_t q = threadIdx.x; q < SSB_MAX_QUADS; q += blockDim.x) s_bins[q] = 0;
+	__syncthreads();
 
 	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += nthreads) {
 		const bool valid = item < n_in;
@@ -679,12 +690,13 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				dx = (float)(ddx * inv); dy = (float)(ddy * inv); dz = (float)(ddz * inv);
 				const float lambda_0 = P.lambda_min + rand_1f(rng) * P.lambda_step;
 				if (!P.flat_field) P.ff[id] = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
-				P.st_od[0][item] = make_float4(ox, oy, oz, __int_as_float(-1));
-				P.st_dl[0][item] = make_float4(dx, dy, dz, lambda_0);
-				P.st_rng[0][item] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
-				P.st_id[0][item] = id;
+				P.recA[0][2 * (size_t)item] = make_float4(ox, oy, oz, __int_as_float(-1));
+				P.recA[0][2 * (size_t)item + 1] = make_float4(dx, dy, dz, lambda_0);
+				P.recR[0][2 * (size_t)item] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
+				                                          __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32)));
+				P.recR[0][2 * (size_t)item + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
 			} else {
-				const float4 a = P.st_od[pin][item], b = P.st_dl[pin][item];
+				const float4 a = P.recA[pin][2 * (size_t)item], b = P.recA[pin][2 * (size_t)item + 1];
 				ox = a.x; oy = a.y; oz = a.z; ignore = __float_as_int(a.w);
 				dx = b.x; dy = b.y; dz = b.z;
 			}
@@ -692,13 +704,16 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 			scene_intersect(S, P.eps, ignore, hit, ox, oy, oz, dx, dy, dz);
 			if (hit.quad >= 0) {
 				hq = (uint32_t)hit.quad | ((uint32_t)hit.tri << 31);
-				P.hit_a[item] = make_float4(hit.dist, hit.bx, hit.by, hit.bz);
+				// hit position (Ray::at, stdafx.hpp:219): origin of the shadow ray and of the next path ray
+				const float d_ = hit.dist;
+				P.recH[2 * (size_t)item] = make_float4(ox + d_ * dx, oy + d_ * dy, oz + d_ * dz, __uint_as_float(hq));
+				P.recH[2 * (size_t)item + 1] = make_float4(hit.bx, hit.by, hit.bz, 0.f);
 			} else {
 				// miss: L() returns 0 (renderer.cpp:161-163 with no hit); hit_anything only if an earlier depth hit
-				const uint32_t id = FIRST ? item : P.st_id[pin][item];
-				const float lambda_0 = FIRST ? P.st_dl[0][item].w : P.st_dl[pin][item].w;
+				const float4 r1 = P.recR[pin][2 * (size_t)item + 1];
+				const uint32_t id = __float_as_uint(r1.x);
 				P.leaf[id] = make_float4(0.f, 0.f, 0.f, 0.f);
-				P.meta[id] = make_float2(lambda_0, __int_as_float(depth | (FIRST ? 0 : (1 << 16))));
+				P.meta[id] = make_float2(r1.y, __int_as_float(depth | (FIRST ? 0 : (1 << 16))));
 			}
 			P.hit_q[item] = hq;
 		}
@@ -708,9 +723,12 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 		if (is_hit) {
 			const uint32_t q = hq & 0x7fffffffu;
 			const unsigned peers = __match_any_sync(hmask, q);
-			if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&bins[q], (uint32_t)__popc(peers));
+			if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_bins[q], (uint32_t)__popc(peers));
 		}
 	}
+	__syncthreads();
+	for (uint32_t q = threadIdx.x; q < SSB_MAX_QUADS; q += blockDim.x)
+		if (s_bins[q]) atomicAdd(&bins[q], s_bins[q]);
 }
 
 // ---- exclusive prefix sum of the per-quad hit counts of depth P.depth -> scatter cursors; one small CTA
@@ -723,27 +741,42 @@ __global__ void ssb_bin_scan_kernel(const __grid_constant__ KParams P, uint32_t 
 	P.nhits[P.depth] = acc;
 }
 
-// ---- counting-sort scatter: order[] = queue positions of the hit paths, grouped by hit quad
-__global__ void __launch_bounds__(256) ssb_bin_scatter_kernel(const __grid_constant__ KParams P, uint32_t first_depth) {
-	const unsigned full = 0xffffffffu;
+// ---- counting-sort scatter: order[] = queue positions of the hit paths, grouped by hit quad.  Each CTA takes tiles of
+// 4 x blockDim queue entries: it counts the tile's hits per quad in shared memory, reserves one contiguous range per
+// quad with a single global atomic, and places the entries through shared-memory cursors.
+#define SSB_SCATTER_PER_THREAD 4
+__global__ void __launch_bounds__(256) ssb_bin_scatter_kernel(const __grid_constant__ KParams P, uint32_t first_depth, uint32_t nquads) {
+	__shared__ uint32_t s_cnt[SSB_MAX_QUADS];
+	__shared__ uint32_t s_base[SSB_MAX_QUADS];
 	const int depth = (int)P.depth;
 	const uint32_t n_in = first_depth ? (uint32_t)P.total_work : P.counts[depth];
-	const uint32_t nthreads = gridDim.x * blockDim.x;
-	const uint32_t n_round = (n_in + 31u) & ~31u;
 	uint32_t* cur = P.bin_cursor + (size_t)depth * SSB_MAX_QUADS;
-	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += nthreads) {
-		const uint32_t hq = item < n_in ? P.hit_q[item] : 0xffffffffu;
-		const bool is_hit = hq != 0xffffffffu;
-		const unsigned hmask = __ballot_sync(full, is_hit);
-		if (is_hit) {
-			const uint32_t q = hq & 0x7fffffffu;
-			const unsigned peers = __match_any_sync(hmask, q);
-			const int leader = __ffs(peers) - 1;
-			uint32_t base = 0;
-			if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cur[q], (uint32_t)__popc(peers));
-			base = __shfl_sync(peers, base, leader);
-			P.order[base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = item;
+	const uint32_t tile = blockDim.x * SSB_SCATTER_PER_THREAD;
+	for (uint32_t t0 = blockIdx.x * tile; t0 < n_in; t0 += gridDim.x * tile) {
+		for (uint32_t q = threadIdx.x; q < nquads; q += blockDim.x) s_cnt[q] = 0;
+		__syncthreads();
+		uint32_t hq[SSB_SCATTER_PER_THREAD];
+#pragma unroll
+		for (int k = 0; k < SSB_SCATTER_PER_THREAD; ++k) {
+			const uint32_t item = t0 + k * blockDim.x + threadIdx.x;
+			hq[k] = item < n_in ? P.hit_q[item] : 0xffffffffu;
+			if (hq[k] != 0xffffffffu) atomicAdd(&s_cnt[hq[k] & 0x7fffffffu], 1u);
 		}
+		__syncthreads();
+		for (uint32_t q = threadIdx.x; q < nquads; q += blockDim.x) {
+			const uint32_t c = s_cnt[q];
+			s_base[q] = c ? atomicAdd(&cur[q], c) : 0u;
+			s_cnt[q] = 0;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < SSB_SCATTER_PER_THREAD; ++k) {
+			if (hq[k] != 0xffffffffu) {
+				const uint32_t q = hq[k] & 0x7fffffffu;
+				P.order[s_base[q] + atomicAdd(&s_cnt[q], 1u)] = t0 + k * blockDim.x + threadIdx.x;
+			}
+		}
+		__syncthreads();
 	}
 }
 
@@ -776,20 +809,17 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 		Rng rng; rng.state = 0; rng.inc = 1;
 		if (valid) {
 			const uint32_t item = P.order[slot];
-			{
-				const float4 a = P.st_od[pin][item], b = P.st_dl[pin][item];
-				const uint4 r = P.st_rng[pin][item];
-				id = P.st_id[pin][item];
-				ox = a.x; oy = a.y; oz = a.z;
-				dx = b.x; dy = b.y; dz = b.z; lambda_0 = b.w;
-				rng.state = ((unsigned long long)r.y << 32) | r.x;
-				rng.inc = ((unsigned long long)r.w << 32) | r.z;
-			}
-			const float4 ha = P.hit_a[item];
-			const uint32_t hq = P.hit_q[item];
+			const float4 h0 = P.recH[2 * (size_t)item], h1 = P.recH[2 * (size_t)item + 1];
+			const float4 r0 = P.recR[pin][2 * (size_t)item], r1 = P.recR[pin][2 * (size_t)item + 1];
+			const float hx = h0.x, hy = h0.y, hz = h0.z;  // hit position
+			const uint32_t hq = __float_as_uint(h0.w);
+			id = __float_as_uint(r1.x);
+			lambda_0 = r1.y;
+			rng.state = ((unsigned long long)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
+			rng.inc = ((unsigned long long)__float_as_uint(r0.w) << 32) | __float_as_uint(r0.z);
 			Hit hit;
 			hit.quad = (int)(hq & 0x7fffffffu); hit.tri = (int)(hq >> 31);
-			hit.dist = ha.x; hit.bx = ha.y; hit.by = ha.z; hit.bz = ha.w;
+			hit.dist = 0.0f; hit.bx = h1.x; hit.by = h1.y; hit.bz = h1.z;
 
 			Hero rad;  // value this L() call returns if the path ends here
 			rad.v[0] = rad.v[1] = rad.v[2] = rad.v[3] = 0.0f;
@@ -811,9 +841,6 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 					for (int c = 0; c < 4; ++c) local.v[c] = local.v[c] + e.v[c];
 				}
 				if ((uint32_t)depth + 1u < P.max_depth) {
-					// hit position (Ray::at): origin of the shadow ray and of the next path ray
-					const float d_ = hit.dist;
-					const float hx = ox + d_ * dx, hy = oy + d_ * dy, hz = oz + d_ * dz;
 					// albedo lookup (the reference does it twice with identical arguments, material.cpp:120-143)
 					Hero f_s = material_albedo<UPS>(P, S, m, st_x, st_y, lambda_0);
 					if (m.kind == SSB_MATERIAL_LAMBERT) {
@@ -871,7 +898,8 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 						wiz = (cx * bxz + cy * nz) + cz * bzz;
 					} else {
 						// MaterialMirror::interact_bsdf (material.cpp:154-167): reflect(w_o = -ray.dir, N)
-						float vx = -dx, vy = -dy, vz = -dz;
+						const float4 din = P.recA[pin][2 * (size_t)item + 1];
+						float vx = -din.x, vy = -din.y, vz = -din.z;
 						float d2 = 2.0f * dot3(vx, vy, vz, nx, ny, nz);
 						wix = -vx + d2 * nx; wiy = -vy + d2 * ny; wiz = -vz + d2 * nz;
 						pdf_w_i = __int_as_float(0x7f800000);
@@ -920,10 +948,11 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			base = __shfl_sync(full, base, leader);
 			if (cont) {
 				const uint32_t o = base + __popc(mask & ((1u << lane) - 1u));
-				P.st_od[pout][o] = make_float4(ox, oy, oz, __int_as_float(ignore));
-				P.st_dl[pout][o] = make_float4(dx, dy, dz, lambda_0);
-				P.st_rng[pout][o] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
-				P.st_id[pout][o] = id;
+				P.recA[pout][2 * (size_t)o] = make_float4(ox, oy, oz, __int_as_float(ignore));
+				P.recA[pout][2 * (size_t)o + 1] = make_float4(dx, dy, dz, lambda_0);
+				P.recR[pout][2 * (size_t)o] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
+				                                          __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32)));
+				P.recR[pout][2 * (size_t)o + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
 			}
 		}
 	}
