@@ -12,6 +12,7 @@ Renderer::Renderer(RendererOptions const& opts) : options(opts) {
 	framebuffer.reset(options.res[0], options.res[1]);
 	color = color_init(options.data_root, options.observer, options.upsampling);  // Color::init(), main.cpp:181
 	scene = scene_new(options.scene_name, options.data_root, color, options.explicit_light_sampling);
+	scene.flatten();  // the flat view holds pointers into the Scene object: rebuild it for this copy
 	if (options.scene_name == "plane-srgb" && options.explicit_light_sampling)  // renderer.cpp:27-31
 		std::fprintf(stderr, "Warning: Plane converges much faster without explicit light sampling!\n");
 	if (options.scene_name != "plane-srgb" && !options.explicit_light_sampling)  // renderer.cpp:18-26
