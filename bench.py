@@ -313,7 +313,7 @@ def main_ours(args, rank, local_rank, world):
             "dtype": "f32", "data": "reference scene (hard-coded cornell-srgb geometry, shipped spectra + 4096^2 sRGB texture); per-sample seeded RNG",
             "config": {"workload": f"{SCENE} {W}x{H} spp{SPP} per GPU (job spp {total_spp}), hero-wavelength x4, OURS upsampling, CIE1931, "
                                    f"ELS on, MAX_DEPTH 10", "parallelism": f"sample-sharded x{world}, one NCCL reduce of f64 XYZA" if world > 1 else "single GPU",
-                       "l2": "no flush needed: each step rewrites a 268 MB sample buffer (> 126 MB L2) and re-reads it",
+                       "l2": "no flush needed: every step streams ~8 GB of path records / fold records through HBM (>> 126 MB L2)",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -321,10 +321,12 @@ def main_ours(args, rank, local_rank, world):
                     "calls": "ssb_upload_color + ssb_upload_scene (pinned RGB8 texture) + ssb_render_frame -> pinned XYZA f64 + sRGBA f32"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "ssb_trace_kernel", "kernel_ms": trace_ms,
+                         "peak_source": peak_src,
+                         "kernel": "bounce stage = ssb_intersect_kernel + counting sort + ssb_shade_kernel over all path depths of one frame "
+                                   "(CUDA events around the launch sequence)", "kernel_ms": trace_ms,
                          "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE[SCENE],
-                         "note": "HBM-model bytes of SURVEY.md §8(d) (wavefront ray-state traffic); the kernel keeps path state in registers, "
-                                 "so its real bound is fp32 issue — see DESIGN.md"},
+                         "note": "achieved = SURVEY.md 8(d) algorithmic bytes (wavefront ray-state model) / bounce-stage time; traffic = ncu dram bytes of the "
+                                 "same launches (profiles/). The stage is instruction-issue bound (un-fused fp32 + f64 exact libm), DRAM ~20-30 % busy: see DESIGN.md (d)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
