@@ -169,6 +169,7 @@ def main_ours(args, rank, local_rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     W, H, SPP = args.width, args.height, args.spp

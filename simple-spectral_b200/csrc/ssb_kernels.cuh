@@ -783,6 +783,18 @@ __global__ void __launch_bounds__(256) ssb_bin_scatter_kernel(const __grid_const
 // ---- stage 2 of a bounce: everything the reference's lambda L does after the closest hit (renderer.cpp:165-251)
 // for the paths that hit something, visited grouped by hit quad: emission, albedo, light sample + shadow query,
 // BSDF sample, fold record, and the compacted state of the continuing paths.
+// The body is written as phases separated by CTA barriers (SSB_SHADE_SYNC): the kernel is ~45 KB of mostly
+// straight-line code, and ncu showed `no_instruction` (instruction fetch) as its top stall with every warp streaming
+// the code on its own; the barriers keep the 8 warps of a CTA inside the same code region so that they share fetched
+// lines.  The barriers are outside all data-dependent control flow (the loop trip count is uniform per CTA).
+#ifndef SSB_SHADE_SYNC
+#define SSB_SHADE_SYNC 1
+#endif
+#if SSB_SHADE_SYNC
+#define SSB_PHASE_BARRIER() __syncthreads()
+#else
+#define SSB_PHASE_BARRIER() ((void)0)
+#endif
 template <bool FIRST, int UPS>
 __global__ void __launch_bounds__(SSB_SHADE_THREADS, SSB_SHADE_MIN_BLOCKS)
 ssb_shade_kernel(const __grid_constant__ KParams P) {
@@ -798,139 +810,153 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 	const uint32_t n_in = P.nhits[depth];
 	const int pin = depth & 1, pout = pin ^ 1;
 	const uint32_t nthreads = gridDim.x * blockDim.x;
-	const uint32_t n_round = (n_in + 31u) & ~31u;
+	const uint32_t n_round = (n_in + blockDim.x - 1u) / blockDim.x * blockDim.x;  // uniform trip count per CTA (barriers)
+	const bool more_depth = (uint32_t)depth + 1u < P.max_depth;
+	const bool light_phase = more_depth && els && (!P.indirect_only || !FIRST);
 
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += nthreads) {
 		const bool valid = slot < n_in;
 		bool cont = false;  // path continues to depth+1
 		float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, lambda_0 = 0;
 		int ignore = -1;
-		uint32_t id = 0;
+		uint32_t id = 0, item = 0;
 		Rng rng; rng.state = 0; rng.inc = 1;
+		float hx = 0, hy = 0, hz = 0, nx = 0, ny = 0, nz = 1;
+		int cur_quad = 0;
+		uint32_t mat_kind = SSB_MATERIAL_LAMBERT;
+		Hero local, f_s;
+		local.v[0] = local.v[1] = local.v[2] = local.v[3] = 0.0f;
+		f_s = local;
+
+		// ---- phase 0: gather the path, emission, albedo (renderer.cpp:165-175; material.cpp:120-143)
 		if (valid) {
-			const uint32_t item = P.order[slot];
+			item = P.order[slot];
 			const float4 h0 = P.recH[2 * (size_t)item], h1 = P.recH[2 * (size_t)item + 1];
 			const float4 r0 = P.recR[pin][2 * (size_t)item], r1 = P.recR[pin][2 * (size_t)item + 1];
-			const float hx = h0.x, hy = h0.y, hz = h0.z;  // hit position
+			hx = h0.x; hy = h0.y; hz = h0.z;  // hit position
 			const uint32_t hq = __float_as_uint(h0.w);
 			id = __float_as_uint(r1.x);
 			lambda_0 = r1.y;
 			rng.state = ((unsigned long long)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
 			rng.inc = ((unsigned long long)__float_as_uint(r0.w) << 32) | __float_as_uint(r0.z);
-			Hit hit;
-			hit.quad = (int)(hq & 0x7fffffffu); hit.tri = (int)(hq >> 31);
-			hit.dist = 0.0f; hit.bx = h1.x; hit.by = h1.y; hit.bz = h1.z;
+			cur_quad = (int)(hq & 0x7fffffffu);
+			const ssb_quad& quad = S.quads()[cur_quad];
+			const ssb_tri& tri = quad.tri[hq >> 31];
+			const DevMaterial& m = S.materials()[quad.material];
+			mat_kind = m.kind;
+			nx = tri.normal[0]; ny = tri.normal[1]; nz = tri.normal[2];
+			const float st_x = (h1.x * tri.v[0].st[0] + h1.y * tri.v[1].st[0]) + h1.z * tri.v[2].st[0];
+			const float st_y = (h1.x * tri.v[0].st[1] + h1.y * tri.v[1].st[1]) + h1.z * tri.v[2].st[1];
+			// emission: last_was_delta is true only for the camera ray (the reference recurses with `false`, :248)
+			if (!els || (FIRST && !P.indirect_only)) {
+				Hero e = spec_hero(S.pool(), m.emission, lambda_0, P.lambda_step);
+#pragma unroll
+				for (int c = 0; c < 4; ++c) local.v[c] = local.v[c] + e.v[c];
+			}
+			if (more_depth) {
+				// albedo lookup (the reference does it twice with identical arguments, material.cpp:120-143)
+				f_s = material_albedo<UPS>(P, S, m, st_x, st_y, lambda_0);
+				if (mat_kind == SSB_MATERIAL_LAMBERT) {
+#pragma unroll
+					for (int c = 0; c < 4; ++c) f_s.v[c] = f_s.v[c] / SSB_PI_F;
+				}
+			}
+		}
+		SSB_PHASE_BARRIER();
 
+		// ---- phase 1: light sample (renderer.cpp:182-191; Scene::get_rand_toward_light, scene.cpp:417-431)
+		float sx = 0, sy = 0, sz = 1, pdf = 1.0f, l_ndl = 0.0f;
+		int light_quad = -1;
+		if (valid && light_phase) {
+			uint32_t li = rand_choice(rng, S.hdr()->nlights);
+			light_quad = (int)S.lights()[li];
+			const int lt = (rand_1f(rng) <= 0.5f) ? 0 : 1;
+			float r0 = rand_1f(rng);
+			float r1 = rand_1f(rng);
+			sample_spherical_triangle(light_quad, lt, hx, hy, hz, r0, r1, sx, sy, sz, pdf);
+			pdf *= 0.5f;
+			pdf /= (float)S.hdr()->nlights;
+			l_ndl = dot3(sx, sy, sz, nx, ny, nz);
+		}
+		SSB_PHASE_BARRIER();
+
+		// ---- phase 2: shadow query + direct contribution (renderer.cpp:192-218)
+		if (valid && light_phase && l_ndl > 0.0f) {
+			Hit hs;
+			scene_intersect(S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
+			if (hs.quad == light_quad) {
+				const DevMaterial& lm = S.materials()[S.quads()[light_quad].material];
+				Hero emitted = spec_hero(S.pool(), lm.emission, lambda_0, P.lambda_step);
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					float fe = (mat_kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;  // MaterialMirror::evaluate_bsdf = 0
+					local.v[c] = local.v[c] + ((emitted.v[c] * l_ndl) * fe) / pdf;
+				}
+			}
+		}
+		SSB_PHASE_BARRIER();
+
+		// ---- phase 3: interact_bsdf + recursion decision + records (renderer.cpp:222-251)
+		if (valid) {
 			Hero rad;  // value this L() call returns if the path ends here
 			rad.v[0] = rad.v[1] = rad.v[2] = rad.v[3] = 0.0f;
-			int nrec = depth;            // fold records written by shallower depths
-			{
-				const int cur_quad = hit.quad;
-				const ssb_quad& quad = S.quads()[cur_quad];
-				const ssb_tri& tri = quad.tri[hit.tri];
-				const DevMaterial& m = S.materials()[quad.material];
-				const float nx = tri.normal[0], ny = tri.normal[1], nz = tri.normal[2];
-				const float st_x = (hit.bx * tri.v[0].st[0] + hit.by * tri.v[1].st[0]) + hit.bz * tri.v[2].st[0];
-				const float st_y = (hit.bx * tri.v[0].st[1] + hit.by * tri.v[1].st[1]) + hit.bz * tri.v[2].st[1];
-				Hero local;
-				local.v[0] = local.v[1] = local.v[2] = local.v[3] = 0.0f;
-				// emission: last_was_delta is true only for the camera ray (the reference recurses with `false`, :248)
-				if (!els || (FIRST && !P.indirect_only)) {
-					Hero e = spec_hero(S.pool(), m.emission, lambda_0, P.lambda_step);
-#pragma unroll
-					for (int c = 0; c < 4; ++c) local.v[c] = local.v[c] + e.v[c];
+			int nrec = depth;  // fold records written by shallower depths
+			if (more_depth) {
+				float wix, wiy, wiz, pdf_w_i;
+				if (mat_kind == SSB_MATERIAL_LAMBERT) {
+					float cx, cy, cz;  // Math::rand_coshemi (random.cpp:29-49)
+					do {
+						float angle = rand_1f(rng) * (2.0f * SSB_PI_F);
+						float co = cosf_x(angle), si = sinf_x(angle);
+						float radius_sq = rand_1f(rng);
+						float radius = sqrtf(radius_sq);
+						cx = radius * co; cy = sqrtf(1.0f - radius_sq); cz = radius * si;
+						pdf_w_i = cy;
+					} while (pdf_w_i <= eps);
+					pdf_w_i *= 1.0f / SSB_PI_F;
+					// Math::get_rotated_to / get_basis (math-helpers.hpp:14-38)
+					float sign = copysignf(1.0f, nz);
+					float a = -1.0f / (sign + nz);
+					float b = nx * ny * a;
+					float bxx = 1.0f + sign * nx * nx * a, bxy = sign * b, bxz = -sign * nx;
+					float bzx = b, bzy = sign + ny * ny * a, bzz = -ny;
+					wix = (cx * bxx + cy * nx) + cz * bzx;
+					wiy = (cx * bxy + cy * ny) + cz * bzy;
+					wiz = (cx * bxz + cy * nz) + cz * bzz;
+				} else {
+					// MaterialMirror::interact_bsdf (material.cpp:154-167): reflect(w_o = -ray.dir, N)
+					const float4 din = P.recA[pin][2 * (size_t)item + 1];
+					float vx = -din.x, vy = -din.y, vz = -din.z;
+					float d2 = 2.0f * dot3(vx, vy, vz, nx, ny, nz);
+					wix = -vx + d2 * nx; wiy = -vy + d2 * ny; wiz = -vz + d2 * nz;
+					pdf_w_i = __int_as_float(0x7f800000);
 				}
-				if ((uint32_t)depth + 1u < P.max_depth) {
-					// albedo lookup (the reference does it twice with identical arguments, material.cpp:120-143)
-					Hero f_s = material_albedo<UPS>(P, S, m, st_x, st_y, lambda_0);
-					if (m.kind == SSB_MATERIAL_LAMBERT) {
-#pragma unroll
-						for (int c = 0; c < 4; ++c) f_s.v[c] = f_s.v[c] / SSB_PI_F;
-					}
-					if (els && (!P.indirect_only || !FIRST)) {
-						// ---- direct lighting (renderer.cpp:182-220; Scene::get_rand_toward_light, scene.cpp:417-431)
-						uint32_t li = rand_choice(rng, S.hdr()->nlights);
-						const int light_quad = (int)S.lights()[li];
-						const ssb_quad& lq = S.quads()[light_quad];
-						const int lt = (rand_1f(rng) <= 0.5f) ? 0 : 1;
-						float r0 = rand_1f(rng);
-						float r1 = rand_1f(rng);
-						float sx, sy, sz, pdf;
-						sample_spherical_triangle(light_quad, lt, hx, hy, hz, r0, r1, sx, sy, sz, pdf);
-						pdf *= 0.5f;
-						pdf /= (float)S.hdr()->nlights;
-						const float l_ndl = dot3(sx, sy, sz, nx, ny, nz);
-						if (l_ndl > 0.0f) {
-							Hit hs;
-							scene_intersect(S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
-							if (hs.quad == light_quad) {
-								const DevMaterial& lm = S.materials()[lq.material];
-								Hero emitted = spec_hero(S.pool(), lm.emission, lambda_0, P.lambda_step);
-#pragma unroll
-								for (int c = 0; c < 4; ++c) {
-									float fe = (m.kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;  // MaterialMirror::evaluate_bsdf = 0
-									local.v[c] = local.v[c] + ((emitted.v[c] * l_ndl) * fe) / pdf;
-								}
-							}
-						}
-					}
-					// ---- interact_bsdf + recursion decision (renderer.cpp:222-251)
-					float wix, wiy, wiz, pdf_w_i;
-					if (m.kind == SSB_MATERIAL_LAMBERT) {
-						float cx, cy, cz;  // Math::rand_coshemi (random.cpp:29-49)
-						do {
-							float angle = rand_1f(rng) * (2.0f * SSB_PI_F);
-							float co = cosf_x(angle), si = sinf_x(angle);
-							float radius_sq = rand_1f(rng);
-							float radius = sqrtf(radius_sq);
-							cx = radius * co; cy = sqrtf(1.0f - radius_sq); cz = radius * si;
-							pdf_w_i = cy;
-						} while (pdf_w_i <= eps);
-						pdf_w_i *= 1.0f / SSB_PI_F;
-						// Math::get_rotated_to / get_basis (math-helpers.hpp:14-38)
-						float sign = copysignf(1.0f, nz);
-						float a = -1.0f / (sign + nz);
-						float b = nx * ny * a;
-						float bxx = 1.0f + sign * nx * nx * a, bxy = sign * b, bxz = -sign * nx;
-						float bzx = b, bzy = sign + ny * ny * a, bzz = -ny;
-						wix = (cx * bxx + cy * nx) + cz * bzx;
-						wiy = (cx * bxy + cy * ny) + cz * bzy;
-						wiz = (cx * bxz + cy * nz) + cz * bzz;
-					} else {
-						// MaterialMirror::interact_bsdf (material.cpp:154-167): reflect(w_o = -ray.dir, N)
-						const float4 din = P.recA[pin][2 * (size_t)item + 1];
-						float vx = -din.x, vy = -din.y, vz = -din.z;
-						float d2 = 2.0f * dot3(vx, vy, vz, nx, ny, nz);
-						wix = -vx + d2 * nx; wiy = -vy + d2 * ny; wiz = -vz + d2 * nz;
-						pdf_w_i = __int_as_float(0x7f800000);
-					}
-					bool recurse = false;
-					float n_dot_l = 0.0f;
-					float ff = (f_s.v[0] * f_s.v[0] + f_s.v[1] * f_s.v[1]) + (f_s.v[2] * f_s.v[2] + f_s.v[3] * f_s.v[3]);
-					if (ff > 0.0f) {
-						if (isfinite(pdf_w_i)) n_dot_l = dot3(wix, wiy, wiz, nx, ny, nz);
-						else { n_dot_l = 1.0f; pdf_w_i = 1.0f; }
-						recurse = n_dot_l > 0.0f;
-					}
-					if (recurse) {
-						const size_t rec = (size_t)depth * P.total_work + id;
-						P.stk_local[rec] = make_float4(local.v[0], local.v[1], local.v[2], local.v[3]);
-						P.stk_f[rec] = make_float4(f_s.v[0], f_s.v[1], f_s.v[2], f_s.v[3]);
-						P.stk_np[rec] = make_float2(n_dot_l, pdf_w_i);
-						nrec = depth + 1;
-						// Dead-work skip (result-identical): with explicit light sampling the L() call at the last depth
-						// can add neither emission (last_was_delta == false) nor children: it returns 0, hit_anything is
-						// already set and no random numbers are drawn there.  rad stays 0.
-						if (!(els && (uint32_t)depth + 2u >= P.max_depth)) {
-							cont = true;
-							ox = hx; oy = hy; oz = hz; dx = wix; dy = wiy; dz = wiz; ignore = cur_quad;
-						}
-					} else {
-						rad = local;
+				bool recurse = false;
+				float n_dot_l = 0.0f;
+				float ff = (f_s.v[0] * f_s.v[0] + f_s.v[1] * f_s.v[1]) + (f_s.v[2] * f_s.v[2] + f_s.v[3] * f_s.v[3]);
+				if (ff > 0.0f) {
+					if (isfinite(pdf_w_i)) n_dot_l = dot3(wix, wiy, wiz, nx, ny, nz);
+					else { n_dot_l = 1.0f; pdf_w_i = 1.0f; }
+					recurse = n_dot_l > 0.0f;
+				}
+				if (recurse) {
+					const size_t rec = (size_t)depth * P.total_work + id;
+					P.stk_local[rec] = make_float4(local.v[0], local.v[1], local.v[2], local.v[3]);
+					P.stk_f[rec] = make_float4(f_s.v[0], f_s.v[1], f_s.v[2], f_s.v[3]);
+					P.stk_np[rec] = make_float2(n_dot_l, pdf_w_i);
+					nrec = depth + 1;
+					// Dead-work skip (result-identical): with explicit light sampling the L() call at the last depth
+					// can add neither emission (last_was_delta == false) nor children: it returns 0, hit_anything is
+					// already set and no random numbers are drawn there.  rad stays 0.
+					if (!(els && (uint32_t)depth + 2u >= P.max_depth)) {
+						cont = true;
+						ox = hx; oy = hy; oz = hz; dx = wix; dy = wiy; dz = wiz; ignore = cur_quad;
 					}
 				} else {
 					rad = local;
 				}
+			} else {
+				rad = local;
 			}
 			// ---- the path ends here: the deepest L() call returns `rad`, `nrec` records wait to be folded
 			if (!cont) {
@@ -955,6 +981,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 				P.recR[pout][2 * (size_t)o + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
 			}
 		}
+		SSB_PHASE_BARRIER();
 	}
 }
 
