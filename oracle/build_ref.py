@@ -38,6 +38,10 @@ VARIANTS = {
     "ours2006": dict(alg=1, observer=2006),
     "meng": dict(alg=2, observer=1931),
     "jh": dict(alg=3, observer=1931),
+    # EXPLICIT_LIGHT_SAMPLING compiled out (stdafx.hpp:44): exercises MaterialMirror (scene.cpp:346-355) and emission
+    # on every hit (renderer.cpp:167-175).  (FLAT_FIELD_CORRECTION cannot be compiled out in this mode: the reference's
+    # own color.cpp:275-279 then refers to an undeclared `flux`.)
+    "ours1931_noels": dict(alg=1, observer=1931, no_els=True),
 }
 CXX_SOURCES = [
     "main.cpp", "renderer.cpp", "scene.cpp", "geometry.cpp", "material.cpp", "spectrum.cpp",
@@ -65,9 +69,13 @@ def sub_once(text, pattern, repl, what):
     return new
 
 
-def patch_variant(src_dir, alg, observer):
+def patch_variant(src_dir, alg, observer, no_els=False, no_ffc=False):
     p = os.path.join(src_dir, "stdafx.hpp")
     t = open(p, encoding="utf-8-sig").read()
+    if no_els:
+        t = sub_once(t, r"^#define EXPLICIT_LIGHT_SAMPLING$", "//#define EXPLICIT_LIGHT_SAMPLING", "ELS")
+    if no_ffc:
+        t = sub_once(t, r"^#define FLAT_FIELD_CORRECTION$", "//#define FLAT_FIELD_CORRECTION", "FFC")
     t = sub_once(t, r"#define RENDER_MODE_SPECTRAL_ALGNUM 1", f"#define RENDER_MODE_SPECTRAL_ALGNUM {alg}", "ALGNUM")
     if observer == 2006:
         t = sub_once(t, r"#if 1(\s+#define CIE_OBSERVER 1931)", r"#if 0\1", "CIE_OBSERVER")
@@ -102,7 +110,7 @@ def patch_hooks(src_dir):
     open(p, "w", encoding="utf-8").write(t)
 
 
-def build_one(tmp, name, alg, observer, hooked, lodepng_obj):
+def build_one(tmp, name, alg, observer, hooked, lodepng_obj, **variant_kw):
     tag = name + ("_hooked" if hooked else "")
     src_dir = os.path.join(tmp, tag, "src")
     shutil.copytree(os.path.join(REF, "src"), src_dir, ignore=shutil.ignore_patterns("lodepng*"))
@@ -110,7 +118,7 @@ def build_one(tmp, name, alg, observer, hooked, lodepng_obj):
         os.chmod(root, 0o755)
         for f in files:
             os.chmod(os.path.join(root, f), 0o644)
-    patch_variant(src_dir, alg, observer)
+    patch_variant(src_dir, alg, observer, **variant_kw)
     if hooked:
         patch_hooks(src_dir)
     flags = FLAGS_HOOKED if hooked else FLAGS_PRISTINE
@@ -147,7 +155,8 @@ def main():
             for name in which:
                 v = VARIANTS[name]
                 for hooked in (False, True):
-                    jobs.append(ex.submit(build_one, tmp, name, v["alg"], v["observer"], hooked, lodepng_obj))
+                    kw = {k: v[k] for k in ("no_els", "no_ffc") if k in v}
+                    jobs.append(ex.submit(build_one, tmp, name, v["alg"], v["observer"], hooked, lodepng_obj, **kw))
             for j in jobs:
                 print("built", os.path.relpath(j.result(), os.path.dirname(HERE)))
     finally:

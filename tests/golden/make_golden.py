@@ -27,6 +27,8 @@ CASES = [  # (scene, variant)
     ("cornell", "ours2006"), ("cornell-srgb", "ours2006"),
     ("cornell-srgb", "jh"), ("plane-srgb", "jh"),
     ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
+    # EXPLICIT_LIGHT_SAMPLING compiled out: MaterialMirror on the plane (scene.cpp:346-355), emission on every hit
+    ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels"),
 ]
 SMALL = dict(w=32, h=24, spp=4, seed=7)
 C1 = dict(w=128, h=128, spp=16, seed=1)  # BASELINE.json configs[0]

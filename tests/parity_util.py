@@ -19,6 +19,7 @@ VARIANT_OPTS = {  # compile-time variants of the reference (stdafx.hpp:66,81) as
     "ours2006": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=390.0, lambda_max=830.0),
     "jh": dict(upsampling=abi.SSB_UPSAMPLE_JH, lambda_min=380.0, lambda_max=780.0),
     "meng": dict(upsampling=abi.SSB_UPSAMPLE_MENG, lambda_min=380.0, lambda_max=780.0),
+    "ours1931_noels": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, explicit_light_sampling=0),
 }
 
 

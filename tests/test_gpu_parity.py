@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 CASES = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("plane-srgb", "ours1931"),
          ("cornell", "ours2006"), ("cornell-srgb", "ours2006"),
-         ("cornell-srgb", "jh"), ("plane-srgb", "jh"), ("cornell-srgb", "meng"), ("plane-srgb", "meng")]
+         ("cornell-srgb", "jh"), ("plane-srgb", "jh"), ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
+         ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels")]
 
 
 def _skip_if_no_assets(scene, variant):
