@@ -138,3 +138,20 @@ def test_gpu_config2_bit_exact_vs_oracle():
         acc_g = ctx.read_accum(512, 512)
     acc_o, _, _ = pu.oracle_render(flat, opt)
     assert pu.bits_equal(acc_g, acc_o), f"max rel {pu.rel_err(acc_g, acc_o).max()}"
+
+
+def test_gpu_multipass_equals_single_pass(monkeypatch):
+    """Frames whose path state does not fit the per-pass memory budget are rendered in several sample passes
+    (configs 3-5 of BASELINE.json need this): the accumulators must not depend on the pass split."""
+    flat = pu.load_flat("cornell", "ours1931")
+    opt = pu.options("ours1931", 64, 48, 8, seed=5)
+    with pu.gpu_context(flat) as ctx:
+        ctx.render(opt)
+        want = ctx.read_accum(64, 48)
+        assert ctx.stats().launches < 60
+    monkeypatch.setenv("SSB_WAVE_BUDGET_MB", "4")  # 64*48 pixels * ~650 B -> 2 samples per pass
+    with pu.gpu_context(flat) as ctx:
+        ctx.render(opt)
+        got = ctx.read_accum(64, 48)
+        assert ctx.stats().launches > 100  # several passes
+    assert pu.bits_equal(got, want)
