@@ -482,7 +482,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 
 	// ---- size one pass: N = npix_rect * chunk samples share the wavefront buffers
 	const uint32_t nrec_depths = o->max_depth > 1 ? o->max_depth - 1 : 1;
-	const size_t bytes_per_sample = 2 * (32 + 64) + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (4 + 4);
+	const size_t bytes_per_sample = 2 * (32 + 32) + 32 + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (4 + 4);
 	size_t budget = kWaveBudgetBytes;
 	if (const char* e = getenv("SSB_WAVE_BUDGET_MB")) {  // tests force multi-pass rendering with a tiny budget
 		long mb = atol(e);
@@ -495,7 +495,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	auto up = [](size_t v) { return (v + 255) / 256 * 256; };
 	size_t off = 0;
 	const size_t o_a0 = off; off += up(N * 32); const size_t o_a1 = off; off += up(N * 32);
-	const size_t o_s0 = off; off += up(N * 64); const size_t o_s1 = off; off += up(N * 64);
+	const size_t o_r0 = off; off += up(N * 32); const size_t o_r1 = off; off += up(N * 32);
+	const size_t o_h = off; off += up(N * 32);
 	const size_t o_sl = off; off += up(N * nrec_depths * 16);
 	const size_t o_sf = off; off += up(N * nrec_depths * 16);
 	const size_t o_sn = off; off += up(N * nrec_depths * 8);
@@ -521,7 +522,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.blob = c->d_blob;
 	unsigned char* wv = c->d_wave;
 	P.recA[0] = reinterpret_cast<float4*>(wv + o_a0); P.recA[1] = reinterpret_cast<float4*>(wv + o_a1);
-	P.recS[0] = reinterpret_cast<float4*>(wv + o_s0); P.recS[1] = reinterpret_cast<float4*>(wv + o_s1);
+	P.recR[0] = reinterpret_cast<float4*>(wv + o_r0); P.recR[1] = reinterpret_cast<float4*>(wv + o_r1);
+	P.recH = reinterpret_cast<float4*>(wv + o_h);
 	P.stk_local = reinterpret_cast<float4*>(wv + o_sl); P.stk_f = reinterpret_cast<float4*>(wv + o_sf);
 	P.stk_np = reinterpret_cast<float2*>(wv + o_sn);
 	P.leaf = reinterpret_cast<float4*>(wv + o_leaf); P.meta = reinterpret_cast<float2*>(wv + o_meta);

@@ -22,9 +22,9 @@
 // double XYZA accumulator in sample order (renderer.cpp:292-295): deterministic, no float/double atomics.
 // History (profiles/): a register-resident megakernel reached 154-222 Msamples/s with 9.8 of 32 lanes active
 // and instruction-cache thrash on 131 KB of SASS; the wavefront forms reach 500-600+.
-// Path state lives in HBM as sector-sized records: recA (32 B) {origin, ignore | direction, lambda0} feeds the
-// intersect stage; recS (64 B) {PCG32 | sample id, lambda0 || hit point, quad | barycentrics} feeds the shade stage
-// (second half written by the intersect stage), gathered with one 64-byte access per path.  The scene, materials, spectra, observer/basis tables, filter records and the sRGB LUT are one
+// Path state lives in HBM as 32-byte (one sector) records: recA {origin, ignore | direction, lambda0} feeds the
+// intersect stage, recH {hit point, quad | barycentrics} goes intersect -> shade, recR {PCG32 | sample id} feeds
+// the shade stage.  The scene, materials, spectra, observer/basis tables, filter records and the sRGB LUT are one
 // contiguous "blob" that each CTA pulls into shared memory with a single TMA bulk copy
 // (cp.async.bulk.shared::cluster.global + mbarrier).
 #pragma once
@@ -66,12 +66,12 @@ struct KParams {
 	const unsigned char* blob;
 	// Path state in HBM, one 32-byte sector per record so that every access moves whole sectors:
 	//   recA[2] (ping-pong): ray        {origin.xyz, ignore (int bits)} {direction.xyz, lambda_0}   read by the intersect stage
-	//   recS[2] (ping-pong), 64 B = {PCG32 state, inc}{sample id, lambda_0, -, -} | {hit point.xyz, quad|tri<<31}{barycentrics, -}
-	//                        first sector written with recA by the stage that creates the ray, second sector by the
-	//                        intersect stage; the shade stage gathers both with one 64-byte access per path.
-	// recA/recS are written densely (compacted) and indexed by queue position.
+	//   recR[2] (ping-pong): the rest   {PCG32 state, inc}              {sample id, lambda_0, -, -}  read by the shade stage
+	//   recH               : closest hit {hit point.xyz, quad|tri<<31}  {barycentrics, -}            intersect -> shade
+	// recA/recR are written densely (compacted) by the stage that creates the next ray; recH is indexed like the queue.
 	float4* recA[2];
-	float4* recS[2];
+	float4* recR[2];
+	float4* recH;
 	// per-depth records for the backward fold, indexed [depth][sample id]
 	float4* stk_local;
 	float4* stk_f;
@@ -82,7 +82,7 @@ struct KParams {
 	float* ff;          // dot(camera ray, camera dir), only when FLAT_FIELD_CORRECTION is off (renderer.cpp:265)
 	uint32_t* counts;   // queue length per depth; counts[0] = samples in the pass
 	// closest-hit records of the current depth (indexed like the input queue) and the sort-by-quad machinery
-	uint32_t* hit_q;    // quad | tri << 31, or 0xffffffff for a miss (dense copy for the counting sort)
+	uint32_t* hit_q;    // quad | tri << 31, or 0xffffffff for a miss (dense copy of recH[].w for the counting sort)
 	uint32_t* order;    // queue positions of the paths that hit something, grouped by hit quad
 	uint32_t* bin_count;   // [max_depth][SSB_MAX_QUADS] paths per hit quad
 	uint32_t* bin_cursor;  // [max_depth][SSB_MAX_QUADS] scatter cursors (start at the bin offset)
@@ -692,9 +692,9 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				if (!P.flat_field) P.ff[id] = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
 				P.recA[0][2 * (size_t)item] = make_float4(ox, oy, oz, __int_as_float(-1));
 				P.recA[0][2 * (size_t)item + 1] = make_float4(dx, dy, dz, lambda_0);
-				P.recS[0][4 * (size_t)item] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
+				P.recR[0][2 * (size_t)item] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
 				                                          __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32)));
-				P.recS[0][4 * (size_t)item + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
+				P.recR[0][2 * (size_t)item + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
 			} else {
 				const float4 a = P.recA[pin][2 * (size_t)item], b = P.recA[pin][2 * (size_t)item + 1];
 				ox = a.x; oy = a.y; oz = a.z; ignore = __float_as_int(a.w);
@@ -706,11 +706,11 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				hq = (uint32_t)hit.quad | ((uint32_t)hit.tri << 31);
 				// hit position (Ray::at, stdafx.hpp:219): origin of the shadow ray and of the next path ray
 				const float d_ = hit.dist;
-				P.recS[pin][4 * (size_t)item + 2] = make_float4(ox + d_ * dx, oy + d_ * dy, oz + d_ * dz, __uint_as_float(hq));
-				P.recS[pin][4 * (size_t)item + 3] = make_float4(hit.bx, hit.by, hit.bz, 0.f);
+				P.recH[2 * (size_t)item] = make_float4(ox + d_ * dx, oy + d_ * dy, oz + d_ * dz, __uint_as_float(hq));
+				P.recH[2 * (size_t)item + 1] = make_float4(hit.bx, hit.by, hit.bz, 0.f);
 			} else {
 				// miss: L() returns 0 (renderer.cpp:161-163 with no hit); hit_anything only if an earlier depth hit
-				const float4 r1 = P.recS[pin][4 * (size_t)item + 1];
+				const float4 r1 = P.recR[pin][2 * (size_t)item + 1];
 				const uint32_t id = __float_as_uint(r1.x);
 				P.leaf[id] = make_float4(0.f, 0.f, 0.f, 0.f);
 				P.meta[id] = make_float2(r1.y, __int_as_float(depth | (FIRST ? 0 : (1 << 16))));
@@ -831,8 +831,8 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 		// ---- phase 0: gather the path, emission, albedo (renderer.cpp:165-175; material.cpp:120-143)
 		if (valid) {
 			item = P.order[slot];
-			const float4* rs = P.recS[pin] + 4 * (size_t)item;
-			const float4 r0 = rs[0], r1 = rs[1], h0 = rs[2], h1 = rs[3];
+			const float4 h0 = P.recH[2 * (size_t)item], h1 = P.recH[2 * (size_t)item + 1];
+			const float4 r0 = P.recR[pin][2 * (size_t)item], r1 = P.recR[pin][2 * (size_t)item + 1];
 			hx = h0.x; hy = h0.y; hz = h0.z;  // hit position
 			const uint32_t hq = __float_as_uint(h0.w);
 			id = __float_as_uint(r1.x);
@@ -976,9 +976,9 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 				const uint32_t o = base + __popc(mask & ((1u << lane) - 1u));
 				P.recA[pout][2 * (size_t)o] = make_float4(ox, oy, oz, __int_as_float(ignore));
 				P.recA[pout][2 * (size_t)o + 1] = make_float4(dx, dy, dz, lambda_0);
-				P.recS[pout][4 * (size_t)o] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
+				P.recR[pout][2 * (size_t)o] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
 				                                          __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32)));
-				P.recS[pout][4 * (size_t)o + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
+				P.recR[pout][2 * (size_t)o + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
 			}
 		}
 		SSB_PHASE_BARRIER();
