@@ -96,15 +96,17 @@ def data_root():
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def ref_binary(variant=VARIANT):
+def ref_binary(variant=None):
+    variant = variant or VARIANT
     p = os.path.join(ROOT, "oracle", "_ref", f"simple_spectral_{variant}")
     if not os.path.exists(p):
         raise SystemExit(f"{p} missing: run __graft_entry__.build() where /root/reference exists")
     return p
 
 
-def run_reference_once(width, height, spp, threads=None, variant=VARIANT, scene=SCENE):
+def run_reference_once(width, height, spp, threads=None, variant=None, scene=None):
     """Runs the UNMODIFIED reference renderer; returns its own 'Render completed in' time (excludes load)."""
+    variant, scene = variant or VARIANT, scene or SCENE
     env = dict(os.environ)
     out = f"/tmp/ssb_ref_bench_{os.getpid()}.pfm"
     r = subprocess.run([ref_binary(variant), f"--scene={scene}", f"-w={width}", f"-h={height}", f"-spp={spp}", f"--output={out}"],
@@ -146,7 +148,7 @@ def main_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "reference scene (hard-coded geometry + shipped spectra/texture)",
-        "config": {"workload": f"{SCENE} {args.width}x{args.height} hero-wavelength OURS CIE1931; each step = one frame at spp{spp} "
+        "config": {"workload": f"{SCENE} {args.width}x{args.height} hero-wavelength {VARIANT}; each step = one frame at spp{spp} "
                                f"(bounded sample of the spp{args.spp} workload)", "timer": "reference's own 'Render completed in' (excludes scene load)"},
         "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "reference",
                          "sample": f"{args.steps} frames of {SCENE} {args.width}x{args.height} spp{spp}, {cores} threads"},
@@ -311,8 +313,8 @@ def main_ours(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "reference scene (hard-coded cornell-srgb geometry, shipped spectra + 4096^2 sRGB texture); per-sample seeded RNG",
-            "config": {"workload": f"{SCENE} {W}x{H} spp{SPP} per GPU (job spp {total_spp}), hero-wavelength x4, OURS upsampling, CIE1931, "
+            "dtype": "f32", "data": "reference scene (hard-coded geometry, shipped spectra + 4096^2 sRGB texture); per-sample seeded RNG",
+            "config": {"workload": f"{SCENE} {W}x{H} spp{SPP} per GPU (job spp {total_spp}), hero-wavelength x4, variant {VARIANT} (upsampling + observer), "
                                    f"ELS on, MAX_DEPTH 10", "parallelism": f"sample-sharded x{world}, one NCCL reduce of f64 XYZA" if world > 1 else "single GPU",
                        "l2": "no flush needed: every step streams ~8 GB of path records / fold records through HBM (>> 126 MB L2)",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
@@ -343,6 +345,7 @@ def main_ours(args, rank, local_rank, world):
 
 
 def main():
+    global SCENE, VARIANT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -354,7 +357,11 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--ref-spp", type=int, default=4, help="spp per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scene", default=SCENE, choices=sorted(ALGO_BYTES_PER_SAMPLE),
+                    help="default = BASELINE configs[1]; the others are SURVEY 8(d) C3-C5 (not the headline)")
+    ap.add_argument("--variant", default=VARIANT, choices=["ours1931", "ours2006", "meng", "jh"])
     args = ap.parse_args()
+    SCENE, VARIANT = args.scene, args.variant
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
