@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1u
+#define SSB_ABI_VERSION 2u /* 2: RGB render mode (ssb_material.*_rgb, ssb_options.render_mode) */
 
 #define SSB_OK 0
 #define SSB_ERR_DATA (-1)
@@ -83,6 +83,10 @@ typedef struct ssb_material {
 	ssb_spectrum albedo;   /* used when albedo_mode == CONSTANT */
 	uint32_t texture;      /* index into ssb_scene.textures when albedo_mode == TEXTURE */
 	ssb_spectrum emission; /* MaterialBase::emission (default: constant 0) */
+	/* RENDER_MODE_RGB only (the `#else` branches of material.hpp:51-55,120-126): l-RGB triples used instead of
+	 * the two spectra when ssb_options.render_mode == SSB_RENDER_RGB; ignored in spectral mode */
+	float albedo_rgb[3];   /* RGB_Reflectance, default (1,1,1) */
+	float emission_rgb[3]; /* RGB_Radiance, default (0,0,0) */
 } ssb_material;
 
 /* sRGB_ReflectanceTexture (material.hpp:14-44): RGB8, scanlines top-to-bottom */
@@ -133,6 +137,12 @@ typedef struct ssb_color {
 	const ssb_meng_tables* meng;            /* MENG only */
 } ssb_color;
 
+/* RENDER_MODE_SPECTRAL vs RENDER_MODE_RGB (stdafx.hpp:62-90) */
+#define SSB_RENDER_SPECTRAL 0u /* hero-wavelength spectral transport, CIE XYZ accumulator (the default) */
+#define SSB_RENDER_RGB 1u      /* three-channel l-RGB transport: no wavelength sample, no upsampling, no colour tables;
+                                * the accumulator holds sum(l-RGB, hit) and resolve is avg/spp -> lrgb_to_srgb
+                                * (renderer.cpp:300-307) */
+
 /* ---- render options: Renderer::Options (renderer.hpp:16-29) + the compile-time macros of
  * stdafx.hpp:44-90 exposed as runtime fields ---- */
 typedef struct ssb_options {
@@ -150,6 +160,8 @@ typedef struct ssb_options {
 	uint32_t flat_field_correction;   /* FLAT_FIELD_CORRECTION, 1 */
 	float eps;                        /* EPS, 1e-3f */
 	uint64_t seed;                    /* per-sample seeding: PCG32.seed(mix(seed, sample index)) */
+	uint32_t render_mode;             /* SSB_RENDER_* */
+	uint32_t reserved;                /* must be 0 */
 } ssb_options;
 
 typedef struct ssb_stats {
@@ -175,7 +187,8 @@ int ssb_upload_scene(ssb_ctx* ctx, const ssb_scene* scene);
 int ssb_upload_color(ssb_ctx* ctx, const ssb_color* color);
 
 /* Trace the requested samples and ADD each sample's float4 (X,Y,Z,hit)*0.001f, in sample order,
- * to the context's per-pixel double XYZA accumulator (renderer.cpp:292-295).  The accumulator is
+ * to the context's per-pixel double XYZA accumulator (renderer.cpp:292-295; RGB mode: the float4
+ * (r,g,b,hit) unscaled, renderer.cpp:301-303).  The accumulator is
  * cleared when sample_begin == 0 or by ssb_clear().  Device-resident; no host transfer. */
 int ssb_render(ssb_ctx* ctx, const ssb_options* opt);
 int ssb_clear(ssb_ctx* ctx);
@@ -190,6 +203,7 @@ int ssb_accum_device(ssb_ctx* ctx, double** dptr, size_t* count);
 
 /* Finish a frame: avg = accum * (1000/spp) (renderer.cpp:296), then
  * sRGBA = (ciexyz_to_srgb(float3(avg)), float(avg.a)) (renderer.cpp:298, color.cpp:237-257).
+ * RGB mode: avg = accum / spp, sRGBA = (lrgb_to_srgb(float3(avg)), float(avg.a)) (renderer.cpp:304-306).
  * Either output may be NULL.  HOST pointers, width*height*4 elements, row 0 = bottom. */
 int ssb_resolve(ssb_ctx* ctx, const ssb_options* opt, double* xyza_host, float* srgba_host);
 

@@ -10,7 +10,7 @@ unpinned dependency (cmake/FindGLM.cmake) and is not installed.  We compile agai
 oracle/glm_shim (our restatement of GLM 0.9.9 scalar semantics for the ~20 functions
 the reference uses).  The reference's CMake build is NOT run.
 
-Outputs (per variant v in ours1931, ours2006, meng, jh):
+Outputs (per variant v in ours1931, ours2006, meng, jh, ours1931_noels, rgb):
   oracle/_ref/simple_spectral_<v>          pristine sources, -O3 -march=x86-64-v3 -DNDEBUG
                                             (CPU timing arm; multi-threaded, nondeterministic)
   oracle/_ref/simple_spectral_<v>_hooked   sources + oracle/ref_hooks.hpp spliced into
@@ -42,6 +42,8 @@ VARIANTS = {
     # on every hit (renderer.cpp:167-175).  (FLAT_FIELD_CORRECTION cannot be compiled out in this mode: the reference's
     # own color.cpp:275-279 then refers to an undeclared `flux`.)
     "ours1931_noels": dict(alg=1, observer=1931, no_els=True),
+    # RENDER_MODE_RGB (stdafx.hpp:62-90 `#if 1` -> `#if 0`): the three-channel comparison renderer
+    "rgb": dict(alg=1, observer=1931, rgb=True),
 }
 CXX_SOURCES = [
     "main.cpp", "renderer.cpp", "scene.cpp", "geometry.cpp", "material.cpp", "spectrum.cpp",
@@ -69,13 +71,15 @@ def sub_once(text, pattern, repl, what):
     return new
 
 
-def patch_variant(src_dir, alg, observer, no_els=False, no_ffc=False):
+def patch_variant(src_dir, alg, observer, no_els=False, no_ffc=False, rgb=False):
     p = os.path.join(src_dir, "stdafx.hpp")
     t = open(p, encoding="utf-8-sig").read()
     if no_els:
         t = sub_once(t, r"^#define EXPLICIT_LIGHT_SAMPLING$", "//#define EXPLICIT_LIGHT_SAMPLING", "ELS")
     if no_ffc:
         t = sub_once(t, r"^#define FLAT_FIELD_CORRECTION$", "//#define FLAT_FIELD_CORRECTION", "FFC")
+    if rgb:
+        t = sub_once(t, r"#if 1(\s+#define RENDER_MODE_SPECTRAL\n)", r"#if 0\1", "RENDER_MODE")
     t = sub_once(t, r"#define RENDER_MODE_SPECTRAL_ALGNUM 1", f"#define RENDER_MODE_SPECTRAL_ALGNUM {alg}", "ALGNUM")
     if observer == 2006:
         t = sub_once(t, r"#if 1(\s+#define CIE_OBSERVER 1931)", r"#if 0\1", "CIE_OBSERVER")
@@ -100,6 +104,12 @@ def patch_hooks(src_dir):
     t = sub_once(t, r"avg \+= _render_sample\(rng, i,j\) \* 0\.001f;",
                  "{ ssb_hooks::seed_sample(rng,i,j,k); auto ssb_s = _render_sample(rng, i,j); "
                  "ssb_hooks::record_sample(i,j,k,ssb_s); avg += ssb_s * 0.001f; }", "sample")
+    # ... and the RGB branch (renderer.cpp:301-303)
+    t = sub_once(t, r"avg \+= _render_sample\(rng, i,j\);",
+                 "{ ssb_hooks::seed_sample(rng,i,j,k); auto ssb_s = _render_sample(rng, i,j); "
+                 "ssb_hooks::record_sample(i,j,k,ssb_s); avg += ssb_s; }", "sample (rgb)")
+    t = sub_once(t, r"(avg /= static_cast<double>\(options\.spp\);\n)",
+                 r"\1\t\tssb_hooks::record_pixel(i,j,avg);\n", "pixel (rgb)")
     # pixel dump (after renderer.cpp:296)
     t = sub_once(t, r"(avg \*= 1000\.0 / static_cast<double>\(options\.spp\);\n)",
                  r"\1\t\tssb_hooks::record_pixel(i,j,avg);\n", "pixel")
@@ -155,7 +165,7 @@ def main():
             for name in which:
                 v = VARIANTS[name]
                 for hooked in (False, True):
-                    kw = {k: v[k] for k in ("no_els", "no_ffc") if k in v}
+                    kw = {k: v[k] for k in ("no_els", "no_ffc", "rgb") if k in v}
                     jobs.append(ex.submit(build_one, tmp, name, v["alg"], v["observer"], hooked, lodepng_obj, **kw))
             for j in jobs:
                 print("built", os.path.relpath(j.result(), os.path.dirname(HERE)))

@@ -104,12 +104,6 @@ inline void rec_f32(FILE* f, std::string const& n, const float* p, size_t c) { r
 inline void rec_f64(FILE* f, std::string const& n, const double* p, size_t c) { rec(f, n, "f64", c, p, 8); }
 inline void rec_u32(FILE* f, std::string const& n, const uint32_t* p, size_t c) { rec(f, n, "u32", c, p, 4); }
 
-#ifdef RENDER_MODE_SPECTRAL
-inline void rec_spectrum(FILE* f, std::string const& name, _Spectrum const& s) {
-	rec_f32(f, name + ".data", s._data.data(), s._data.size());
-	float lh[2] = { s._low, s._high };
-	rec_f32(f, name + ".lowhigh", lh, 2);
-}
 template <class M3> inline void rec_mat3(FILE* f, std::string const& name, M3 const& m) {
 	float v[9]; for (size_t c = 0; c < 3; ++c) for (size_t r = 0; r < 3; ++r) v[c * 3 + r] = m[c][r];
 	rec_f32(f, name, v, 9);
@@ -118,12 +112,20 @@ template <class M4> inline void rec_dmat4(FILE* f, std::string const& name, M4 c
 	double v[16]; for (size_t c = 0; c < 4; ++c) for (size_t r = 0; r < 4; ++r) v[c * 4 + r] = m[c][r];
 	rec_f64(f, name, v, 16);
 }
+#ifdef RENDER_MODE_SPECTRAL
+inline void rec_spectrum(FILE* f, std::string const& name, _Spectrum const& s) {
+	rec_f32(f, name + ".data", s._data.data(), s._data.size());
+	float lh[2] = { s._low, s._high };
+	rec_f32(f, name + ".lowhigh", lh, 2);
+}
+#endif
 
 inline void dump_tables(Scene* scene) {
 	State& s = st();
 	if (!s.dump_tables) return;
 	FILE* f = std::fopen(s.dump_tables, "wb");
 	if (!f) return;
+#ifdef RENDER_MODE_SPECTRAL
 	// colour data (util/color.hpp:22-69)
 	rec_spectrum(f, "color.xbar", Color::data->std_obs_xbar);
 	rec_spectrum(f, "color.ybar", Color::data->std_obs_ybar);
@@ -141,6 +143,7 @@ inline void dump_tables(Scene* scene) {
 	rec_mat3(f, "color.matr_xyz_to_lrgb", Color::data->matr_xyz_to_lrgb);
 	float lam[3] = { LAMBDA_MIN, LAMBDA_MAX, LAMBDA_STEP };
 	rec_f32(f, "config.lambda_min_max_step", lam, 3);
+#endif
 	// camera (scene.hpp:16-33)
 	rec_f32(f, "camera.pos", &scene->camera.pos[0], 3);
 	rec_f32(f, "camera.dir", &scene->camera.dir[0], 3);
@@ -181,8 +184,13 @@ inline void dump_tables(Scene* scene) {
 		MaterialSimpleAlbedoBase const* mat = static_cast<MaterialSimpleAlbedoBase const*>(mats[m]);
 		uint32_t kind[2] = { dynamic_cast<MaterialLambertian const*>(mats[m]) ? 0u : 1u, mat->mode == MaterialSimpleAlbedoBase::CONSTANT ? 0u : 1u };
 		rec_u32(f, base + ".kind_mode", kind, 2);
+#ifdef RENDER_MODE_SPECTRAL
 		rec_spectrum(f, base + ".emission", mat->emission);
 		if (mat->mode == MaterialSimpleAlbedoBase::CONSTANT) rec_spectrum(f, base + ".albedo", *mat->albedo.constant);
+#else
+		rec_f32(f, base + ".emission_rgb", &mat->emission[0], 3);
+		if (mat->mode == MaterialSimpleAlbedoBase::CONSTANT) rec_f32(f, base + ".albedo_rgb", &mat->albedo.constant[0], 3);
+#endif
 		else {
 			uint32_t res[2] = { static_cast<uint32_t>(mat->albedo.texture->res[0]), static_cast<uint32_t>(mat->albedo.texture->res[1]) };
 			rec_u32(f, base + ".texture_res", res, 2);
@@ -190,6 +198,5 @@ inline void dump_tables(Scene* scene) {
 	}
 	std::fclose(f);
 }
-#endif
 
 }  // namespace ssb_hooks

@@ -283,11 +283,21 @@ static hero texture_sample(const octx* c, const ssb_texture* tex, v2 st, float l
 	float srgb[3] = { (float)px[0] * (1.0f / 255.0f), (float)px[1] * (1.0f / 255.0f), (float)px[2] * (1.0f / 255.0f) };
 	float lrgb[3] = { srgb_to_lrgb_1(srgb[0]), srgb_to_lrgb_1(srgb[1]), srgb_to_lrgb_1(srgb[2]) };
 	if (c->counters) c->counters->texture_lookups++;
+	if (c->opt->render_mode == SSB_RENDER_RGB) { hero h = { { lrgb[0], lrgb[1], lrgb[2], 0.0f } }; return h; } /* material.cpp:64-66 */
 	return lrgb_to_specrefl(c, lrgb, lambda_0);
 }
 static hero material_albedo(const octx* c, const ssb_material* m, v2 st, float lambda_0) {
+	if (c->opt->render_mode == SSB_RENDER_RGB) { /* the `#else` branches of material.cpp:120-167: RGB triple or texel l-RGB */
+		if (m->albedo_mode == SSB_ALBEDO_CONSTANT) { hero h = { { m->albedo_rgb[0], m->albedo_rgb[1], m->albedo_rgb[2], 0.0f } }; return h; }
+		return texture_sample(c, &c->scene->textures[m->texture], st, lambda_0);
+	}
 	if (m->albedo_mode == SSB_ALBEDO_CONSTANT) return spectrum_hero(c, &m->albedo, lambda_0);
 	return texture_sample(c, &c->scene->textures[m->texture], st, lambda_0);
+}
+/* MaterialBase::evaluate_emission, material.hpp:96-104 */
+static hero material_emission(const octx* c, const ssb_material* m, float lambda_0) {
+	if (c->opt->render_mode == SSB_RENDER_RGB) { hero h = { { m->emission_rgb[0], m->emission_rgb[1], m->emission_rgb[2], 0.0f } }; return h; }
+	return spectrum_hero(c, &m->emission, lambda_0);
 }
 
 /* Color::specradflux_to_ciexyz(HeroSample, lambda_0), color.hpp:115-139 */
@@ -544,7 +554,7 @@ static hero L(path_t* p, const ray_t* ray, int last_was_delta, unsigned depth, i
 		const ssb_material* mat = &c->scene->materials[quad->material];
 		int els = opt->explicit_light_sampling != 0;
 		if (!els || (last_was_delta && (!opt->indirect_only || depth > 0u))) { /* renderer.cpp:167-175 */
-			radiance = hero_add(radiance, spectrum_hero(c, &mat->emission, p->lambda_0));
+			radiance = hero_add(radiance, material_emission(c, mat, p->lambda_0));
 		}
 		if (depth + 1u < opt->max_depth) {
 			v3 hit_pos = v3_add(ray->orig, v3_scale(ray->dir, hitrec.dist)); /* Ray::at, stdafx.hpp:219 */
@@ -559,7 +569,7 @@ static hero L(path_t* p, const ray_t* ray, int last_was_delta, unsigned depth, i
 					scene_intersect(c, &ray_shad, &hs, hitrec.quad);
 					if (hs.quad == light) {
 						const ssb_material* lm = &c->scene->materials[c->scene->quads[light].material];
-						hero emitted = spectrum_hero(c, &lm->emission, p->lambda_0);
+						hero emitted = material_emission(c, lm, p->lambda_0);
 						hero f_s; /* evaluate_bsdf, material.cpp:120-129 / 146-153 */
 						if (mat->kind == SSB_MATERIAL_LAMBERT) f_s = hero_div(material_albedo(c, mat, hitrec.st, p->lambda_0), PI_F);
 						else f_s = hero_splat(0.0f);
@@ -618,23 +628,28 @@ static void render_sample(const octx* c, rng_t* rng, uint32_t i, uint32_t j, flo
 	ray_camera.orig = v3_make(cam->pos[0], cam->pos[1], cam->pos[2]);
 	ray_camera.dir = v3_make((float)(dx * inv), (float)(dy * inv), (float)(dz * inv));
 
-	float lambda_0 = opt->lambda_min + rand_1f(rng) * c->lambda_step; /* renderer.cpp:138 */
+	/* renderer.cpp:134-143: the hero wavelength is drawn in spectral mode only */
+	const int rgb = opt->render_mode == SSB_RENDER_RGB;
+	float lambda_0 = rgb ? 0.0f : opt->lambda_min + rand_1f(rng) * c->lambda_step;
 
 	path_t p = { c, rng, lambda_0, 0 };
 	hero pixel_rad_est = L(&p, &ray_camera, 1, 0u, -1);
 	hero pixel_flux_est = pixel_rad_est;
 	if (!opt->flat_field_correction) /* renderer.cpp:262-266 */
 		pixel_flux_est = hero_scale(pixel_rad_est, v3_dot(ray_camera.dir, v3_make(cam->dir[0], cam->dir[1], cam->dir[2])));
-	specradflux_to_ciexyz(c, pixel_flux_est, lambda_0, out);
+	if (rgb) { out[0] = pixel_flux_est.v[0]; out[1] = pixel_flux_est.v[1]; out[2] = pixel_flux_est.v[2]; } /* renderer.cpp:274-275 */
+	else specradflux_to_ciexyz(c, pixel_flux_est, lambda_0, out);
 	out[3] = p.hit_anything ? 1.0f : 0.0f;
 	if (c->counters) c->counters->samples++;
 }
 
 static int prepare(octx* c, const ssb_scene* scene, const ssb_color* color, const ssb_options* opt) {
 	memset(c, 0, sizeof(*c));
-	if (!scene || !color || !opt) return SSB_ERR_ARG;
+	if (!scene || !opt) return SSB_ERR_ARG;
+	if (opt->render_mode > SSB_RENDER_RGB) return SSB_ERR_UNSUPPORTED;
+	if (!color && opt->render_mode != SSB_RENDER_RGB) return SSB_ERR_ARG; /* RGB mode needs no colour tables */
 	if (opt->width == 0 || opt->height == 0 || opt->spp == 0) return SSB_ERR_ARG;
-	if (opt->upsampling < SSB_UPSAMPLE_OURS || opt->upsampling > SSB_UPSAMPLE_JH) return SSB_ERR_UNSUPPORTED;
+	if (opt->render_mode != SSB_RENDER_RGB && (opt->upsampling < SSB_UPSAMPLE_OURS || opt->upsampling > SSB_UPSAMPLE_JH)) return SSB_ERR_UNSUPPORTED;
 	c->scene = scene; c->color = color; c->opt = opt;
 	c->lambda_step = (opt->lambda_max - opt->lambda_min) / (float)4; /* stdafx.hpp:289 */
 	for (uint32_t q = 0; q < scene->nquads; ++q)
@@ -673,7 +688,10 @@ int ssb_oracle_render(const ssb_scene* scene, const ssb_color* color, const ssb_
 					float s[4];
 					render_sample(&c, &rng, i, j, s);
 					if (samples_out) memcpy(samples_out + 4 * (pixel * ns + (k - opt->sample_begin)), s, sizeof(s));
-					if (avg) for (int ch = 0; ch < 4; ++ch) avg[ch] += (double)(s[ch] * 0.001f);
+					if (avg) {
+						if (opt->render_mode == SSB_RENDER_RGB) for (int ch = 0; ch < 4; ++ch) avg[ch] += (double)s[ch]; /* renderer.cpp:301-303 */
+						else for (int ch = 0; ch < 4; ++ch) avg[ch] += (double)(s[ch] * 0.001f);
+					}
 				}
 			}
 		}
@@ -691,14 +709,20 @@ int ssb_oracle_render(const ssb_scene* scene, const ssb_color* color, const ssb_
 
 /* renderer.cpp:296-298 + Color::ciexyz_to_srgb, color.cpp:237-257 */
 int ssb_oracle_resolve(const ssb_color* color, const ssb_options* opt, const double* accum, double* xyza, float* srgba) {
-	if (!color || !opt || !accum) return SSB_ERR_ARG;
+	if (!opt || !accum) return SSB_ERR_ARG;
+	const int rgb = opt->render_mode == SSB_RENDER_RGB;
+	if (!color && !rgb) return SSB_ERR_ARG;
 	size_t npix = (size_t)opt->width * opt->height;
 	double scale = 1000.0 / (double)opt->spp;
 	for (size_t p = 0; p < npix; ++p) {
 		double avg[4];
-		for (int ch = 0; ch < 4; ++ch) avg[ch] = accum[4 * p + ch] * scale;
+		if (rgb) for (int ch = 0; ch < 4; ++ch) avg[ch] = accum[4 * p + ch] / (double)opt->spp; /* renderer.cpp:304 */
+		else for (int ch = 0; ch < 4; ++ch) avg[ch] = accum[4 * p + ch] * scale;
 		if (xyza) memcpy(xyza + 4 * p, avg, sizeof(avg));
-		if (srgba) {
+		if (srgba && rgb) { /* Color::lrgb_to_srgb(lRGB_F32(avg)), renderer.cpp:306 */
+			for (int ch = 0; ch < 3; ++ch) srgba[4 * p + ch] = lrgb_to_srgb_1((float)avg[ch]);
+			srgba[4 * p + 3] = (float)avg[3];
+		} else if (srgba) {
 			float xyz[3] = { (float)avg[0], (float)avg[1], (float)avg[2] };
 			float lrgb[3];
 			if (opt->upsampling == SSB_UPSAMPLE_MENG) { /* color.cpp:243-254 */

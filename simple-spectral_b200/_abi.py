@@ -6,6 +6,7 @@ SSB_FILTER_LINEAR, SSB_FILTER_NEAREST = 0, 1
 SSB_MATERIAL_LAMBERT, SSB_MATERIAL_MIRROR = 0, 1
 SSB_ALBEDO_CONSTANT, SSB_ALBEDO_TEXTURE = 0, 1
 SSB_UPSAMPLE_OURS, SSB_UPSAMPLE_MENG, SSB_UPSAMPLE_JH = 1, 2, 3
+SSB_RENDER_SPECTRAL, SSB_RENDER_RGB = 0, 1
 
 
 class ssb_vertex(C.Structure):
@@ -27,7 +28,8 @@ class ssb_spectrum(C.Structure):
 
 class ssb_material(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("albedo_mode", C.c_uint32), ("albedo", ssb_spectrum),
-                ("texture", C.c_uint32), ("emission", ssb_spectrum)]
+                ("texture", C.c_uint32), ("emission", ssb_spectrum),
+                ("albedo_rgb", C.c_float * 3), ("emission_rgb", C.c_float * 3)]
 
 
 class ssb_texture(C.Structure):
@@ -65,7 +67,8 @@ class ssb_options(C.Structure):
                 ("indirect_only", C.c_uint32), ("upsampling", C.c_uint32),
                 ("lambda_min", C.c_float), ("lambda_max", C.c_float),
                 ("max_depth", C.c_uint32), ("explicit_light_sampling", C.c_uint32),
-                ("flat_field_correction", C.c_uint32), ("eps", C.c_float), ("seed", C.c_uint64)]
+                ("flat_field_correction", C.c_uint32), ("eps", C.c_float), ("seed", C.c_uint64),
+                ("render_mode", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class ssb_stats(C.Structure):

@@ -29,6 +29,8 @@ CASES = [  # (scene, variant)
     ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
     # EXPLICIT_LIGHT_SAMPLING compiled out: MaterialMirror on the plane (scene.cpp:346-355), emission on every hit
     ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels"),
+    # RENDER_MODE_RGB: the three-channel comparison renderer (the stored "xyza" is the l-RGB+alpha average)
+    ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb"),
 ]
 SMALL = dict(w=32, h=24, spp=4, seed=7)
 C1 = dict(w=128, h=128, spp=16, seed=1)  # BASELINE.json configs[0]
@@ -49,15 +51,23 @@ def run_ref(scene, variant, w, h, spp, seed, tables=None, indirect_only=False):
 
 def main():
     index = {}
+    only = sys.argv[1:]  # optional: regenerate only these variants (the others are left untouched)
+    if only and os.path.exists(os.path.join(HERE, "golden_index.json")):
+        index = json.load(open(os.path.join(HERE, "golden_index.json")))
     for scene, variant in CASES:
+        if only and variant not in only:
+            continue
         tables = os.path.join(HERE, f"tables_{scene}_{variant}.bin")
         x = run_ref(scene, variant, tables=tables, **SMALL)
         name = f"xyza_{scene}_{variant}_{SMALL['w']}x{SMALL['h']}_spp{SMALL['spp']}_seed{SMALL['seed']}.npy"
         np.save(os.path.join(HERE, name), x)
         print("wrote", name, "mean", x.mean(axis=(0, 1)))
-    x = run_ref("cornell-srgb", "ours1931", indirect_only=True, **SMALL)
-    np.save(os.path.join(HERE, f"xyza_cornell-srgb_ours1931_indirect_{SMALL['w']}x{SMALL['h']}_spp{SMALL['spp']}_seed{SMALL['seed']}.npy"), x)
-    for scene, variant in (("cornell-srgb", "ours1931"), ("cornell", "ours1931")):
+    if not only or "ours1931" in only:
+        x = run_ref("cornell-srgb", "ours1931", indirect_only=True, **SMALL)
+        np.save(os.path.join(HERE, f"xyza_cornell-srgb_ours1931_indirect_{SMALL['w']}x{SMALL['h']}_spp{SMALL['spp']}_seed{SMALL['seed']}.npy"), x)
+    for scene, variant in (("cornell-srgb", "ours1931"), ("cornell", "ours1931"), ("cornell-srgb", "rgb")):
+        if only and variant not in only:
+            continue
         x = run_ref(scene, variant, **C1)
         key = f"{scene}_{variant}_{C1['w']}x{C1['h']}_spp{C1['spp']}_seed{C1['seed']}"
         index[key] = dict(sha256=hashlib.sha256(x.tobytes()).hexdigest(), mean=list(x.mean(axis=(0, 1))),

@@ -20,6 +20,7 @@ VARIANT_OPTS = {  # compile-time variants of the reference (stdafx.hpp:66,81) as
     "jh": dict(upsampling=abi.SSB_UPSAMPLE_JH, lambda_min=380.0, lambda_max=780.0),
     "meng": dict(upsampling=abi.SSB_UPSAMPLE_MENG, lambda_min=380.0, lambda_max=780.0),
     "ours1931_noels": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, explicit_light_sampling=0),
+    "rgb": dict(render_mode=abi.SSB_RENDER_RGB),  # RENDER_MODE_RGB (stdafx.hpp:62-90)
 }
 
 
@@ -152,7 +153,8 @@ def oracle_resolve(flat, opt, acc):
 def gpu_context(flat, device=0):
     ctx = ssb.Context(device)
     ctx.upload_scene(flat.scene)
-    ctx.upload_color(flat.color)
+    if not getattr(flat, "rgb", False):  # RGB mode needs no colour tables
+        ctx.upload_color(flat.color)
     return ctx
 
 

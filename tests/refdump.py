@@ -64,14 +64,16 @@ def flat_from_dump(t, texture_rgb8=None, jh=None, meng=None):
     """t: parse() result.  texture_rgb8: HxWx3 uint8 (required if a material is textured)."""
     f = Flat()
     col = f.color
-    for name in ("xbar", "ybar", "zbar"):
-        setattr(col, name, f.spectrum(t[f"color.{name}.data"], *t[f"color.{name}.lowhigh"]))
-    if "color.basis_r.data" in t:
-        for name in ("basis_r", "basis_g", "basis_b"):
+    f.rgb = "color.xbar.data" not in t  # dump of the RENDER_MODE_RGB build: no colour tables, RGB material constants
+    if not f.rgb:
+        for name in ("xbar", "ybar", "zbar"):
             setattr(col, name, f.spectrum(t[f"color.{name}.data"], *t[f"color.{name}.lowhigh"]))
-    for i in range(9):
-        col.xyz_to_lrgb[i] = float(t["color.matr_xyz_to_lrgb"][i])
-    col.d65_rad_Y = float(t["color.D65_rad_XYZ"][1])
+        if "color.basis_r.data" in t:
+            for name in ("basis_r", "basis_g", "basis_b"):
+                setattr(col, name, f.spectrum(t[f"color.{name}.data"], *t[f"color.{name}.lowhigh"]))
+        for i in range(9):
+            col.xyz_to_lrgb[i] = float(t["color.matr_xyz_to_lrgb"][i])
+        col.d65_rad_Y = float(t["color.D65_rad_XYZ"][1])
     if jh is not None:
         scale, data, res = jh
         f.keep += [scale, data]
@@ -79,8 +81,9 @@ def flat_from_dump(t, texture_rgb8=None, jh=None, meng=None):
     if meng is not None:
         f.keep.append(meng)
         col.meng = C.pointer(meng)
-    f.lambda_min = float(t["config.lambda_min_max_step"][0])
-    f.lambda_max = float(t["config.lambda_min_max_step"][1])
+    if not f.rgb:
+        f.lambda_min = float(t["config.lambda_min_max_step"][0])
+        f.lambda_max = float(t["config.lambda_min_max_step"][1])
 
     sc = f.scene
     for i in range(16):
@@ -110,10 +113,16 @@ def flat_from_dump(t, texture_rgb8=None, jh=None, meng=None):
     for m in range(nm):
         kind, mode = t[f"material.{m}.kind_mode"]
         mats[m].kind, mats[m].albedo_mode = int(kind), int(mode)
-        mats[m].emission = f.spectrum(t[f"material.{m}.emission.data"], *t[f"material.{m}.emission.lowhigh"])
-        if mode == 0:
-            mats[m].albedo = f.spectrum(t[f"material.{m}.albedo.data"], *t[f"material.{m}.albedo.lowhigh"])
+        if f.rgb:
+            for k in range(3):
+                mats[m].emission_rgb[k] = float(t[f"material.{m}.emission_rgb"][k])
+                if mode == 0:
+                    mats[m].albedo_rgb[k] = float(t[f"material.{m}.albedo_rgb"][k])
         else:
+            mats[m].emission = f.spectrum(t[f"material.{m}.emission.data"], *t[f"material.{m}.emission.lowhigh"])
+            if mode == 0:
+                mats[m].albedo = f.spectrum(t[f"material.{m}.albedo.data"], *t[f"material.{m}.albedo.lowhigh"])
+        if mode != 0:
             assert texture_rgb8 is not None, "scene has a textured material: pass texture_rgb8"
             w, h = t[f"material.{m}.texture_res"]
             assert texture_rgb8.shape == (h, w, 3)

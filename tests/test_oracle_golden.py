@@ -12,7 +12,8 @@ import parity_util as pu
 SMALL = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("plane-srgb", "ours1931"),
          ("cornell", "ours2006"), ("cornell-srgb", "ours2006"),
          ("cornell-srgb", "jh"), ("plane-srgb", "jh"), ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
-         ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels")]
+         ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels"),
+         ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb")]  # RENDER_MODE_RGB
 
 
 @pytest.mark.parametrize("scene,variant", SMALL)
@@ -52,6 +53,18 @@ def test_oracle_config1_sha(scene):
     # path statistics of SURVEY.md §6 (5.30 closest-hit and 3.14 shadow queries per sample)
     assert abs(cnt.closest_queries / cnt.samples - 5.30) < 0.05
     assert abs(cnt.shadow_queries / cnt.samples - 3.14) < 0.05
+
+
+def test_oracle_rgb_config1_sha():
+    """RENDER_MODE_RGB at BASELINE configs[0]'s size: sha256 of the reference's l-RGB+alpha buffer."""
+    if not pu.have_assets():
+        pytest.skip("texture not staged")
+    idx = json.load(open(os.path.join(pu.GOLDEN, "golden_index.json")))["cornell-srgb_rgb_128x128_spp16_seed1"]
+    flat = pu.load_flat("cornell-srgb", "rgb")
+    opt = pu.options("rgb", 128, 128, 16, seed=1)
+    acc, _, _ = pu.oracle_render(flat, opt)
+    avg, _ = pu.oracle_resolve(flat, opt, acc)
+    assert hashlib.sha256(avg.tobytes()).hexdigest() == idx["sha256"]
 
 
 def test_sample_subsets_compose():
