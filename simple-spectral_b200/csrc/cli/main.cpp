@@ -2,7 +2,7 @@
 //   --scene=<name>/-s  --width=<w>/-w  --height=<h>/-h  --samples=<n>/-spp  --output=<path>/-o  [--indirect-only/-io]
 // so that `simple_spectral_b200 --scene=cornell-srgb -w=512 -h=512 -spp=64 --output=out.png` is a drop-in for the
 // reference binary, rendering on the GPU through the Renderer façade.  The reference's compile-time variants are
-// extra, optional flags here: --variant=ours1931|ours2006|meng|jh  --seed=<n>  --device=<n>  --data-root=<dir>
+// extra, optional flags here: --variant=ours1931|ours2006|meng|jh|rgb  --seed=<n>  --device=<n>  --data-root=<dir>
 // (default data root: the current directory, like the reference's cwd-relative "data/..." paths).
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +23,7 @@ void print_usage() {
 		"    --output=<path>/-o=<path>           .png / .pfm / .hdr / .csv by extension\n"
 		"  Optional arguments:\n"
 		"    --indirect-only/-io\n"
-		"    --variant=ours1931|ours2006|meng|jh   (the reference's compile-time modes)\n"
+		"    --variant=ours1931|ours2006|meng|jh|rgb   (the reference's compile-time modes)\n"
 		"    --seed=<n>  --device=<n>  --data-root=<dir containing data/>\n");
 }
 
@@ -84,6 +84,7 @@ int main(int argc, char* argv[]) {
 			else if (v == "ours2006") { o.observer = 2006; o.upsampling = SSB_UPSAMPLE_OURS; }
 			else if (v == "meng") { o.observer = 1931; o.upsampling = SSB_UPSAMPLE_MENG; }
 			else if (v == "jh") { o.observer = 1931; o.upsampling = SSB_UPSAMPLE_JH; }
+			else if (v == "rgb") { o.render_mode = SSB_RENDER_RGB; }  // the reference's RENDER_MODE_RGB build
 			else { std::fprintf(stderr, "Unknown variant \"%s\"\n", v.c_str()); throw -3; }
 		} catch (int code) { if (code != -2) throw; }
 		try { o.seed = std::strtoull(a.get("--seed", "--seed").c_str(), nullptr, 10); } catch (int code) { if (code != -2) throw; }

@@ -110,12 +110,15 @@ CornellIds build_cornell(Builder& b, std::string const& data_root) {
 	id.blocks = b.add_material("white-blocks", white);
 	id.floorceil = b.add_material("white-floorceil", white);
 	Material green; green.albedo = Spectrum(wgr[1], 400, 700);
+	green.albedo_rgb[0] = 0.07f; green.albedo_rgb[1] = 0.38f; green.albedo_rgb[2] = 0.07f;  // scene.cpp:73 ("set heuristically")
 	id.green = b.add_material("green", green);
 	Material red; red.albedo = Spectrum(wgr[2], 400, 700);
+	red.albedo_rgb[0] = 1; red.albedo_rgb[1] = 0; red.albedo_rgb[2] = 0;  // scene.cpp:76
 	id.red = b.add_material("red", red);
 	Material light;
 	light.emission = Spectrum(lcsv[0], 400, 700) * 200.0f;
 	light.albedo = b.constant(0.78f);
+	for (int k = 0; k < 3; ++k) { light.emission_rgb[k] = 1.0f * 200.0f; light.albedo_rgb[k] = 0.78f; }  // scene.cpp:97-98
 	id.light = b.add_material("light", light);
 
 	const float Y = 548.8f;
@@ -164,6 +167,7 @@ void Scene::flatten() {
 		if (materials[m].albedo_mode == SSB_ALBEDO_CONSTANT) f.albedo = materials[m].albedo.flat();
 		f.texture = materials[m].texture < 0 ? 0u : static_cast<uint32_t>(materials[m].texture);
 		f.emission = materials[m].emission.flat();
+		for (int k = 0; k < 3; ++k) { f.albedo_rgb[k] = materials[m].albedo_rgb[k]; f.emission_rgb[k] = materials[m].emission_rgb[k]; }
 	}
 	flat_textures.resize(textures.size());
 	for (size_t t = 0; t < textures.size(); ++t) flat_textures[t] = ssb_texture{ textures[t].rgb8.data(), textures[t].width, textures[t].height };
@@ -196,6 +200,7 @@ Scene scene_new(std::string const& name, std::string const& data_root, ColorData
 			else if (m == id.red) q.material = static_cast<uint32_t>(mtl_tex);
 		}
 		b.pending(id.light).emission = color.D65_rad * 30.0f;
+		for (int k = 0; k < 3; ++k) b.pending(id.light).emission_rgb[k] = 1.0f * 30.0f;  // scene.cpp:313-316
 	} else if (name == "plane-srgb") {  // Scene::get_new_plane_srgb, scene.cpp:320-415
 		Camera& cam = b.scene.camera;
 		cam.pos[0] = 0; cam.pos[1] = 0; cam.pos[2] = 5;
@@ -205,6 +210,7 @@ Scene scene_new(std::string const& name, std::string const& data_root, ColorData
 		cam.res[0] = 512; cam.res[1] = 512; cam.near_ = 0.1f; cam.far_ = 1.0f;
 		cam.vfov_deg = (2.0f * std::atan2(1.0f, cam.pos[2])) * static_cast<float>(57.295779513082320876798154814105);
 		Material light; light.albedo = b.constant(0.0f); light.emission = color.D65_rad;
+		for (int k = 0; k < 3; ++k) { light.albedo_rgb[k] = 0.0f; light.emission_rgb[k] = 1.0f; }  // scene.cpp:340-341
 		int mtl_light = b.add_material("light", light);
 		b.scene.textures.push_back(load_png_rgb8(lizard));
 		Material tex; tex.albedo_mode = SSB_ALBEDO_TEXTURE; tex.texture = 0;

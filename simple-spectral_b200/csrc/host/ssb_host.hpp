@@ -84,6 +84,9 @@ struct Material {
 	Spectrum albedo;
 	int texture = -1;
 	Spectrum emission;
+	// the same material in the reference's RENDER_MODE_RGB build (the `#else` branches of scene.cpp:48-101,297-343)
+	float albedo_rgb[3] = { 1, 1, 1 };    // Albedo(): RGB_Reflectance(1.0f), material.hpp:131
+	float emission_rgb[3] = { 0, 0, 0 };  // MaterialBase(): emission(0.0f)
 	bool is_emissive() const;  // material.cpp:100-106
 };
 
@@ -132,6 +135,7 @@ struct RendererOptions {
 	bool explicit_light_sampling = true;
 	uint32_t max_depth = 10;
 	bool flat_field_correction = true;
+	uint32_t render_mode = SSB_RENDER_SPECTRAL;  // SSB_RENDER_RGB = the RENDER_MODE_RGB build
 	uint64_t seed = 1;
 	int device = 0;
 	std::string data_root = ".";

@@ -50,6 +50,7 @@ struct HostSpectrum {
 struct HostMaterial {
 	uint32_t kind = 0, albedo_mode = 0, texture = 0;
 	HostSpectrum albedo, emission;
+	float albedo_rgb[3] = { 1, 1, 1 }, emission_rgb[3] = { 0, 0, 0 };  // RENDER_MODE_RGB constants
 };
 
 int copy_spectrum(const ssb_spectrum& s, HostSpectrum& out, const char* what, bool required) {
@@ -144,7 +145,7 @@ DevSpectrum pack_spectrum(const HostSpectrum& s, std::vector<float>& pool) {
 // Build the shared-memory image: [DevHeader][quads][materials][lights][textures][float pool]
 int build_blob(ssb_ctx* c) {
 	if (!c->have_scene) return fail(SSB_ERR_ARG, "ssb_render: no scene uploaded");
-	if (!c->have_color) return fail(SSB_ERR_ARG, "ssb_render: no colour tables uploaded");
+	// (colour tables may be absent: RGB mode needs none; ssb_render checks what the chosen mode needs)
 	std::vector<float> pool;
 	DevHeader hdr{};
 	hdr.nquads = (uint32_t)c->quads.size();
@@ -167,6 +168,8 @@ int build_blob(ssb_ctx* c) {
 		mats[m].kind = hm.kind; mats[m].albedo_mode = hm.albedo_mode; mats[m].texture = hm.texture; mats[m].pad = 0;
 		mats[m].albedo = pack_spectrum(hm.albedo, pool);
 		mats[m].emission = pack_spectrum(hm.emission, pool);
+		for (int k = 0; k < 3; ++k) { mats[m].albedo_rgb[k] = hm.albedo_rgb[k]; mats[m].emission_rgb[k] = hm.emission_rgb[k]; }
+		mats[m].albedo_rgb[3] = mats[m].emission_rgb[3] = 0.0f;
 	}
 	std::vector<DevTexture> texs(c->d_textures.size());
 	for (size_t t = 0; t < texs.size(); ++t) { texs[t].rgba = c->d_textures[t]; texs[t].width = c->tex_w[t]; texs[t].height = c->tex_h[t]; }
@@ -281,9 +284,11 @@ int validate_options(const ssb_options* o, uint32_t& x1, uint32_t& y1, uint32_t&
 	x1 = o->x1 ? o->x1 : o->width; y1 = o->y1 ? o->y1 : o->height; s1 = o->sample_end ? o->sample_end : o->spp;
 	if (x1 > o->width || y1 > o->height || o->x0 > x1 || o->y0 > y1 || o->sample_begin > s1)
 		return fail(SSB_ERR_ARG, "work subset out of range");
-	if (o->upsampling < SSB_UPSAMPLE_OURS || o->upsampling > SSB_UPSAMPLE_JH) return fail(SSB_ERR_UNSUPPORTED, "unknown upsampling mode %u", o->upsampling);
+	if (o->render_mode > SSB_RENDER_RGB) return fail(SSB_ERR_UNSUPPORTED, "unknown render mode %u", o->render_mode);
+	const bool rgb = o->render_mode == SSB_RENDER_RGB;  // upsampling / wavelength range are not used in RGB mode
+	if (!rgb && (o->upsampling < SSB_UPSAMPLE_OURS || o->upsampling > SSB_UPSAMPLE_JH)) return fail(SSB_ERR_UNSUPPORTED, "unknown upsampling mode %u", o->upsampling);
 	if (o->max_depth == 0 || o->max_depth > SSB_MAX_DEPTH) return fail(SSB_ERR_UNSUPPORTED, "max_depth must be in [1,%u]", SSB_MAX_DEPTH);
-	if (!(o->lambda_max > o->lambda_min)) return fail(SSB_ERR_ARG, "lambda_max must exceed lambda_min");
+	if (!rgb && !(o->lambda_max > o->lambda_min)) return fail(SSB_ERR_ARG, "lambda_max must exceed lambda_min");
 	return SSB_OK;
 }
 
@@ -368,9 +373,11 @@ int ssb_upload_scene(ssb_ctx* c, const ssb_scene* scene) {
 		if (sm.kind > SSB_MATERIAL_MIRROR || sm.albedo_mode > SSB_ALBEDO_TEXTURE) return fail(SSB_ERR_ARG, "material %u: bad kind/mode", m);
 		mats[m].kind = sm.kind; mats[m].albedo_mode = sm.albedo_mode; mats[m].texture = sm.texture;
 		int rc;
-		if (sm.albedo_mode == SSB_ALBEDO_CONSTANT) { if ((rc = copy_spectrum(sm.albedo, mats[m].albedo, "material albedo", true)) != SSB_OK) return rc; }
+		// the spectra may be absent in a scene meant for RGB mode only; ssb_render checks what its mode needs
+		if (sm.albedo_mode == SSB_ALBEDO_CONSTANT) { if ((rc = copy_spectrum(sm.albedo, mats[m].albedo, "material albedo", false)) != SSB_OK) return rc; }
 		else if (sm.texture >= scene->ntextures) return fail(SSB_ERR_ARG, "material %u: texture index out of range", m);
-		if ((rc = copy_spectrum(sm.emission, mats[m].emission, "material emission", true)) != SSB_OK) return rc;
+		if ((rc = copy_spectrum(sm.emission, mats[m].emission, "material emission", false)) != SSB_OK) return rc;
+		for (int k = 0; k < 3; ++k) { mats[m].albedo_rgb[k] = sm.albedo_rgb[k]; mats[m].emission_rgb[k] = sm.emission_rgb[k]; }
 	}
 	std::vector<uint32_t> lights;
 	for (uint32_t q = 0; q < scene->nquads; ++q) {
@@ -465,12 +472,21 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	SSB_CUDA(cudaSetDevice(c->device));
 	if (c->blob_dirty && (rc = build_blob(c)) != SSB_OK) return rc;
 	if (o->explicit_light_sampling && c->lights.empty()) return fail(SSB_ERR_ARG, "explicit light sampling needs at least one light (scene.cpp:30)");
-	if (o->upsampling == SSB_UPSAMPLE_OURS && !c->basis_r.present) {
+	const bool rgb = o->render_mode == SSB_RENDER_RGB;
+	if (!rgb) {
+		if (!c->have_color) return fail(SSB_ERR_ARG, "ssb_render: no colour tables uploaded");
+		for (size_t m = 0; m < c->materials.size(); ++m) {
+			const HostMaterial& hm = c->materials[m];
+			if (!hm.emission.present || (hm.albedo_mode == SSB_ALBEDO_CONSTANT && !hm.albedo.present))
+				return fail(SSB_ERR_ARG, "material %zu: missing spectrum (the scene was uploaded with RGB constants only)", m);
+		}
+	}
+	if (!rgb && o->upsampling == SSB_UPSAMPLE_OURS && !c->basis_r.present) {
 		for (const HostMaterial& m : c->materials)
 			if (m.albedo_mode == SSB_ALBEDO_TEXTURE) return fail(SSB_ERR_ARG, "OURS upsampling needs the basis spectra");
 	}
-	if (o->upsampling == SSB_UPSAMPLE_JH && !c->jh_res) return fail(SSB_ERR_ARG, "JH upsampling needs the coefficient tables");
-	if (o->upsampling == SSB_UPSAMPLE_MENG && !c->have_meng) return fail(SSB_ERR_ARG, "MENG upsampling needs the grid tables");
+	if (!rgb && o->upsampling == SSB_UPSAMPLE_JH && !c->jh_res) return fail(SSB_ERR_ARG, "JH upsampling needs the coefficient tables");
+	if (!rgb && o->upsampling == SSB_UPSAMPLE_MENG && !c->have_meng) return fail(SSB_ERR_ARG, "MENG upsampling needs the grid tables");
 	if ((rc = ensure_accum(c, o->width, o->height)) != SSB_OK) return rc;
 	if (o->sample_begin == 0) SSB_CUDA(cudaMemsetAsync(c->d_accum, 0, (size_t)o->width * o->height * 4 * sizeof(double), c->stream));
 
@@ -539,6 +555,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.width = o->width; P.height = o->height; P.x0 = o->x0; P.y0 = o->y0; P.rect_w = rect_w; P.rect_h = rect_h;
 	P.indirect_only = o->indirect_only; P.upsampling = o->upsampling; P.max_depth = o->max_depth;
 	P.els = o->explicit_light_sampling; P.flat_field = o->flat_field_correction;
+	P.render_mode = o->render_mode;
 	P.eps = o->eps; P.lambda_min = o->lambda_min;
 	P.lambda_step = (o->lambda_max - o->lambda_min) / (float)4;  // LAMBDA_STEP (stdafx.hpp:289)
 	P.seed = o->seed;
@@ -554,7 +571,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	const size_t smem = c->blob_bytes;
 	typedef void (*kfn)(const KParams);
 	kfn k_shade_first = nullptr, k_shade_next = nullptr;
-	switch (o->upsampling) {  // one instantiation per upsampling mode keeps the instruction footprint small
+	switch (rgb ? (uint32_t)SSB_UPS_RGB : o->upsampling) {  // one instantiation per upsampling mode keeps the instruction footprint small
+		case SSB_UPS_RGB: k_shade_first = ssb_shade_kernel<true, SSB_UPS_RGB>; k_shade_next = ssb_shade_kernel<false, SSB_UPS_RGB>; break;
 		case SSB_UPSAMPLE_OURS: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_OURS>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_OURS>; break;
 		case SSB_UPSAMPLE_JH: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_JH>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_JH>; break;
 		default: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_MENG>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_MENG>; break;
@@ -678,7 +696,7 @@ static int resolve_impl(ssb_ctx* c, const ssb_options* o, double* xyza_host, flo
 	double scale = 1000.0 / (double)o->spp;  // renderer.cpp:296
 	unsigned grid = (unsigned)((npix + 127) / 128);
 	ssb_resolve_kernel<<<grid, 128, 0, c->stream>>>(c->d_accum, (device_only || xyza_host) ? c->d_xyza : nullptr, (device_only || srgba_host) ? c->d_srgba : nullptr,
-	                                                (uint32_t)npix, scale, o->upsampling, c->d65_rad_Y,
+	                                                (uint32_t)npix, scale, o->render_mode == SSB_RENDER_RGB ? (double)o->spp : 0.0, o->upsampling, c->d65_rad_Y,
 	                                                m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
 	SSB_CUDA(cudaGetLastError());
 	c->stats.launches += 1;

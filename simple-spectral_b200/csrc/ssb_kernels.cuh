@@ -47,6 +47,7 @@ struct DevSpectrum {  // _Spectrum (spectrum.hpp:12-70), data in the float pool
 struct DevMaterial {
 	uint32_t kind, albedo_mode, texture, pad;
 	DevSpectrum albedo, emission;
+	float albedo_rgb[4], emission_rgb[4];  // RENDER_MODE_RGB constants (4th = 0)
 };
 struct DevTexture {
 	const uchar4* rgba;  // RGB8 re-packed to RGBA8 at upload: one aligned 4-byte load per texel
@@ -92,6 +93,7 @@ struct KParams {
 	unsigned long long total_work;  // npix_rect * nsamp
 	uint32_t width, height, x0, y0, rect_w, rect_h, sample_begin, nsamp;
 	uint32_t indirect_only, upsampling, max_depth, els, flat_field;
+	uint32_t render_mode;  // SSB_RENDER_SPECTRAL / SSB_RENDER_RGB
 	uint32_t depth;     // depth processed by this launch
 	float eps, lambda_min, lambda_step;
 	unsigned long long seed;
@@ -325,12 +327,33 @@ __device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, f
 	return h;
 }
 
+// Template parameter UPS of the shading code: one of SSB_UPSAMPLE_* for spectral transport, or SSB_UPS_RGB for the
+// reference's RENDER_MODE_RGB build (three l-RGB channels carried in v[0..2], v[3] = 0: every per-channel operation of
+// the reference's vec3 arithmetic is the same expression, and dot(f,f) = (f0^2+f1^2)+(f2^2+0) is unchanged by the zero).
+#define SSB_UPS_RGB 0
+
+// MaterialBase::evaluate_emission (material.hpp:96-104)
+template <int UPS>
+__device__ __forceinline__ Hero material_emission(const KParams& P, const SceneView& S, const DevMaterial& m, float lambda_0) {
+	if (UPS == SSB_UPS_RGB) {
+		Hero h; h.v[0] = m.emission_rgb[0]; h.v[1] = m.emission_rgb[1]; h.v[2] = m.emission_rgb[2]; h.v[3] = 0.0f;
+		return h;
+	}
+	return spec_hero(S.pool(), m.emission, lambda_0, P.lambda_step);
+}
+
 // material albedo at (st, lambda_0): constant spectrum or sRGB texture + upsampling
 // (material.cpp:45-97,120-143; color.cpp:166-232)
 template <int UPS>
 __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneView& S, const DevMaterial& m,
                                                 float st_x, float st_y, float lambda_0) {
-	if (m.albedo_mode == SSB_ALBEDO_CONSTANT) return spec_hero(S.pool(), m.albedo, lambda_0, P.lambda_step);
+	if (m.albedo_mode == SSB_ALBEDO_CONSTANT) {
+		if (UPS == SSB_UPS_RGB) {
+			Hero h; h.v[0] = m.albedo_rgb[0]; h.v[1] = m.albedo_rgb[1]; h.v[2] = m.albedo_rgb[2]; h.v[3] = 0.0f;
+			return h;
+		}
+		return spec_hero(S.pool(), m.albedo, lambda_0, P.lambda_step);
+	}
 	const DevTexture tex = S.textures()[m.texture];
 	float index_x = st_x * (float)tex.width;
 	float index_y = (float)tex.height - st_y * (float)tex.height;
@@ -339,7 +362,10 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 	j = max(j, 0); j = min(j, (int)tex.height - 1);
 	uchar4 px = __ldg(tex.rgba + ((size_t)j * tex.width + (size_t)i));
 	float r = S.hdr()->srgb_lut[px.x], g = S.hdr()->srgb_lut[px.y], b = S.hdr()->srgb_lut[px.z];
-	if (UPS == SSB_UPSAMPLE_OURS) {
+	if (UPS == SSB_UPS_RGB) {  // material.cpp:64-66: the texel's l-RGB is the reflectance
+		Hero h; h.v[0] = r; h.v[1] = g; h.v[2] = b; h.v[3] = 0.0f;
+		return h;
+	} else if (UPS == SSB_UPSAMPLE_OURS) {
 		Hero br = spec_hero(S.pool(), S.hdr()->basis_r, lambda_0, P.lambda_step);
 		Hero bg = spec_hero(S.pool(), S.hdr()->basis_g, lambda_0, P.lambda_step);
 		Hero bb = spec_hero(S.pool(), S.hdr()->basis_b, lambda_0, P.lambda_step);
@@ -688,7 +714,8 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				double inv = 1.0 / sqrt((ddx * ddx + ddy * ddy) + ddz * ddz);
 				ox = P.cam_pos[0]; oy = P.cam_pos[1]; oz = P.cam_pos[2];
 				dx = (float)(ddx * inv); dy = (float)(ddy * inv); dz = (float)(ddz * inv);
-				const float lambda_0 = P.lambda_min + rand_1f(rng) * P.lambda_step;
+				// hero wavelength (renderer.cpp:134-143): drawn in spectral mode only
+				const float lambda_0 = (P.render_mode == SSB_RENDER_RGB) ? 0.0f : P.lambda_min + rand_1f(rng) * P.lambda_step;
 				if (!P.flat_field) P.ff[id] = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
 				P.recA[0][2 * (size_t)item] = make_float4(ox, oy, oz, __int_as_float(-1));
 				P.recA[0][2 * (size_t)item + 1] = make_float4(dx, dy, dz, lambda_0);
@@ -849,7 +876,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			const float st_y = (h1.x * tri.v[0].st[1] + h1.y * tri.v[1].st[1]) + h1.z * tri.v[2].st[1];
 			// emission: last_was_delta is true only for the camera ray (the reference recurses with `false`, :248)
 			if (!els || (FIRST && !P.indirect_only)) {
-				Hero e = spec_hero(S.pool(), m.emission, lambda_0, P.lambda_step);
+				Hero e = material_emission<UPS>(P, S, m, lambda_0);
 #pragma unroll
 				for (int c = 0; c < 4; ++c) local.v[c] = local.v[c] + e.v[c];
 			}
@@ -886,7 +913,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			scene_intersect(S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
 			if (hs.quad == light_quad) {
 				const DevMaterial& lm = S.materials()[S.quads()[light_quad].material];
-				Hero emitted = spec_hero(S.pool(), lm.emission, lambda_0, P.lambda_step);
+				Hero emitted = material_emission<UPS>(P, S, lm, lambda_0);
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
 					float fe = (mat_kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;  // MaterialMirror::evaluate_bsdf = 0
@@ -1032,6 +1059,13 @@ __global__ void __launch_bounds__(128) ssb_finalize_kernel(const __grid_constant
 			const float s = P.ff[id];
 			r0 *= s; r1 *= s; r2 *= s; r3 *= s;
 		}
+		const float hitf = (info >> 16) ? 1.0f : 0.0f;
+		if (P.render_mode == SSB_RENDER_RGB) {
+			// RENDER_MODE_RGB (renderer.cpp:274-275, 301-303): the sample is (l-RGB flux, hit), accumulated unscaled
+			if (P.samples) P.samples[id] = make_float4(r0, r1, r2, hitf);
+			a0 += (double)r0; a1 += (double)r1; a2 += (double)r2; a3 += (double)hitf;
+			continue;
+		}
 		float rad[4] = { r0, r1, r2, r3 };
 		float X = 0.0f, Y = 0.0f, Z = 0.0f;
 #pragma unroll
@@ -1041,7 +1075,6 @@ __global__ void __launch_bounds__(128) ssb_finalize_kernel(const __grid_constant
 			Y += (spec_sample(pool, sy, lambda) * rad[c]) * P.lambda_step;
 			Z += (spec_sample(pool, sz, lambda) * rad[c]) * P.lambda_step;
 		}
-		const float hitf = (info >> 16) ? 1.0f : 0.0f;
 		if (P.samples) P.samples[id] = make_float4(X, Y, Z, hitf);
 		a0 += (double)(X * 0.001f); a1 += (double)(Y * 0.001f);
 		a2 += (double)(Z * 0.001f); a3 += (double)(hitf * 0.001f);
@@ -1051,13 +1084,17 @@ __global__ void __launch_bounds__(128) ssb_finalize_kernel(const __grid_constant
 
 // avg *= 1000/spp; framebuffer = (ciexyz_to_srgb(float3(avg)), float(avg.a)) (renderer.cpp:296-298, color.cpp:237-257)
 __global__ void ssb_resolve_kernel(const double* __restrict__ accum, double* __restrict__ xyza, float4* __restrict__ srgba,
-                                   uint32_t npix, double scale, uint32_t upsampling, float d65_rad_Y,
+                                   uint32_t npix, double scale, double spp_rgb, uint32_t upsampling, float d65_rad_Y,
                                    float m0, float m1, float m2, float m3, float m4, float m5, float m6, float m7, float m8) {
 	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= npix) return;
 	double avg[4];
 #pragma unroll
-	for (int c = 0; c < 4; ++c) avg[c] = accum[4 * (size_t)p + c] * scale;
+	for (int c = 0; c < 4; ++c) {
+		// spp_rgb > 0 selects RENDER_MODE_RGB: avg /= double(spp) (renderer.cpp:304) instead of avg *= 1000/spp (:296)
+		const double a = accum[4 * (size_t)p + c];
+		avg[c] = spp_rgb > 0.0 ? a / spp_rgb : a * scale;
+	}
 	if (xyza) {
 #pragma unroll
 		for (int c = 0; c < 4; ++c) xyza[4 * (size_t)p + c] = avg[c];
@@ -1065,7 +1102,9 @@ __global__ void ssb_resolve_kernel(const double* __restrict__ accum, double* __r
 	if (srgba) {
 		float x = (float)avg[0], y = (float)avg[1], z = (float)avg[2];
 		float lr, lg, lb;
-		if (upsampling == SSB_UPSAMPLE_MENG) {
+		if (spp_rgb > 0.0) {  // Color::lrgb_to_srgb(lRGB_F32(avg)), renderer.cpp:306
+			lr = x; lg = y; lb = z;
+		} else if (upsampling == SSB_UPSAMPLE_MENG) {
 			x = x / d65_rad_Y; y = y / d65_rad_Y; z = z / d65_rad_Y;
 			lr = (3.24156456f * x + -1.53766524f * y) + -0.49870224f * z;
 			lg = (-0.96920119f * x + 1.87588535f * y) + 0.04155324f * z;

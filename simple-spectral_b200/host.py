@@ -14,7 +14,7 @@ class ssbh_renderer_options(C.Structure):
                 ("indirect_only", C.c_uint32), ("output_path", C.c_char_p), ("observer", C.c_int),
                 ("upsampling", C.c_uint32), ("explicit_light_sampling", C.c_uint32), ("max_depth", C.c_uint32),
                 ("flat_field_correction", C.c_uint32), ("seed", C.c_uint64), ("device", C.c_int),
-                ("data_root", C.c_char_p)]
+                ("data_root", C.c_char_p), ("render_mode", C.c_uint32)]
 
 
 HOST_SYMBOLS = (
@@ -82,6 +82,7 @@ def find_data_root():
 VARIANTS = {  # the reference's compile-time variants (stdafx.hpp:66,81)
     "ours1931": (1931, _abi.SSB_UPSAMPLE_OURS), "ours2006": (2006, _abi.SSB_UPSAMPLE_OURS),
     "jh": (1931, _abi.SSB_UPSAMPLE_JH), "meng": (1931, _abi.SSB_UPSAMPLE_MENG),
+    "rgb": (1931, _abi.SSB_UPSAMPLE_OURS),  # RENDER_MODE_RGB: the colour tables are built but not used by the render
 }
 
 
@@ -185,7 +186,8 @@ class Renderer:
         obs, ups = VARIANTS[variant]
         self._keep = (scene_name.encode(), output_path.encode() if output_path else None, (data_root or find_data_root()).encode())
         o = ssbh_renderer_options(self._keep[0], width, height, spp, int(indirect_only), self._keep[1], obs, ups,
-                                  int(explicit_light_sampling), max_depth, int(flat_field_correction), seed, device, self._keep[2])
+                                  int(explicit_light_sampling), max_depth, int(flat_field_correction), seed, device, self._keep[2],
+                                  _abi.SSB_RENDER_RGB if variant == "rgb" else _abi.SSB_RENDER_SPECTRAL)
         self._h = C.c_void_p()
         self.width, self.height = width, height
         _check(hostlib().ssbh_renderer_new(C.byref(o), C.byref(self._h)))

@@ -27,16 +27,18 @@ def test_cli_usage_and_error_codes():
 
 
 @pytest.mark.gpu
-def test_cli_renders_the_oracle_image(tmp_path):
-    """`simple_spectral_b200 --scene=cornell ...` writes the same PFM the oracle's framebuffer gives."""
+@pytest.mark.parametrize("variant", ["ours1931", "rgb"])
+def test_cli_renders_the_oracle_image(tmp_path, variant):
+    """`simple_spectral_b200 --scene=cornell ...` writes the same PFM the oracle's framebuffer gives
+    (host-layer scene + CUDA path vs reference-dumped scene + oracle), in spectral and in RGB mode."""
     import importlib
     host = importlib.import_module("simple-spectral_b200.host")
     out = str(tmp_path / "o.pfm")
-    r = _run("--scene=cornell", "-w=32", "-h=24", "-spp=4", f"--output={out}", "--seed=7", f"--data-root={pu.data_root()}")
+    r = _run("--scene=cornell", "-w=32", "-h=24", "-spp=4", f"--output={out}", "--seed=7", f"--data-root={pu.data_root()}", f"--variant={variant}")
     assert r.returncode == 0, r.stderr
     assert "Render completed in" in r.stdout
-    flat = pu.load_flat("cornell", "ours1931")
-    opt = pu.options("ours1931", 32, 24, 4, seed=7)
+    flat = pu.load_flat("cornell", variant)
+    opt = pu.options(variant, 32, 24, 4, seed=7)
     acc, _, _ = pu.oracle_render(flat, opt)
     _, srgba = pu.oracle_resolve(flat, opt, acc)
     want = str(tmp_path / "w.pfm")

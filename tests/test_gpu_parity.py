@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 CASES = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("plane-srgb", "ours1931"),
          ("cornell", "ours2006"), ("cornell-srgb", "ours2006"),
          ("cornell-srgb", "jh"), ("plane-srgb", "jh"), ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
-         ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels")]
+         ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels"),
+         ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb")]  # RENDER_MODE_RGB build of the reference
 
 
 def _skip_if_no_assets(scene, variant):
@@ -81,6 +82,29 @@ def test_gpu_config1_bit_exact():
         xg, _ = ctx.render_frame(opt)
     idx = json.load(open(os.path.join(pu.GOLDEN, "golden_index.json")))["cornell-srgb_ours1931_128x128_spp16_seed1"]
     assert hashlib.sha256(xg.tobytes()).hexdigest() == idx["sha256"]
+
+
+def test_gpu_rgb_config1_bit_exact():
+    """RENDER_MODE_RGB, cornell-srgb 128x128 spp16: CUDA == the RGB build of the real reference (sha of the l-RGB+alpha buffer)."""
+    import hashlib, json
+    _skip_if_no_assets("cornell-srgb", "rgb")
+    flat = pu.load_flat("cornell-srgb", "rgb")
+    opt = pu.options("rgb", 128, 128, 16, seed=1)
+    with pu.gpu_context(flat) as ctx:
+        avg, _ = ctx.render_frame(opt)
+    idx = json.load(open(os.path.join(pu.GOLDEN, "golden_index.json")))["cornell-srgb_rgb_128x128_spp16_seed1"]
+    assert hashlib.sha256(avg.tobytes()).hexdigest() == idx["sha256"]
+
+
+def test_gpu_spectral_scene_needs_spectra():
+    """A scene uploaded with RGB constants only (no spectra) must be refused in spectral mode, not rendered black."""
+    import importlib
+    ssb = importlib.import_module("simple-spectral_b200")
+    flat = pu.load_flat("cornell", "rgb")
+    with pu.gpu_context(flat) as ctx:
+        with pytest.raises(ssb.SsbError) as e:
+            ctx.render(pu.options("ours1931", 16, 16, 1))
+        assert e.value.code == -2
 
 
 def test_gpu_subsets_compose():

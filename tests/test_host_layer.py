@@ -85,6 +85,34 @@ def test_host_tables_match_reference_dump(scene, variant):
     assert fs.nmaterials == m
 
 
+@pytest.mark.parametrize("scene", ["cornell", "cornell-srgb", "plane-srgb"])
+def test_host_rgb_constants_match_rgb_reference_dump(scene):
+    """The RENDER_MODE_RGB build of the reference: same geometry / material ids / light flags, RGB constants."""
+    t = refdump.parse(os.path.join(pu.GOLDEN, f"tables_{scene}_rgb.bin"))
+    color = host.Color(pu.data_root())
+    sc = host.Scene(scene, color)  # keep alive: `flat` points into it
+    fs = sc.flat
+    assert pu.bits_equal(np.array(fs.camera.pv_inv[:]), t["camera.matr_PV_inv"])
+    q = t["scene.quads"].reshape(-1, 2, 18)
+    assert fs.nquads == q.shape[0]
+    for qi in range(fs.nquads):
+        for ti in range(2):
+            tri = fs.quads[qi].tri[ti]
+            got = np.concatenate([np.concatenate([tri.v[vi].pos[:], tri.v[vi].st[:]]) for vi in range(3)] + [tri.normal[:]]).astype(np.float32)
+            assert pu.bits_equal(got, q[qi, ti])
+    assert [fs.quads[i].material for i in range(fs.nquads)] == list(t["scene.quad_material"])
+    assert [fs.quads[i].is_light for i in range(fs.nquads)] == list(t["scene.quad_is_light"])
+    m = 0
+    while f"material.{m}.kind_mode" in t:
+        fm = fs.materials[m]
+        assert (fm.kind, fm.albedo_mode) == tuple(t[f"material.{m}.kind_mode"])
+        assert pu.bits_equal(np.array(fm.emission_rgb[:], np.float32), t[f"material.{m}.emission_rgb"])
+        if fm.albedo_mode == 0:
+            assert pu.bits_equal(np.array(fm.albedo_rgb[:], np.float32), t[f"material.{m}.albedo_rgb"])
+        m += 1
+    assert fs.nmaterials == m
+
+
 def test_png_decoder_matches_pillow():
     root = pu.data_root()
     for name in ("scenes/test-img.png", "scenes/crystal-lizard-512.png"):
