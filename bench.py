@@ -188,7 +188,8 @@ def main_ours(args, rank, local_rank, world):
     ctx.set_stream(stream.cuda_stream)
 
     total_spp = SPP * world  # weak scaling: the job is the same frame at spp 64*N
-    opt = host.options_for(color, W, H, total_spp, seed=1, sample_begin=rank * SPP, sample_end=(rank + 1) * SPP)
+    opt = host.options_for(color, W, H, total_spp, seed=1, sample_begin=rank * SPP, sample_end=(rank + 1) * SPP,
+                           render_mode=ssb.SSB_RENDER_RGB if VARIANT == "rgb" else ssb.SSB_RENDER_SPECTRAL)
     npix = W * H
 
     def device_accum_tensor():
@@ -248,21 +249,24 @@ def main_ours(args, rank, local_rank, world):
     value = samples_per_step * args.steps / (dev_ms * 1e-3) / 1e6
 
     # ---------------- e2e: host buffers in, host buffers out, every step
-    tex_np = host.load_png_rgb8(os.path.join(color.data_root, "data", "scenes", "crystal-lizard-4096.png"))
-    pinned_tex = torch.empty(tex_np.shape, dtype=torch.uint8, pin_memory=True)
-    pinned_tex.numpy()[...] = tex_np
     flat_scene = scene.flat
-    tex_desc = (ssb.ssb_texture * 1)()
-    tex_desc[0].rgb8 = C.cast(pinned_tex.data_ptr(), C.POINTER(C.c_uint8))
-    tex_desc[0].width, tex_desc[0].height = tex_np.shape[1], tex_np.shape[0]
     e2e_scene = ssb.ssb_scene()
     C.memmove(C.byref(e2e_scene), C.byref(flat_scene), C.sizeof(e2e_scene))
-    e2e_scene.textures = tex_desc
+    tex_bytes = 0
+    if flat_scene.ntextures:  # the textured scenes re-upload their 4096^2 texture from pinned memory every step
+        tex_np = host.load_png_rgb8(os.path.join(color.data_root, "data", "scenes", "crystal-lizard-4096.png"))
+        pinned_tex = torch.empty(tex_np.shape, dtype=torch.uint8, pin_memory=True)
+        pinned_tex.numpy()[...] = tex_np
+        tex_desc = (ssb.ssb_texture * 1)()
+        tex_desc[0].rgb8 = C.cast(pinned_tex.data_ptr(), C.POINTER(C.c_uint8))
+        tex_desc[0].width, tex_desc[0].height = tex_np.shape[1], tex_np.shape[0]
+        e2e_scene.textures = tex_desc
+        tex_bytes = tex_np.nbytes
     xyza_host = torch.empty((H, W, 4), dtype=torch.float64, pin_memory=True)
     srgba_host = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
     xyza_np, srgba_np = xyza_host.numpy(), srgba_host.numpy()
     accum_host = torch.empty(npix * 4, dtype=torch.float64, pin_memory=True) if world > 1 else None
-    h2d = tex_np.nbytes + 16 * 1024  # texture + (scene blob + colour tables, < 16 KiB)
+    h2d = tex_bytes + 16 * 1024  # texture + (scene blob + colour tables, < 16 KiB)
     d2h = xyza_np.nbytes + srgba_np.nbytes
 
     def step_e2e():
@@ -359,7 +363,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scene", default=SCENE, choices=sorted(ALGO_BYTES_PER_SAMPLE),
                     help="default = BASELINE configs[1]; the others are SURVEY 8(d) C3-C5 (not the headline)")
-    ap.add_argument("--variant", default=VARIANT, choices=["ours1931", "ours2006", "meng", "jh"])
+    ap.add_argument("--variant", default=VARIANT, choices=["ours1931", "ours2006", "meng", "jh", "rgb"])
     args = ap.parse_args()
     SCENE, VARIANT = args.scene, args.variant
     if args.warmup < 3 and args.impl == "ours":

@@ -224,7 +224,8 @@ int ssb_get_stats(ssb_ctx* ctx, ssb_stats* out);
 int ssb_synchronize(ssb_ctx* ctx);
 
 /* Test hooks (bit-exactness of the device maths against the host libm the reference links):
- * evaluates fn over n inputs ON THE GPU.  fn: 0 sinf, 1 cosf, 2 acosf, 3 powf(x, y=arg). */
+ * evaluates fn over n inputs ON THE GPU.  fn: 0 sinf, 1 cosf, 2 acosf, 3 powf(x, y=arg),
+ * 4 / 5: the sin / cos result of the paired sincos the kernels use. */
 int ssb_debug_eval_math(ssb_ctx* ctx, uint32_t fn, const float* x_host, float arg, float* out_host, size_t n);
 /* Per-sample outputs of one pixel (float4 per sample), for matched-seed debugging. */
 int ssb_debug_trace_samples(ssb_ctx* ctx, const ssb_options* opt, uint32_t px, uint32_t py, float* out_host);

@@ -173,6 +173,14 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 __device__ __noinline__ float acosf_x(float x) { return ssbm::acosf_exact(x); }
 __device__ __noinline__ float sinf_x(float x) { return ssbm::sinf_exact(x); }
 __device__ __noinline__ float cosf_x(float x) { return ssbm::cosf_exact(x); }
+// sin and cos of the same argument share glibc's argument reduction (ssbm::sincosf_exact): each result is the scalar
+// function's, bit for bit, for ~40 % fewer instructions than two calls (measured: +0.8 % frame rate, profiles/r1p_tune.txt).
+// (Returned by value: reference parameters of a non-inlined function would go through local memory.)
+__device__ __noinline__ float2 sincosf_x(float x) {  // (sin, cos)
+	float s, c;
+	ssbm::sincosf_exact(x, &s, &c);
+	return make_float2(s, c);
+}
 
 // ------------------------------------------------------------------ shared-memory view of the blob
 // The blob lives in dynamic shared memory.  It is declared at namespace scope and reached through these accessors
@@ -590,7 +598,8 @@ __device__ __noinline__ void sample_spherical_triangle(int light_quad, int light
 	if (sin_alpha > 0) {
 		float random_area = r0 * surface_area;
 		float phi = random_area - alpha;
-		float s = sinf_x(phi), tt = cosf_x(phi);
+		const float2 sc_phi = sincosf_x(phi);
+		const float s = sc_phi.x, tt = sc_phi.y;
 		float u = tt - cos_alpha;
 		float v = s + sin_alpha * cos_c;
 		float denom = (v * s + u * tt) * sin_alpha;
@@ -934,7 +943,8 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 					float cx, cy, cz;  // Math::rand_coshemi (random.cpp:29-49)
 					do {
 						float angle = rand_1f(rng) * (2.0f * SSB_PI_F);
-						float co = cosf_x(angle), si = sinf_x(angle);
+						const float2 sc_angle = sincosf_x(angle);
+						const float si = sc_angle.x, co = sc_angle.y;
 						float radius_sq = rand_1f(rng);
 						float radius = sqrtf(radius_sq);
 						cx = radius * co; cy = sqrtf(1.0f - radius_sq); cz = radius * si;
@@ -1139,6 +1149,8 @@ __global__ void ssb_eval_math_kernel(uint32_t fn, const float* __restrict__ x, f
 		case 0: r = ssbm::sinf_exact(v); break;
 		case 1: r = ssbm::cosf_exact(v); break;
 		case 2: r = ssbm::acosf_exact(v); break;
+		case 4: { float s, c; ssbm::sincosf_exact(v, &s, &c); r = s; break; }  // the paired form used by the kernels
+		case 5: { float s, c; ssbm::sincosf_exact(v, &s, &c); r = c; break; }
 		default: r = ssbm::powf_exact(v, arg); break;
 	}
 	out[i] = r;
