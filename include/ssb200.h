@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 2u /* 2: RGB render mode (ssb_material.*_rgb, ssb_options.render_mode) */
+#define SSB_ABI_VERSION 2u /* 2: RGB render mode (ssb_material.*_rgb, ssb_options.render_mode), n_wavelengths */
 
 #define SSB_OK 0
 #define SSB_ERR_DATA (-1)
@@ -161,7 +161,8 @@ typedef struct ssb_options {
 	float eps;                        /* EPS, 1e-3f */
 	uint64_t seed;                    /* per-sample seeding: PCG32.seed(mix(seed, sample index)) */
 	uint32_t render_mode;             /* SSB_RENDER_* */
-	uint32_t reserved;                /* must be 0 */
+	uint32_t n_wavelengths;           /* SAMPLE_WAVELENGTHS (stdafx.hpp:90): 0 = the default 4; 2, 3 or 4 (the sizes of
+	                                   * glm::vec the reference compiles with).  LAMBDA_STEP = (max-min)/n (stdafx.hpp:289) */
 } ssb_options;
 
 typedef struct ssb_stats {

@@ -48,6 +48,7 @@ typedef struct ssbh_renderer_options {
 	int device;
 	const char* data_root;
 	uint32_t render_mode; /* SSB_RENDER_SPECTRAL | SSB_RENDER_RGB (RENDER_MODE_RGB, stdafx.hpp:62-90) */
+	uint32_t n_wavelengths; /* SAMPLE_WAVELENGTHS (stdafx.hpp:90): 0 = 4; 2, 3 or 4 */
 } ssbh_renderer_options;
 int ssbh_renderer_new(const ssbh_renderer_options* options, ssbh_renderer** out);
 int ssbh_renderer_render(ssbh_renderer* r); /* render_start() + render_wait() */

@@ -114,6 +114,7 @@ typedef struct {
 	const ssb_color* color;
 	const ssb_options* opt;
 	float lambda_step;  /* LAMBDA_STEP, stdafx.hpp:289 */
+	int nw;             /* SAMPLE_WAVELENGTHS (stdafx.hpp:90): channels nw..3 of a `hero` stay 0 (glm::vec<nw,float>) */
 	uint32_t nlights;
 	uint32_t lights[SSB_MAX_LIGHTS]; /* Scene::lights, scene.cpp:27-29 */
 	ssb_oracle_counters* counters;
@@ -143,8 +144,8 @@ static float spectrum_sample_nearest(const ssb_spectrum* s, float lambda) { /* s
 	return 0.0f;
 }
 static hero spectrum_hero(const octx* c, const ssb_spectrum* s, float lambda_0) { /* spectrum.cpp:61-67 */
-	hero result;
-	for (int i = 0; i < 4; ++i) {
+	hero result = { { 0.0f, 0.0f, 0.0f, 0.0f } };
+	for (int i = 0; i < c->nw; ++i) {
 		float lambda = lambda_0 + (float)i * c->lambda_step;
 		result.v[i] = (s->filter == SSB_FILTER_NEAREST) ? spectrum_sample_nearest(s, lambda)
 		                                                : spectrum_sample_linear(s, lambda);
@@ -250,23 +251,23 @@ static float meng_xyz_to_p(const ssb_meng_tables* m, float lambda, const float* 
 
 static hero lrgb_to_specrefl(const octx* c, const float lrgb[3], float lambda_0) {
 	const ssb_color* col = c->color;
-	hero result;
+	hero result = { { 0.0f, 0.0f, 0.0f, 0.0f } };
 	if (c->opt->upsampling == SSB_UPSAMPLE_OURS) { /* color.cpp:166-173 */
 		hero br = spectrum_hero(c, &col->basis_r, lambda_0);
 		hero bg = spectrum_hero(c, &col->basis_g, lambda_0);
 		hero bb = spectrum_hero(c, &col->basis_b, lambda_0);
-		for (int i = 0; i < 4; ++i) result.v[i] = (lrgb[0] * br.v[i] + lrgb[1] * bg.v[i]) + lrgb[2] * bb.v[i];
+		for (int i = 0; i < c->nw; ++i) result.v[i] = (lrgb[0] * br.v[i] + lrgb[1] * bg.v[i]) + lrgb[2] * bb.v[i];
 	} else if (c->opt->upsampling == SSB_UPSAMPLE_JH) { /* color.cpp:202-232 */
 		float coeffs[3];
 		jh_fetch(col, lrgb, coeffs);
-		for (int i = 0; i < 4; ++i) result.v[i] = jh_eval_precise(coeffs, lambda_0 + (float)i * c->lambda_step);
+		for (int i = 0; i < c->nw; ++i) result.v[i] = jh_eval_precise(coeffs, lambda_0 + (float)i * c->lambda_step);
 	} else { /* MENG, color.cpp:174-201: xyz_rel = transpose(M) * 100 * lrgb */
 		static const float M[9] = { 0.41231515f, 0.3576f, 0.1805f, 0.2126f, 0.7152f, 0.0722f, 0.01932727f, 0.1192f, 0.95063333f };
 		/* glm::transpose(mat3(9 scalars column-major)) * 100.0f: element (row r, col k) = M[r*3+k]*100 */
 		float xyz_rel[3];
 		for (int r = 0; r < 3; ++r)
 			xyz_rel[r] = ((M[r * 3 + 0] * 100.0f) * lrgb[0] + (M[r * 3 + 1] * 100.0f) * lrgb[1]) + (M[r * 3 + 2] * 100.0f) * lrgb[2];
-		for (int i = 0; i < 4; ++i) result.v[i] = meng_xyz_to_p(col->meng, lambda_0 + (float)i * c->lambda_step, xyz_rel);
+		for (int i = 0; i < c->nw; ++i) result.v[i] = meng_xyz_to_p(col->meng, lambda_0 + (float)i * c->lambda_step, xyz_rel);
 	}
 	return result;
 }
@@ -306,7 +307,7 @@ static void specradflux_to_ciexyz(const octx* c, hero flux, float lambda_0, floa
 	for (int k = 0; k < 3; ++k) {
 		hero v = hero_scale(hero_mul(spectrum_hero(c, obs[k], lambda_0), flux), c->lambda_step);
 		float acc = 0.0f;
-		for (int i = 0; i < 4; ++i) acc += v.v[i];
+		for (int i = 0; i < c->nw; ++i) acc += v.v[i];
 		xyz[k] = acc;
 	}
 }
@@ -651,7 +652,9 @@ static int prepare(octx* c, const ssb_scene* scene, const ssb_color* color, cons
 	if (opt->width == 0 || opt->height == 0 || opt->spp == 0) return SSB_ERR_ARG;
 	if (opt->render_mode != SSB_RENDER_RGB && (opt->upsampling < SSB_UPSAMPLE_OURS || opt->upsampling > SSB_UPSAMPLE_JH)) return SSB_ERR_UNSUPPORTED;
 	c->scene = scene; c->color = color; c->opt = opt;
-	c->lambda_step = (opt->lambda_max - opt->lambda_min) / (float)4; /* stdafx.hpp:289 */
+	c->nw = opt->n_wavelengths ? (int)opt->n_wavelengths : 4;
+	if (c->nw < 2 || c->nw > 4) return SSB_ERR_UNSUPPORTED; /* glm::vec<N,float>: the reference compiles for N = 2, 3, 4 */
+	c->lambda_step = (opt->lambda_max - opt->lambda_min) / (float)c->nw; /* stdafx.hpp:289 */
 	for (uint32_t q = 0; q < scene->nquads; ++q)
 		if (scene->quads[q].is_light) { if (c->nlights >= SSB_MAX_LIGHTS) return SSB_ERR_UNSUPPORTED; c->lights[c->nlights++] = q; }
 	if (opt->explicit_light_sampling && c->nlights == 0) return SSB_ERR_ARG; /* assert(!lights.empty()), scene.cpp:30 */

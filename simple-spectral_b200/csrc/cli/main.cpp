@@ -24,6 +24,7 @@ void print_usage() {
 		"  Optional arguments:\n"
 		"    --indirect-only/-io\n"
 		"    --variant=ours1931|ours2006|meng|jh|rgb   (the reference's compile-time modes)\n"
+		"    --wavelengths=2|3|4                       (SAMPLE_WAVELENGTHS, default 4)\n"
 		"    --seed=<n>  --device=<n>  --data-root=<dir containing data/>\n");
 }
 
@@ -86,6 +87,11 @@ int main(int argc, char* argv[]) {
 			else if (v == "jh") { o.observer = 1931; o.upsampling = SSB_UPSAMPLE_JH; }
 			else if (v == "rgb") { o.render_mode = SSB_RENDER_RGB; }  // the reference's RENDER_MODE_RGB build
 			else { std::fprintf(stderr, "Unknown variant \"%s\"\n", v.c_str()); throw -3; }
+		} catch (int code) { if (code != -2) throw; }
+		try {  // SAMPLE_WAVELENGTHS (stdafx.hpp:90)
+			int n = std::atoi(a.get("--wavelengths", "--wavelengths").c_str());
+			if (n < 2 || n > 4) { std::fprintf(stderr, "Invalid number of wavelengths (2, 3 or 4)!\n"); throw -1; }
+			o.n_wavelengths = static_cast<uint32_t>(n);
 		} catch (int code) { if (code != -2) throw; }
 		try { o.seed = std::strtoull(a.get("--seed", "--seed").c_str(), nullptr, 10); } catch (int code) { if (code != -2) throw; }
 		try { o.device = std::atoi(a.get("--device", "--device").c_str()); } catch (int code) { if (code != -2) throw; }

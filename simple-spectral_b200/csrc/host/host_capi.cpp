@@ -109,6 +109,7 @@ int ssbh_renderer_new(const ssbh_renderer_options* o, ssbh_renderer** out) {
 		r.max_depth = o->max_depth; r.flat_field_correction = o->flat_field_correction != 0;
 		r.seed = o->seed; r.device = o->device;
 		r.render_mode = o->render_mode;
+		r.n_wavelengths = o->n_wavelengths ? o->n_wavelengths : 4u;
 		r.data_root = o->data_root ? o->data_root : ".";
 		*out = new ssbh_renderer{ new Renderer(r) };
 	});

@@ -39,6 +39,7 @@ ssb_options Renderer::make_options() const {
 	o.explicit_light_sampling = options.explicit_light_sampling ? 1u : 0u;
 	o.flat_field_correction = options.flat_field_correction ? 1u : 0u;
 	o.render_mode = options.render_mode;
+	o.n_wavelengths = options.n_wavelengths;
 	o.seed = options.seed;
 	return o;
 }

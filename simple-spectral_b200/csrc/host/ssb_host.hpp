@@ -136,6 +136,7 @@ struct RendererOptions {
 	uint32_t max_depth = 10;
 	bool flat_field_correction = true;
 	uint32_t render_mode = SSB_RENDER_SPECTRAL;  // SSB_RENDER_RGB = the RENDER_MODE_RGB build
+	uint32_t n_wavelengths = 4;                  // SAMPLE_WAVELENGTHS (stdafx.hpp:90): 2, 3 or 4
 	uint64_t seed = 1;
 	int device = 0;
 	std::string data_root = ".";

@@ -289,6 +289,8 @@ int validate_options(const ssb_options* o, uint32_t& x1, uint32_t& y1, uint32_t&
 	if (!rgb && (o->upsampling < SSB_UPSAMPLE_OURS || o->upsampling > SSB_UPSAMPLE_JH)) return fail(SSB_ERR_UNSUPPORTED, "unknown upsampling mode %u", o->upsampling);
 	if (o->max_depth == 0 || o->max_depth > SSB_MAX_DEPTH) return fail(SSB_ERR_UNSUPPORTED, "max_depth must be in [1,%u]", SSB_MAX_DEPTH);
 	if (!rgb && !(o->lambda_max > o->lambda_min)) return fail(SSB_ERR_ARG, "lambda_max must exceed lambda_min");
+	if (o->n_wavelengths != 0 && (o->n_wavelengths < 2 || o->n_wavelengths > 4))  // glm::vec<N,float> of the reference: N = 2, 3, 4
+		return fail(SSB_ERR_UNSUPPORTED, "n_wavelengths must be 0 (= 4), 2, 3 or 4");
 	return SSB_OK;
 }
 
@@ -557,7 +559,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.els = o->explicit_light_sampling; P.flat_field = o->flat_field_correction;
 	P.render_mode = o->render_mode;
 	P.eps = o->eps; P.lambda_min = o->lambda_min;
-	P.lambda_step = (o->lambda_max - o->lambda_min) / (float)4;  // LAMBDA_STEP (stdafx.hpp:289)
+	P.n_wavelengths = o->n_wavelengths ? o->n_wavelengths : 4u;  // SAMPLE_WAVELENGTHS (stdafx.hpp:90)
+	P.lambda_step = (o->lambda_max - o->lambda_min) / (float)P.n_wavelengths;  // LAMBDA_STEP (stdafx.hpp:289)
 	P.seed = o->seed;
 	memcpy(P.pv_inv, c->camera.pv_inv, sizeof(P.pv_inv));
 	memcpy(P.cam_pos, c->camera.pos, sizeof(P.cam_pos));

@@ -94,6 +94,7 @@ struct KParams {
 	uint32_t width, height, x0, y0, rect_w, rect_h, sample_begin, nsamp;
 	uint32_t indirect_only, upsampling, max_depth, els, flat_field;
 	uint32_t render_mode;  // SSB_RENDER_SPECTRAL / SSB_RENDER_RGB
+	uint32_t n_wavelengths;  // SAMPLE_WAVELENGTHS (2..4): channels >= n of every Hero are exactly 0
 	uint32_t depth;     // depth processed by this launch
 	float eps, lambda_min, lambda_step;
 	unsigned long long seed;
@@ -215,17 +216,19 @@ __device__ __forceinline__ float spec_sample(const float* pool, const DevSpectru
 	return val0 * (1.0f - frac) + val1 * frac;
 }
 // _Spectrum::operator[] (spectrum.cpp:61-67)
-__device__ __noinline__ float4 spec_hero4(DevSpectrum s, float lambda_0, float step) {
+// (HeroSample = glm::vec<SAMPLE_WAVELENGTHS,float>: with nw < 4 the unused channels are held at exactly 0, which every
+// later per-channel operation and the pairwise dot product preserve)
+__device__ __noinline__ float4 spec_hero4(DevSpectrum s, float lambda_0, float step, uint32_t nw) {
 	const float* pool = SceneView().pool();
 	float4 h;
 	h.x = spec_sample(pool, s, lambda_0 + 0.0f * step);
 	h.y = spec_sample(pool, s, lambda_0 + 1.0f * step);
-	h.z = spec_sample(pool, s, lambda_0 + 2.0f * step);
-	h.w = spec_sample(pool, s, lambda_0 + 3.0f * step);
+	h.z = nw > 2u ? spec_sample(pool, s, lambda_0 + 2.0f * step) : 0.0f;
+	h.w = nw > 3u ? spec_sample(pool, s, lambda_0 + 3.0f * step) : 0.0f;
 	return h;
 }
-__device__ __forceinline__ Hero spec_hero(const float*, const DevSpectrum& s, float lambda_0, float step) {
-	float4 v = spec_hero4(s, lambda_0, step);
+__device__ __forceinline__ Hero spec_hero(const KParams& P, const DevSpectrum& s, float lambda_0, float step) {
+	float4 v = spec_hero4(s, lambda_0, step, P.n_wavelengths);
 	Hero h;
 	h.v[0] = v.x; h.v[1] = v.y; h.v[2] = v.z; h.v[3] = v.w;
 	return h;
@@ -269,7 +272,7 @@ __device__ __noinline__ Hero jh_upsample(const KParams& P, float r, float g, flo
 		float lambda = lambda_0 + (float)k * P.lambda_step;
 		float xx = (coeff[0] * lambda + coeff[1]) * lambda + coeff[2];
 		float yy = 1.f / sqrtf(xx * xx + 1.f);
-		h.v[k] = (.5f * xx) * yy + .5f;
+		h.v[k] = (uint32_t)k < P.n_wavelengths ? (.5f * xx) * yy + .5f : 0.0f;
 	}
 	return h;
 }
@@ -331,7 +334,8 @@ __device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, f
 	for (int rr = 0; rr < 3; ++rr)
 		xyz_rel[rr] = ((M[rr * 3 + 0] * 100.0f) * r + (M[rr * 3 + 1] * 100.0f) * g) + (M[rr * 3 + 2] * 100.0f) * b;
 	Hero h;
-	for (int k = 0; k < 4; ++k) h.v[k] = meng_xyz_to_p(P, lambda_0 + (float)k * P.lambda_step, xyz_rel);
+	for (int k = 0; k < 4; ++k)  // (wavelengths past the last channel may lie outside the tables: not evaluated)
+		h.v[k] = (uint32_t)k < P.n_wavelengths ? meng_xyz_to_p(P, lambda_0 + (float)k * P.lambda_step, xyz_rel) : 0.0f;
 	return h;
 }
 
@@ -347,7 +351,7 @@ __device__ __forceinline__ Hero material_emission(const KParams& P, const SceneV
 		Hero h; h.v[0] = m.emission_rgb[0]; h.v[1] = m.emission_rgb[1]; h.v[2] = m.emission_rgb[2]; h.v[3] = 0.0f;
 		return h;
 	}
-	return spec_hero(S.pool(), m.emission, lambda_0, P.lambda_step);
+	return spec_hero(P, m.emission, lambda_0, P.lambda_step);
 }
 
 // material albedo at (st, lambda_0): constant spectrum or sRGB texture + upsampling
@@ -360,7 +364,7 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 			Hero h; h.v[0] = m.albedo_rgb[0]; h.v[1] = m.albedo_rgb[1]; h.v[2] = m.albedo_rgb[2]; h.v[3] = 0.0f;
 			return h;
 		}
-		return spec_hero(S.pool(), m.albedo, lambda_0, P.lambda_step);
+		return spec_hero(P, m.albedo, lambda_0, P.lambda_step);
 	}
 	const DevTexture tex = S.textures()[m.texture];
 	float index_x = st_x * (float)tex.width;
@@ -374,9 +378,9 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 		Hero h; h.v[0] = r; h.v[1] = g; h.v[2] = b; h.v[3] = 0.0f;
 		return h;
 	} else if (UPS == SSB_UPSAMPLE_OURS) {
-		Hero br = spec_hero(S.pool(), S.hdr()->basis_r, lambda_0, P.lambda_step);
-		Hero bg = spec_hero(S.pool(), S.hdr()->basis_g, lambda_0, P.lambda_step);
-		Hero bb = spec_hero(S.pool(), S.hdr()->basis_b, lambda_0, P.lambda_step);
+		Hero br = spec_hero(P, S.hdr()->basis_r, lambda_0, P.lambda_step);
+		Hero bg = spec_hero(P, S.hdr()->basis_g, lambda_0, P.lambda_step);
+		Hero bb = spec_hero(P, S.hdr()->basis_b, lambda_0, P.lambda_step);
 		Hero h;
 #pragma unroll
 		for (int k = 0; k < 4; ++k) h.v[k] = (r * br.v[k] + g * bg.v[k]) + b * bb.v[k];

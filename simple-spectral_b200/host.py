@@ -14,7 +14,7 @@ class ssbh_renderer_options(C.Structure):
                 ("indirect_only", C.c_uint32), ("output_path", C.c_char_p), ("observer", C.c_int),
                 ("upsampling", C.c_uint32), ("explicit_light_sampling", C.c_uint32), ("max_depth", C.c_uint32),
                 ("flat_field_correction", C.c_uint32), ("seed", C.c_uint64), ("device", C.c_int),
-                ("data_root", C.c_char_p), ("render_mode", C.c_uint32)]
+                ("data_root", C.c_char_p), ("render_mode", C.c_uint32), ("n_wavelengths", C.c_uint32)]
 
 
 HOST_SYMBOLS = (
@@ -182,12 +182,13 @@ class Renderer:
     """Renderer(options): same knobs as the reference's CLI + its compile-time macros; render() = render_start()+render_wait()."""
 
     def __init__(self, scene_name, width, height, spp, output_path=None, indirect_only=False, variant="ours1931",
-                 explicit_light_sampling=True, max_depth=10, flat_field_correction=True, seed=1, device=0, data_root=None):
+                 explicit_light_sampling=True, max_depth=10, flat_field_correction=True, seed=1, device=0, data_root=None,
+                 n_wavelengths=4):
         obs, ups = VARIANTS[variant]
         self._keep = (scene_name.encode(), output_path.encode() if output_path else None, (data_root or find_data_root()).encode())
         o = ssbh_renderer_options(self._keep[0], width, height, spp, int(indirect_only), self._keep[1], obs, ups,
                                   int(explicit_light_sampling), max_depth, int(flat_field_correction), seed, device, self._keep[2],
-                                  _abi.SSB_RENDER_RGB if variant == "rgb" else _abi.SSB_RENDER_SPECTRAL)
+                                  _abi.SSB_RENDER_RGB if variant == "rgb" else _abi.SSB_RENDER_SPECTRAL, n_wavelengths)
         self._h = C.c_void_p()
         self.width, self.height = width, height
         _check(hostlib().ssbh_renderer_new(C.byref(o), C.byref(self._h)))

@@ -21,6 +21,9 @@ VARIANT_OPTS = {  # compile-time variants of the reference (stdafx.hpp:66,81) as
     "meng": dict(upsampling=abi.SSB_UPSAMPLE_MENG, lambda_min=380.0, lambda_max=780.0),
     "ours1931_noels": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, explicit_light_sampling=0),
     "rgb": dict(render_mode=abi.SSB_RENDER_RGB),  # RENDER_MODE_RGB (stdafx.hpp:62-90)
+    # SAMPLE_WAVELENGTHS 3 / 2 (stdafx.hpp:90)
+    "ours1931_nw3": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, n_wavelengths=3),
+    "meng_nw2": dict(upsampling=abi.SSB_UPSAMPLE_MENG, lambda_min=380.0, lambda_max=780.0, n_wavelengths=2),
 }
 
 
@@ -103,7 +106,7 @@ def meng_tables():
 
 
 def needs_assets(scene, variant):
-    return scene != "cornell" or variant in ("jh", "meng")
+    return scene != "cornell" or variant in ("jh", "meng", "meng_nw2")
 
 
 def have_assets():
@@ -115,7 +118,7 @@ def load_flat(scene, variant):
     t = refdump.parse(os.path.join(GOLDEN, f"tables_{scene}_{variant}.bin"))
     tex = lizard_texture() if scene != "cornell" else None
     jh = jh_tables() if variant == "jh" else None
-    meng = meng_tables() if variant == "meng" else None
+    meng = meng_tables() if variant.startswith("meng") else None
     return refdump.flat_from_dump(t, tex, jh=jh, meng=meng)
 
 

@@ -13,7 +13,8 @@ CASES = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("plane-srgb", "
          ("cornell", "ours2006"), ("cornell-srgb", "ours2006"),
          ("cornell-srgb", "jh"), ("plane-srgb", "jh"), ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
          ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels"),
-         ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb")]  # RENDER_MODE_RGB build of the reference
+         ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb"),  # RENDER_MODE_RGB build of the reference
+         ("cornell-srgb", "ours1931_nw3"), ("plane-srgb", "ours1931_nw3"), ("cornell-srgb", "meng_nw2")]  # SAMPLE_WAVELENGTHS 3 / 2
 
 
 def _skip_if_no_assets(scene, variant):
@@ -106,6 +107,17 @@ def test_gpu_spectral_scene_needs_spectra():
         with pytest.raises(ssb.SsbError) as e:
             ctx.render(pu.options("ours1931", 16, 16, 1))
         assert e.value.code == -2
+
+
+def test_gpu_rejects_unsupported_wavelength_counts():
+    import importlib
+    ssb = importlib.import_module("simple-spectral_b200")
+    flat = pu.load_flat("cornell", "ours1931")
+    with pu.gpu_context(flat) as ctx:
+        for n in (1, 5):
+            with pytest.raises(ssb.SsbError) as e:
+                ctx.render(pu.options("ours1931", 16, 16, 1, n_wavelengths=n))
+            assert e.value.code == -3
 
 
 def test_gpu_subsets_compose():
