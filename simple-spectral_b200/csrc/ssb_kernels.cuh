@@ -216,19 +216,27 @@ __device__ __forceinline__ float spec_sample(const float* pool, const DevSpectru
 	return val0 * (1.0f - frac) + val1 * frac;
 }
 // _Spectrum::operator[] (spectrum.cpp:61-67)
-// (HeroSample = glm::vec<SAMPLE_WAVELENGTHS,float>: with nw < 4 the unused channels are held at exactly 0, which every
-// later per-channel operation and the pairwise dot product preserve)
-__device__ __noinline__ float4 spec_hero4(DevSpectrum s, float lambda_0, float step, uint32_t nw) {
+__device__ __noinline__ float4 spec_hero4(DevSpectrum s, float lambda_0, float step) {
 	const float* pool = SceneView().pool();
 	float4 h;
 	h.x = spec_sample(pool, s, lambda_0 + 0.0f * step);
 	h.y = spec_sample(pool, s, lambda_0 + 1.0f * step);
-	h.z = nw > 2u ? spec_sample(pool, s, lambda_0 + 2.0f * step) : 0.0f;
-	h.w = nw > 3u ? spec_sample(pool, s, lambda_0 + 3.0f * step) : 0.0f;
+	h.z = spec_sample(pool, s, lambda_0 + 2.0f * step);
+	h.w = spec_sample(pool, s, lambda_0 + 3.0f * step);
 	return h;
 }
+// HeroSample = glm::vec<SAMPLE_WAVELENGTHS,float>: with fewer than 4 wavelengths the unused channels are held at exactly
+// 0 (which every later per-channel operation and the pairwise dot product preserve).  spec_sample is bounds-checked,
+// so sampling the unused wavelengths is harmless; they are cleared where a Hero enters the path state.  The test is
+// uniform and false in the default configuration.
+__device__ __forceinline__ void hero_clear_unused(const KParams& P, Hero& h) {
+	if (P.n_wavelengths != 4u) {
+		if (P.n_wavelengths < 3u) h.v[2] = 0.0f;
+		h.v[3] = 0.0f;
+	}
+}
 __device__ __forceinline__ Hero spec_hero(const KParams& P, const DevSpectrum& s, float lambda_0, float step) {
-	float4 v = spec_hero4(s, lambda_0, step, P.n_wavelengths);
+	float4 v = spec_hero4(s, lambda_0, step);
 	Hero h;
 	h.v[0] = v.x; h.v[1] = v.y; h.v[2] = v.z; h.v[3] = v.w;
 	return h;
@@ -351,7 +359,9 @@ __device__ __forceinline__ Hero material_emission(const KParams& P, const SceneV
 		Hero h; h.v[0] = m.emission_rgb[0]; h.v[1] = m.emission_rgb[1]; h.v[2] = m.emission_rgb[2]; h.v[3] = 0.0f;
 		return h;
 	}
-	return spec_hero(P, m.emission, lambda_0, P.lambda_step);
+	Hero h = spec_hero(P, m.emission, lambda_0, P.lambda_step);
+	hero_clear_unused(P, h);
+	return h;
 }
 
 // material albedo at (st, lambda_0): constant spectrum or sRGB texture + upsampling
@@ -364,7 +374,9 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 			Hero h; h.v[0] = m.albedo_rgb[0]; h.v[1] = m.albedo_rgb[1]; h.v[2] = m.albedo_rgb[2]; h.v[3] = 0.0f;
 			return h;
 		}
-		return spec_hero(P, m.albedo, lambda_0, P.lambda_step);
+		Hero h = spec_hero(P, m.albedo, lambda_0, P.lambda_step);
+		hero_clear_unused(P, h);
+		return h;
 	}
 	const DevTexture tex = S.textures()[m.texture];
 	float index_x = st_x * (float)tex.width;
@@ -384,6 +396,7 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 		Hero h;
 #pragma unroll
 		for (int k = 0; k < 4; ++k) h.v[k] = (r * br.v[k] + g * bg.v[k]) + b * bb.v[k];
+		hero_clear_unused(P, h);
 		return h;
 	} else if (UPS == SSB_UPSAMPLE_JH) {
 		return jh_upsample(P, r, g, b, lambda_0);
