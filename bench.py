@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mpath-samples/s"
+JSON_OUT = None  # where the one JSON line goes (stdout unless main_ours redirected fd 1, see there)
 SCENE, VARIANT = "cornell-srgb", "ours1931"
 # SURVEY.md §8(d) algorithmic HBM bytes per path sample (wavefront model the north star names):
 # 5.30 closest-hit stages x 192 B ray state read+write + 47 B texture sectors + 32 B f64 XYZA output
@@ -171,7 +172,13 @@ def main_ours(args, rank, local_rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL writes its version banner (and anything NCCL_DEBUG asks for) to
+        # fd 1 from native code, so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor
+        global JSON_OUT
+        sys.stdout.flush()
+        _json_fd = os.dup(1)
+        os.dup2(2, 1)
+        JSON_OUT = os.fdopen(_json_fd, "w")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     W, H, SPP = args.width, args.height, args.spp
@@ -340,7 +347,7 @@ def main_ours(args, rank, local_rank, world):
                 line["cpu_baseline"] = cpu_baseline(W, H, args.cpu_spp)
             except SystemExit as e:
                 line["cpu_baseline"] = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT or sys.stdout, flush=True)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -359,7 +366,7 @@ def main():
     ap.add_argument("--height", type=int, default=512)
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded CPU-baseline sample")
-    ap.add_argument("--ref-spp", type=int, default=4, help="spp per step of the reference arm")
+    ap.add_argument("--ref-spp", type=int, default=16, help="spp per step of the reference arm (same bounded sample as cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scene", default=SCENE, choices=sorted(ALGO_BYTES_PER_SAMPLE),
                     help="default = BASELINE configs[1]; the others are SURVEY 8(d) C3-C5 (not the headline)")
