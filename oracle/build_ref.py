@@ -10,7 +10,7 @@ unpinned dependency (cmake/FindGLM.cmake) and is not installed.  We compile agai
 oracle/glm_shim (our restatement of GLM 0.9.9 scalar semantics for the ~20 functions
 the reference uses).  The reference's CMake build is NOT run.
 
-Outputs (per variant v in ours1931, ours2006, meng, jh, ours1931_noels, rgb, ours1931_nw3, meng_nw2):
+Outputs (per variant v in ours1931, ours2006, meng, jh, ours1931_noels, rgb, ours1931_nw3, meng_nw2, ours1931_d3):
   oracle/_ref/simple_spectral_<v>          pristine sources, -O3 -march=x86-64-v3 -DNDEBUG
                                             (CPU timing arm; multi-threaded, nondeterministic)
   oracle/_ref/simple_spectral_<v>_hooked   sources + oracle/ref_hooks.hpp spliced into
@@ -47,6 +47,8 @@ VARIANTS = {
     # SAMPLE_WAVELENGTHS (stdafx.hpp:90) other than 4: glm::vec<N,float> exists for N = 2, 3 (not 1 without extra headers)
     "ours1931_nw3": dict(alg=1, observer=1931, nw=3),
     "meng_nw2": dict(alg=2, observer=1931, nw=2),
+    # MAX_DEPTH (stdafx.hpp:47) 3 instead of 10
+    "ours1931_d3": dict(alg=1, observer=1931, max_depth=3),
 }
 CXX_SOURCES = [
     "main.cpp", "renderer.cpp", "scene.cpp", "geometry.cpp", "material.cpp", "spectrum.cpp",
@@ -74,13 +76,15 @@ def sub_once(text, pattern, repl, what):
     return new
 
 
-def patch_variant(src_dir, alg, observer, no_els=False, no_ffc=False, rgb=False, nw=4):
+def patch_variant(src_dir, alg, observer, no_els=False, no_ffc=False, rgb=False, nw=4, max_depth=10):
     p = os.path.join(src_dir, "stdafx.hpp")
     t = open(p, encoding="utf-8-sig").read()
     if no_els:
         t = sub_once(t, r"^#define EXPLICIT_LIGHT_SAMPLING$", "//#define EXPLICIT_LIGHT_SAMPLING", "ELS")
     if no_ffc:
         t = sub_once(t, r"^#define FLAT_FIELD_CORRECTION$", "//#define FLAT_FIELD_CORRECTION", "FFC")
+    if max_depth != 10:
+        t = sub_once(t, r"#define MAX_DEPTH 10u", f"#define MAX_DEPTH {max_depth}u", "MAX_DEPTH")
     if nw != 4:
         t = sub_once(t, r"#define SAMPLE_WAVELENGTHS 4_zu", f"#define SAMPLE_WAVELENGTHS {nw}_zu", "SAMPLE_WAVELENGTHS")
     if rgb:
@@ -170,7 +174,7 @@ def main():
             for name in which:
                 v = VARIANTS[name]
                 for hooked in (False, True):
-                    kw = {k: v[k] for k in ("no_els", "no_ffc", "rgb", "nw") if k in v}
+                    kw = {k: v[k] for k in ("no_els", "no_ffc", "rgb", "nw", "max_depth") if k in v}
                     jobs.append(ex.submit(build_one, tmp, name, v["alg"], v["observer"], hooked, lodepng_obj, **kw))
             for j in jobs:
                 print("built", os.path.relpath(j.result(), os.path.dirname(HERE)))

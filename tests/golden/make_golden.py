@@ -33,6 +33,7 @@ CASES = [  # (scene, variant)
     ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb"),
     # SAMPLE_WAVELENGTHS 3 (OURS) and 2 (Meng)
     ("cornell-srgb", "ours1931_nw3"), ("plane-srgb", "ours1931_nw3"), ("cornell-srgb", "meng_nw2"),
+    ("cornell-srgb", "ours1931_d3"),  # MAX_DEPTH 3
 ]
 SMALL = dict(w=32, h=24, spp=4, seed=7)
 C1 = dict(w=128, h=128, spp=16, seed=1)  # BASELINE.json configs[0]

@@ -24,6 +24,7 @@ VARIANT_OPTS = {  # compile-time variants of the reference (stdafx.hpp:66,81) as
     # SAMPLE_WAVELENGTHS 3 / 2 (stdafx.hpp:90)
     "ours1931_nw3": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, n_wavelengths=3),
     "meng_nw2": dict(upsampling=abi.SSB_UPSAMPLE_MENG, lambda_min=380.0, lambda_max=780.0, n_wavelengths=2),
+    "ours1931_d3": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, max_depth=3),  # MAX_DEPTH 3
 }
 
 

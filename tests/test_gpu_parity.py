@@ -14,7 +14,8 @@ CASES = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("plane-srgb", "
          ("cornell-srgb", "jh"), ("plane-srgb", "jh"), ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
          ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels"),
          ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb"),  # RENDER_MODE_RGB build of the reference
-         ("cornell-srgb", "ours1931_nw3"), ("plane-srgb", "ours1931_nw3"), ("cornell-srgb", "meng_nw2")]  # SAMPLE_WAVELENGTHS 3 / 2
+         ("cornell-srgb", "ours1931_nw3"), ("plane-srgb", "ours1931_nw3"), ("cornell-srgb", "meng_nw2"),  # SAMPLE_WAVELENGTHS 3 / 2
+         ("cornell-srgb", "ours1931_d3")]  # MAX_DEPTH 3
 
 
 def _skip_if_no_assets(scene, variant):
