@@ -34,6 +34,7 @@ SCENE, VARIANT = "cornell-srgb", "ours1931"
 # SURVEY.md §8(d) algorithmic HBM bytes per path sample (wavefront model the north star names):
 # 5.30 closest-hit stages x 192 B ray state read+write + 47 B texture sectors + 32 B f64 XYZA output
 ALGO_BYTES_PER_SAMPLE = {"cornell-srgb": 5.30 * 192 + 47 + 32, "cornell": 5.30 * 192 + 32, "plane-srgb": 2.0 * 192 + 64 + 32}
+JH_EXTRA_BYTES_PER_SAMPLE = {"cornell-srgb": 375.0, "cornell": 0.0, "plane-srgb": 512.0}  # 8 coefficient sectors per textured lookup
 
 
 def measured_peaks():
@@ -312,15 +313,27 @@ def main_ours(args, rank, local_rank, world):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        algo_bytes = ALGO_BYTES_PER_SAMPLE[SCENE] * npix * SPP  # per trace-kernel launch (one rank's launch)
+        algo_per_sample = ALGO_BYTES_PER_SAMPLE[SCENE] + (JH_EXTRA_BYTES_PER_SAMPLE[SCENE] if VARIANT == "jh" else 0.0)
+        algo_bytes = algo_per_sample * npix * SPP  # per trace-kernel launch (one rank's launch)
         achieved = algo_bytes / (trace_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, issue = None, None
         tp = os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")
-        if os.path.exists(tp):
+        headline = (SCENE, VARIANT, W, H, SPP) == ("cornell-srgb", "ours1931", 512, 512, 64)  # what the ncu capture ran
+        if os.path.exists(tp) and headline:
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                prof = json.load(open(tp))
+                traffic = prof.get("dram_bytes_per_launch")
+                wi, ti = prof.get("warp_instructions_per_frame"), prof.get("thread_instructions_per_frame")
+                if wi and clocks.get("sm_mhz"):
+                    # the bound that actually binds (SURVEY 8(d) "FP32-issue bound"): warp instructions of one frame (ncu
+                    # smsp__inst_executed.sum over its launches, profiles/) against the SMs' issue slots during the measured step
+                    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                    slots = sms * 4 * clocks["sm_mhz"] * 1e6 * (dev_ms / args.steps) * 1e-3
+                    issue = {"warp_instructions_per_frame": wi, "thread_instructions_per_sample": ti / (npix * SPP),
+                             "lanes_per_instruction": ti / wi, "issue_slots_per_frame": slots, "frac": wi / slots,
+                             "note": "fraction of all warp-issue slots (SMs x 4 schedulers x SM clock x step time) used by the frame's instructions"}
             except Exception:
-                traffic = None
+                traffic, issue = None, None
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -338,7 +351,7 @@ def main_ours(args, rank, local_rank, world):
                          "peak_source": peak_src,
                          "kernel": "bounce stage = ssb_intersect_kernel + counting sort + ssb_shade_kernel over all path depths of one frame "
                                    "(CUDA events around the launch sequence)", "kernel_ms": trace_ms,
-                         "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE[SCENE],
+                         "algorithmic_bytes_per_sample": algo_per_sample, "issue": issue,
                          "note": "achieved = SURVEY.md 8(d) algorithmic bytes (wavefront ray-state model) / bounce-stage time; traffic = ncu dram bytes of the "
                                  "same launches (profiles/). The stage is instruction-issue bound (un-fused fp32 + f64 exact libm), DRAM ~20-30 % busy: see DESIGN.md (d)"},
         }

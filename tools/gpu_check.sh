@@ -11,7 +11,7 @@ tail -5 $OUT/${TAG}_pytest.txt
 timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
 cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
 if [ "${2:-}" != "noprof" ]; then
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1; echo "ncu launches rc=$?"
 # one whole frame of bounce launches (depths 0..8) + its finalize, after two warm frames
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"ssb_intersect|ssb_shade|ssb_bin|ssb_finalize" -s 78 -c 4 -f -o $OUT/${TAG}_trace \

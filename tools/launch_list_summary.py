@@ -26,16 +26,24 @@ full = [f for f in frames if sum("intersect" in l["name"] for l in f) >= 2]
 if not full:
     print("no complete frame in the list"); sys.exit(1)
 f = full[-1]
-agg = defaultdict(lambda: [0, 0.0, 0.0])
+agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
 for l in f:
     a = agg[l["name"]]
     a[0] += 1; a[1] += l.get("gpu__time_duration.sum", 0.0)
     a[2] += l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0)
+    a[3] += l.get("smsp__inst_executed.sum", 0.0); a[4] += l.get("smsp__thread_inst_executed.sum", 0.0)
 tot_ms = sum(a[1] for a in agg.values()); tot_b = sum(a[2] for a in agg.values())
 print(f"one frame: {len(f)} launches, {tot_ms:.3f} ms (under ncu: serialised, cold caches), {tot_b/1e9:.2f} GB DRAM traffic")
 for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"  {n:45s} x{a[0]:3d}  {a[1]:8.3f} ms  {100*a[1]/tot_ms:5.1f}%   {a[2]/1e9:7.2f} GB")
+tot_wi = sum(a[3] for a in agg.values()); tot_ti = sum(a[4] for a in agg.values())
+if tot_wi:
+    print(f"instructions per frame: {tot_wi/1e9:.3f} G warp-level, {tot_ti/1e9:.2f} G thread-level ({tot_ti/tot_wi:.1f} lanes per instruction)")
+    for n, a in sorted(agg.items(), key=lambda kv: -kv[1][3]):
+        if a[3]:
+            print(f"  {n:45s} {a[3]/1e9:8.3f} G warp-inst  {100*a[3]/tot_wi:5.1f}%   lanes {a[4]/a[3]:5.1f}")
 if len(sys.argv) > 2:
     bounce_b = sum(a[2] for n, a in agg.items() if "finalize" not in n and "resolve" not in n)
     json.dump({"dram_bytes_per_frame": tot_b, "dram_bytes_per_launch": bounce_b, "launches_per_frame": len(f),
+               "warp_instructions_per_frame": tot_wi, "thread_instructions_per_frame": tot_ti,
                "share": {n: a[1] / tot_ms for n, a in agg.items()}}, open(sys.argv[2], "w"), indent=1)
