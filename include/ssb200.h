@@ -186,6 +186,13 @@ void ssb_destroy(ssb_ctx* ctx);
  * MaterialBase* -> _Spectrum that _render_sample walks, renderer.cpp:147-255). */
 int ssb_upload_scene(ssb_ctx* ctx, const ssb_scene* scene);
 int ssb_upload_color(ssb_ctx* ctx, const ssb_color* color);
+/* Same as ssb_upload_scene, but the texel copies are only ENQUEUED (own copy stream): they overlap the camera-ray
+ * stage of the next ssb_render, whose first shading stage waits for them.  The caller's ssb_texture.rgb8 buffers must
+ * stay valid and unmodified until ssb_synchronize returns, or until a host-returning call (ssb_render_frame,
+ * ssb_resolve, ssb_read_accum) that FOLLOWS an ssb_render of this scene returns; use pinned host memory for the copy
+ * to be truly asynchronous.
+ * Everything else (quads, materials, camera) is copied before the call returns, as in ssb_upload_scene. */
+int ssb_upload_scene_async(ssb_ctx* ctx, const ssb_scene* scene);
 
 /* Trace the requested samples and ADD each sample's float4 (X,Y,Z,hit)*0.001f, in sample order,
  * to the context's per-pixel double XYZA accumulator (renderer.cpp:292-295; RGB mode: the float4

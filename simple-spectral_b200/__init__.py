@@ -40,6 +40,7 @@ def lib():
     L.ssb_destroy.argtypes = [C.c_void_p]
     L.ssb_destroy.restype = None
     L.ssb_upload_scene.argtypes = [C.c_void_p, P(_abi.ssb_scene)]
+    L.ssb_upload_scene_async.argtypes = [C.c_void_p, P(_abi.ssb_scene)]
     L.ssb_upload_color.argtypes = [C.c_void_p, P(_abi.ssb_color)]
     L.ssb_render.argtypes = [C.c_void_p, P(_abi.ssb_options)]
     L.ssb_clear.argtypes = [C.c_void_p]
@@ -54,7 +55,7 @@ def lib():
     L.ssb_synchronize.argtypes = [C.c_void_p]
     L.ssb_debug_eval_math.argtypes = [C.c_void_p, C.c_uint32, P(C.c_float), C.c_float, P(C.c_float), C.c_size_t]
     L.ssb_debug_trace_samples.argtypes = [C.c_void_p, P(_abi.ssb_options), C.c_uint32, C.c_uint32, P(C.c_float)]
-    for name in ("ssb_create", "ssb_upload_scene", "ssb_upload_color", "ssb_render", "ssb_clear", "ssb_read_accum",
+    for name in ("ssb_create", "ssb_upload_scene", "ssb_upload_scene_async", "ssb_upload_color", "ssb_render", "ssb_clear", "ssb_read_accum",
                  "ssb_write_accum", "ssb_accum_device", "ssb_resolve", "ssb_resolve_device", "ssb_set_stream",
                  "ssb_render_frame", "ssb_get_stats", "ssb_synchronize", "ssb_debug_eval_math", "ssb_debug_trace_samples"):
         getattr(L, name).restype = C.c_int
@@ -64,7 +65,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_last_error", "ssb_default_options", "ssb_create", "ssb_destroy", "ssb_upload_scene",
-    "ssb_upload_color", "ssb_render", "ssb_clear", "ssb_read_accum", "ssb_write_accum", "ssb_accum_device",
+    "ssb_upload_scene_async", "ssb_upload_color", "ssb_render", "ssb_clear", "ssb_read_accum", "ssb_write_accum", "ssb_accum_device",
     "ssb_resolve", "ssb_resolve_device", "ssb_set_stream", "ssb_render_frame", "ssb_get_stats", "ssb_synchronize", "ssb_debug_eval_math",
     "ssb_debug_trace_samples",
 )
@@ -101,6 +102,11 @@ class Context:
 
     def upload_scene(self, scene):
         check(lib().ssb_upload_scene(self._h, C.byref(scene)))
+
+    def upload_scene_async(self, scene):
+        """Texel copies are only enqueued (they overlap the next render's camera-ray stage): keep the texture buffers
+        alive and unmodified until a synchronising call (render_frame / resolve / synchronize) has returned."""
+        check(lib().ssb_upload_scene_async(self._h, C.byref(scene)))
 
     def upload_color(self, color):
         check(lib().ssb_upload_color(self._h, C.byref(color)))

@@ -76,6 +76,10 @@ struct ssb_ctx {
 	cudaStream_t stream = nullptr;      // the stream every kernel / copy of this context is issued on
 	cudaStream_t own_stream = nullptr;  // created by ssb_create; `stream` may be replaced by ssb_set_stream
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	// ssb_upload_scene_async: texture copies run on their own stream and overlap the first kernels of the next render
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_tex_ready = nullptr, ev_tex_free = nullptr;  // copy finished / last render that read the textures finished
+	bool tex_pending = false, tex_in_use = false;
 	std::vector<cudaEvent_t> ev_pass;   // (t0,t1) pairs around each trace-kernel launch of the last ssb_render
 	uint32_t passes = 0;
 	bool stats_pending = false;
@@ -341,6 +345,9 @@ int ssb_create(int device, ssb_ctx** out) {
 	SSB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
 	SSB_CUDA(cudaEventCreate(&c->ev_begin)); SSB_CUDA(cudaEventCreate(&c->ev_end));
+	SSB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	SSB_CUDA(cudaEventCreateWithFlags(&c->ev_tex_ready, cudaEventDisableTiming));
+	SSB_CUDA(cudaEventCreateWithFlags(&c->ev_tex_free, cudaEventDisableTiming));
 	SSB_CUDA(cudaMalloc(&c->d_counts, kCounterWords * sizeof(uint32_t)));
 	*out = c;
 	return SSB_OK;
@@ -350,6 +357,7 @@ void ssb_destroy(ssb_ctx* c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	free_textures(c);
 	cudaFree(c->d_blob); cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points);
 	cudaFree(c->d_accum); cudaFree(c->d_samples); cudaFree(c->d_counts); cudaFree(c->d_wave); cudaFree(c->d_xyza); cudaFree(c->d_srgba);
@@ -361,7 +369,11 @@ void ssb_destroy(ssb_ctx* c) {
 	delete c;
 }
 
-int ssb_upload_scene(ssb_ctx* c, const ssb_scene* scene) {
+static int upload_scene_impl(ssb_ctx* c, const ssb_scene* scene, bool async);
+int ssb_upload_scene(ssb_ctx* c, const ssb_scene* scene) { return upload_scene_impl(c, scene, false); }
+int ssb_upload_scene_async(ssb_ctx* c, const ssb_scene* scene) { return upload_scene_impl(c, scene, true); }
+
+static int upload_scene_impl(ssb_ctx* c, const ssb_scene* scene, bool async) {
 	if (!c || !scene) return fail(SSB_ERR_ARG, "ssb_upload_scene: NULL argument");
 	if (scene->nquads == 0 || !scene->quads) return fail(SSB_ERR_ARG, "ssb_upload_scene: empty primitive list");
 	if (scene->nquads > SSB_MAX_QUADS) return fail(SSB_ERR_UNSUPPORTED, "ssb_upload_scene: %u quads exceed SSB_MAX_QUADS=%u", scene->nquads, SSB_MAX_QUADS);
@@ -387,8 +399,18 @@ int ssb_upload_scene(ssb_ctx* c, const ssb_scene* scene) {
 		if (scene->quads[q].is_light) lights.push_back(q);  // Scene::_init (scene.cpp:26-29)
 	}
 	if (lights.size() > SSB_MAX_LIGHTS) return fail(SSB_ERR_UNSUPPORTED, "more than %u lights", SSB_MAX_LIGHTS);
-	// textures: RGB8 -> RGBA8 on the device
-	SSB_CUDA(cudaStreamSynchronize(c->stream));
+	// textures: RGB8 -> RGBA8 on the device.  Synchronous form: on the render stream, returns when the caller's buffers
+	// are no longer needed.  Asynchronous form: on the copy stream, ordered after the last render that read the old
+	// texels and before the first shade kernel of the next render (which waits on ev_tex_ready, see ssb_render).
+	cudaStream_t up = c->stream;
+	if (async) {
+		up = c->copy_stream;
+		if (c->tex_in_use) SSB_CUDA(cudaStreamWaitEvent(up, c->ev_tex_free, 0));
+	} else {
+		SSB_CUDA(cudaStreamSynchronize(c->copy_stream));
+		SSB_CUDA(cudaStreamSynchronize(c->stream));
+		c->tex_pending = false;
+	}
 	std::vector<uchar4*> old_tex; old_tex.swap(c->d_textures);
 	std::vector<uint32_t> old_w; old_w.swap(c->tex_w);
 	std::vector<uint32_t> old_h; old_h.swap(c->tex_h);
@@ -406,12 +428,17 @@ int ssb_upload_scene(ssb_ctx* c, const ssb_scene* scene) {
 			c->rgb_staging_capacity = 3 * n;
 		}
 		// one H2D copy of the caller's RGB8 scanlines (fast when the caller's buffer is pinned), repack on the device
-		SSB_CUDA(cudaMemcpyAsync(c->d_rgb_staging, tx.rgb8, 3 * n, cudaMemcpyHostToDevice, c->stream));
-		ssb_repack_rgb8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_rgb_staging, d, n);
+		SSB_CUDA(cudaMemcpyAsync(c->d_rgb_staging, tx.rgb8, 3 * n, cudaMemcpyHostToDevice, up));
+		ssb_repack_rgb8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, up>>>(c->d_rgb_staging, d, n);
 		SSB_CUDA(cudaGetLastError());
 	}
 	for (uchar4* p : old_tex) if (p) cudaFree(p);
-	SSB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's host buffers may be released after return
+	if (async) {
+		SSB_CUDA(cudaEventRecord(c->ev_tex_ready, up));
+		c->tex_pending = scene->ntextures != 0;
+	} else {
+		SSB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's host buffers may be released after return
+	}
 	c->camera = scene->camera;
 	c->quads.assign(scene->quads, scene->quads + scene->nquads);
 	c->materials.swap(mats);
@@ -613,6 +640,10 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			const unsigned grid_s = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_sf : occ_sn), want_s);
 			(d == 0 ? k_isect_first : k_isect_next)<<<grid_i, SSB_INTERSECT_THREADS, smem, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
+			if (c->tex_pending) {  // texels are first read by the shade stage: the camera-ray queries overlap the upload
+				SSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tex_ready, 0));
+				c->tex_pending = false;
+			}
 			ssb_bin_scan_kernel<<<1, 32, 0, c->stream>>>(P, nquads);
 			SSB_CUDA(cudaGetLastError());
 			const unsigned grid_b = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * 8, (P.total_work + 1023) / 1024);
@@ -629,6 +660,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 		launches += 1; passes += 1;
 	}
 	SSB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SSB_CUDA(cudaEventRecord(c->ev_tex_free, c->stream));
+	c->tex_in_use = true;
 	// asynchronous: the event times are read lazily by ssb_get_stats()
 	c->stats.samples = (uint64_t)npix_rect * nsamp_total;
 	c->stats.launches = launches;
@@ -738,6 +771,7 @@ int ssb_get_stats(ssb_ctx* c, ssb_stats* out) {
 int ssb_synchronize(ssb_ctx* c) {
 	if (!c) return fail(SSB_ERR_ARG, "ssb_synchronize: NULL context");
 	SSB_CUDA(cudaSetDevice(c->device));
+	SSB_CUDA(cudaStreamSynchronize(c->copy_stream));  // an ssb_upload_scene_async that no render has consumed yet
 	SSB_CUDA(cudaStreamSynchronize(c->stream));
 	return SSB_OK;
 }

@@ -175,3 +175,30 @@ def test_small_textures(tw, th):
     flat.scene.textures[0].rgb8 = tex.ctypes.data_as(C.POINTER(C.c_uint8))
     flat.scene.textures[0].width, flat.scene.textures[0].height = tw, th
     _compare(flat, pu.options("ours1931", 24, 24, 2, seed=23), pixels=((12, 12),))
+
+
+def test_async_scene_upload_overlaps_and_orders():
+    """ssb_upload_scene_async: the texel copy runs on the copy stream while the camera rays are traced; the result must
+    equal the synchronous upload's, also when the SAME device texture buffer is overwritten between two frames (the copy
+    has to wait for the previous frame's shading) and when the texture size changes."""
+    _need_assets()
+    flat = pu.load_flat("plane-srgb", "ours1931")
+    opt = pu.options("ours1931", 32, 24, 4, seed=29)
+    want1, _ = pu.oracle_resolve(flat, opt, pu.oracle_render(flat, opt)[0])
+    rng = np.random.default_rng(5)
+    tex2 = np.ascontiguousarray(rng.integers(0, 256, (4096, 4096, 3), dtype=np.uint8))  # same size: device buffer is reused
+    tex3 = np.ascontiguousarray(rng.integers(0, 256, (40, 24, 3), dtype=np.uint8))      # other size: reallocated
+    with pu.gpu_context(flat) as ctx:
+        ctx.upload_scene_async(flat.scene)
+        got1, _ = ctx.render_frame(opt)
+        assert pu.bits_equal(got1, want1)
+        for tex in (tex2, tex3):
+            flat.keep.append(tex)
+            flat.scene.textures[0].rgb8 = tex.ctypes.data_as(C.POINTER(C.c_uint8))
+            flat.scene.textures[0].width, flat.scene.textures[0].height = tex.shape[1], tex.shape[0]
+            want, _ = pu.oracle_resolve(flat, opt, pu.oracle_render(flat, opt)[0])
+            ctx.upload_scene_async(flat.scene)
+            got, _ = ctx.render_frame(opt)
+            assert pu.bits_equal(got, want) and not pu.bits_equal(got, want1)
+        ctx.upload_scene_async(flat.scene)
+        ctx.synchronize()  # an upload that no render consumes must still complete here
