@@ -114,7 +114,7 @@ struct ssb_ctx {
 	// wavefront buffers of one pass (see KParams)
 	unsigned char* d_wave = nullptr;
 	size_t wave_bytes = 0;
-	float4* d_samples = nullptr;      // per-sample outputs, only allocated for ssb_debug_trace_samples
+	float4* d_samples = nullptr;      // per-sample (X,Y,Z,hit) of the last pass: alias into d_wave (see ssb_render)
 	size_t samples_capacity = 0;      // in float4
 	bool want_samples = false;
 	uint32_t* d_counts = nullptr;     // queue lengths per depth
@@ -360,7 +360,7 @@ void ssb_destroy(ssb_ctx* c) {
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	free_textures(c);
 	cudaFree(c->d_blob); cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points);
-	cudaFree(c->d_accum); cudaFree(c->d_samples); cudaFree(c->d_counts); cudaFree(c->d_wave); cudaFree(c->d_xyza); cudaFree(c->d_srgba);
+	cudaFree(c->d_accum); cudaFree(c->d_counts); cudaFree(c->d_wave); cudaFree(c->d_xyza); cudaFree(c->d_srgba);
 	cudaFree(c->d_rgb_staging);
 	if (c->ev_begin) cudaEventDestroy(c->ev_begin);
 	if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -556,12 +556,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 		SSB_CUDA(cudaMalloc(&c->d_wave, off));
 		c->wave_bytes = off;
 	}
-	if (c->want_samples && N > c->samples_capacity) {
-		if (c->d_samples) cudaFree(c->d_samples);
-		c->d_samples = nullptr; c->samples_capacity = 0;
-		SSB_CUDA(cudaMalloc(&c->d_samples, N * sizeof(float4)));
-		c->samples_capacity = N;
-	}
+	c->d_samples = reinterpret_cast<float4*>(c->d_wave + o_a0);  // dead ray records of the pass are reused (N x 16 B <= N x 32 B)
+	c->samples_capacity = N;
 
 	KParams P{};
 	P.blob = c->d_blob;
@@ -579,7 +575,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.bin_cursor = c->d_counts + kBinCursorOff;
 	P.hit_q = reinterpret_cast<uint32_t*>(wv + o_hq);
 	P.order = reinterpret_cast<uint32_t*>(wv + o_ord);
-	P.samples = c->want_samples ? c->d_samples : nullptr;
+	P.samples = c->d_samples;
 	P.accum = c->d_accum;
 	P.width = o->width; P.height = o->height; P.x0 = o->x0; P.y0 = o->y0; P.rect_w = rect_w; P.rect_h = rect_h;
 	P.indirect_only = o->indirect_only; P.upsampling = o->upsampling; P.max_depth = o->max_depth;
@@ -654,10 +650,11 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			launches += 4;
 		}
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes + 1], c->stream));
-		const unsigned fgrid = (unsigned)((npix_rect + 127) / 128);
-		ssb_finalize_kernel<<<fgrid, 128, 0, c->stream>>>(P);
+		ssb_fold_kernel<<<(unsigned)((P.total_work + 255) / 256), 256, 0, c->stream>>>(P);
 		SSB_CUDA(cudaGetLastError());
-		launches += 1; passes += 1;
+		ssb_accumulate_kernel<<<(unsigned)((npix_rect + 127) / 128), 128, 0, c->stream>>>(P);
+		SSB_CUDA(cudaGetLastError());
+		launches += 2; passes += 1;
 	}
 	SSB_CUDA(cudaEventRecord(c->ev_end, c->stream));
 	SSB_CUDA(cudaEventRecord(c->ev_tex_free, c->stream));

@@ -88,7 +88,7 @@ struct KParams {
 	uint32_t* bin_count;   // [max_depth][SSB_MAX_QUADS] paths per hit quad
 	uint32_t* bin_cursor;  // [max_depth][SSB_MAX_QUADS] scatter cursors (start at the bin offset)
 	uint32_t* nhits;       // [max_depth] total hits (= length of `order`)
-	float4* samples;    // optional [nsamp][npix_rect] per-sample output (debug), may be null
+	float4* samples;    // [nsamp][npix_rect] per-sample (X,Y,Z,hit): fold stage -> in-order accumulation (aliases recA[0])
 	double* accum;
 	unsigned long long total_work;  // npix_rect * nsamp
 	uint32_t width, height, x0, y0, rect_w, rect_h, sample_begin, nsamp;
@@ -1039,72 +1039,81 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 	}
 }
 
-// Unwind the recursion of every sample of a pixel, convert to XYZ and accumulate, in sample order:
+// Unwind the recursion of one sample and convert it to the value the reference's _render_sample returns:
 //   radiance = local + ((child * n.l) * f_s) / pdf        (renderer.cpp:216,248)
-//   XYZ = specradflux_to_ciexyz(radiance, lambda_0)        (color.hpp:115-139)
-//   avg += double4(float4(XYZ, hit) * 0.001f)              (renderer.cpp:292-295)
-// One thread per pixel of the pass rectangle; lanes = neighbouring pixels, so every record array is read coalesced.
-__global__ void __launch_bounds__(128) ssb_finalize_kernel(const __grid_constant__ KParams P) {
-	const uint32_t npix_rect = P.rect_w * P.rect_h;
-	const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
-	if (pr >= npix_rect) return;
+//   XYZ = specradflux_to_ciexyz(radiance, lambda_0)        (color.hpp:115-139)      [RGB mode: the l-RGB flux itself]
+// One thread per sample (ncu on the one-thread-per-pixel form: a single wave of 262 k threads, `long_scoreboard` 6.2 —
+// latency bound at half the DRAM rate); lanes = neighbouring pixels of the same sample index, so every record array is
+// read coalesced.  The float4 (X,Y,Z,hit) goes to `samples`, which aliases path-state memory that is dead by now.
+__global__ void __launch_bounds__(256) ssb_fold_kernel(const __grid_constant__ KParams P) {
+	const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= P.total_work) return;
 	const DevHeader* hdr = reinterpret_cast<const DevHeader*>(P.blob);
 	const float* pool = reinterpret_cast<const float*>(P.blob + hdr->off_pool);
 	const DevSpectrum sx = hdr->xbar, sy = hdr->ybar, sz = hdr->zbar;
+	const float4 lf = P.leaf[id];
+	const float2 mt = P.meta[id];
+	const float lambda_0 = mt.x;
+	const int info = __float_as_int(mt.y);
+	const int nrec = info & 0xffff;
+	float r0 = lf.x, r1 = lf.y, r2 = lf.z, r3 = lf.w;
+	for (int d = nrec - 1; d >= 0; --d) {
+		const size_t rec = (size_t)d * P.total_work + id;
+		const float4 lo = P.stk_local[rec], f = P.stk_f[rec];
+		const float2 np = P.stk_np[rec];
+		// Exact shortcut: the child radiance is +0 in all four channels (miss / skipped last depth — the common
+		// case at the deepest record) and n.l, pdf are positive finite, f_s non-negative finite: then
+		// ((+0*n.l)*f_s)/pdf is +0 and local + (+0) == local bit for bit (local is never -0: it is a sum that
+		// starts at +0).  Saves four IEEE divisions that would take the zero-numerator slow path.
+		if (__float_as_uint(r0) == 0u && __float_as_uint(r1) == 0u && __float_as_uint(r2) == 0u && __float_as_uint(r3) == 0u &&
+		    np.x > 0.0f && np.x < __int_as_float(0x7f800000) && np.y > 0.0f && np.y < __int_as_float(0x7f800000) &&
+		    f.x >= 0.0f && f.y >= 0.0f && f.z >= 0.0f && f.w >= 0.0f &&
+		    f.x < __int_as_float(0x7f800000) && f.y < __int_as_float(0x7f800000) && f.z < __int_as_float(0x7f800000) && f.w < __int_as_float(0x7f800000)) {
+			r0 = lo.x; r1 = lo.y; r2 = lo.z; r3 = lo.w;
+			continue;
+		}
+		r0 = lo.x + ((r0 * np.x) * f.x) / np.y;
+		r1 = lo.y + ((r1 * np.x) * f.y) / np.y;
+		r2 = lo.z + ((r2 * np.x) * f.z) / np.y;
+		r3 = lo.w + ((r3 * np.x) * f.w) / np.y;
+	}
+	if (!P.flat_field) {
+		const float s = P.ff[id];
+		r0 *= s; r1 *= s; r2 *= s; r3 *= s;
+	}
+	const float hitf = (info >> 16) ? 1.0f : 0.0f;
+	if (P.render_mode == SSB_RENDER_RGB) {  // renderer.cpp:274-275: the sample is (l-RGB flux, hit)
+		P.samples[id] = make_float4(r0, r1, r2, hitf);
+		return;
+	}
+	float rad[4] = { r0, r1, r2, r3 };
+	float X = 0.0f, Y = 0.0f, Z = 0.0f;
+#pragma unroll
+	for (int c = 0; c < 4; ++c) {
+		const float lambda = lambda_0 + (float)c * P.lambda_step;
+		X += (spec_sample(pool, sx, lambda) * rad[c]) * P.lambda_step;
+		Y += (spec_sample(pool, sy, lambda) * rad[c]) * P.lambda_step;
+		Z += (spec_sample(pool, sz, lambda) * rad[c]) * P.lambda_step;
+	}
+	P.samples[id] = make_float4(X, Y, Z, hitf);
+}
+
+// Renderer::_render_pixel's sample loop (renderer.cpp:292-295 / 301-303): per pixel, IN SAMPLE ORDER,
+//   avg += double4(sample * 0.001f)      [RGB mode: avg += double4(sample)]
+// One thread per pixel of the pass rectangle; lanes = neighbouring pixels (coalesced float4 reads).
+__global__ void __launch_bounds__(128) ssb_accumulate_kernel(const __grid_constant__ KParams P) {
+	const uint32_t npix_rect = P.rect_w * P.rect_h;
+	const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pr >= npix_rect) return;
 	const uint32_t pi = P.x0 + pr % P.rect_w, pj = P.y0 + pr / P.rect_w;
 	double* a = P.accum + 4 * ((size_t)pj * P.width + pi);
 	double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+	const bool rgb = P.render_mode == SSB_RENDER_RGB;
+#pragma unroll 8
 	for (uint32_t kk = 0; kk < P.nsamp; ++kk) {
-		const size_t id = (size_t)kk * npix_rect + pr;
-		const float4 lf = P.leaf[id];
-		const float2 mt = P.meta[id];
-		const float lambda_0 = mt.x;
-		const int info = __float_as_int(mt.y);
-		const int nrec = info & 0xffff;
-		float r0 = lf.x, r1 = lf.y, r2 = lf.z, r3 = lf.w;
-		for (int d = nrec - 1; d >= 0; --d) {
-			const size_t rec = (size_t)d * P.total_work + id;
-			const float4 lo = P.stk_local[rec], f = P.stk_f[rec];
-			const float2 np = P.stk_np[rec];
-			// Exact shortcut: the child radiance is +0 in all four channels (miss / skipped last depth — the common
-			// case at the deepest record) and n.l, pdf are positive finite, f_s non-negative finite: then
-			// ((+0*n.l)*f_s)/pdf is +0 and local + (+0) == local bit for bit (local is never -0: it is a sum that
-			// starts at +0).  Saves four IEEE divisions that would take the zero-numerator slow path.
-			if (__float_as_uint(r0) == 0u && __float_as_uint(r1) == 0u && __float_as_uint(r2) == 0u && __float_as_uint(r3) == 0u &&
-			    np.x > 0.0f && np.x < __int_as_float(0x7f800000) && np.y > 0.0f && np.y < __int_as_float(0x7f800000) &&
-			    f.x >= 0.0f && f.y >= 0.0f && f.z >= 0.0f && f.w >= 0.0f &&
-			    f.x < __int_as_float(0x7f800000) && f.y < __int_as_float(0x7f800000) && f.z < __int_as_float(0x7f800000) && f.w < __int_as_float(0x7f800000)) {
-				r0 = lo.x; r1 = lo.y; r2 = lo.z; r3 = lo.w;
-				continue;
-			}
-			r0 = lo.x + ((r0 * np.x) * f.x) / np.y;
-			r1 = lo.y + ((r1 * np.x) * f.y) / np.y;
-			r2 = lo.z + ((r2 * np.x) * f.z) / np.y;
-			r3 = lo.w + ((r3 * np.x) * f.w) / np.y;
-		}
-		if (!P.flat_field) {
-			const float s = P.ff[id];
-			r0 *= s; r1 *= s; r2 *= s; r3 *= s;
-		}
-		const float hitf = (info >> 16) ? 1.0f : 0.0f;
-		if (P.render_mode == SSB_RENDER_RGB) {
-			// RENDER_MODE_RGB (renderer.cpp:274-275, 301-303): the sample is (l-RGB flux, hit), accumulated unscaled
-			if (P.samples) P.samples[id] = make_float4(r0, r1, r2, hitf);
-			a0 += (double)r0; a1 += (double)r1; a2 += (double)r2; a3 += (double)hitf;
-			continue;
-		}
-		float rad[4] = { r0, r1, r2, r3 };
-		float X = 0.0f, Y = 0.0f, Z = 0.0f;
-#pragma unroll
-		for (int c = 0; c < 4; ++c) {
-			const float lambda = lambda_0 + (float)c * P.lambda_step;
-			X += (spec_sample(pool, sx, lambda) * rad[c]) * P.lambda_step;
-			Y += (spec_sample(pool, sy, lambda) * rad[c]) * P.lambda_step;
-			Z += (spec_sample(pool, sz, lambda) * rad[c]) * P.lambda_step;
-		}
-		if (P.samples) P.samples[id] = make_float4(X, Y, Z, hitf);
-		a0 += (double)(X * 0.001f); a1 += (double)(Y * 0.001f);
-		a2 += (double)(Z * 0.001f); a3 += (double)(hitf * 0.001f);
+		const float4 s = P.samples[(size_t)kk * npix_rect + pr];
+		if (rgb) { a0 += (double)s.x; a1 += (double)s.y; a2 += (double)s.z; a3 += (double)s.w; }
+		else { a0 += (double)(s.x * 0.001f); a1 += (double)(s.y * 0.001f); a2 += (double)(s.z * 0.001f); a3 += (double)(s.w * 0.001f); }
 	}
 	a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
 }

@@ -20,7 +20,7 @@ timeout 600 python bench.py --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_b
 cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
 if [ "${2:-}" != "noprof" ]; then
 # one whole frame of bounce launches (depths 0..8) + its finalize, after two warm frames
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"ssb_intersect|ssb_shade|ssb_bin|ssb_finalize" -s 78 -c 4 -f -o $OUT/${TAG}_trace \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"ssb_intersect|ssb_shade|ssb_bin|ssb_fold|ssb_accumulate" -s 80 -c 4 -f -o $OUT/${TAG}_trace \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT | tail -12
 fi

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Summarise an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list:
-time share and DRAM bytes per kernel, and per frame (one frame = the launches between two ssb_finalize_kernel).
+time share and DRAM bytes per kernel, and per frame (one frame = the launches up to and including ssb_accumulate_kernel).
 usage: launch_list_summary.py launches.csv [out.json]"""
 import csv, json, sys
 from collections import defaultdict
@@ -20,7 +20,7 @@ ids = sorted(launch)
 frames, cur = [], []
 for i in ids:
     cur.append(launch[i])
-    if "finalize" in launch[i]["name"]:
+    if "accumulate" in launch[i]["name"]:
         frames.append(cur); cur = []
 full = [f for f in frames if sum("intersect" in l["name"] for l in f) >= 2]
 if not full:
@@ -43,7 +43,7 @@ if tot_wi:
         if a[3]:
             print(f"  {n:45s} {a[3]/1e9:8.3f} G warp-inst  {100*a[3]/tot_wi:5.1f}%   lanes {a[4]/a[3]:5.1f}")
 if len(sys.argv) > 2:
-    bounce_b = sum(a[2] for n, a in agg.items() if "finalize" not in n and "resolve" not in n)
+    bounce_b = sum(a[2] for n, a in agg.items() if "fold" not in n and "accumulate" not in n and "resolve" not in n)
     json.dump({"dram_bytes_per_frame": tot_b, "dram_bytes_per_launch": bounce_b, "launches_per_frame": len(f),
                "warp_instructions_per_frame": tot_wi, "thread_instructions_per_frame": tot_ti,
                "share": {n: a[1] / tot_ms for n, a in agg.items()}}, open(sys.argv[2], "w"), indent=1)
