@@ -17,11 +17,12 @@
 //      upsampling, light sample, shadow query, BSDF sample, fold record), visiting paths grouped by hit quad so
 //      that a warp shares material, light-sampling geometry class and branch behaviour; surviving paths are
 //      stream-compacted (warp ballot + one atomic per warp) into dense records for the next depth.
-// then ssb_finalize_kernel folds the per-depth records backwards per sample (the reference folds radiance on the
-// way back UP its recursion, renderer.cpp:216,248 — kept exact), converts to XYZ and adds sample*0.001f to the
-// double XYZA accumulator in sample order (renderer.cpp:292-295): deterministic, no float/double atomics.
+// then ssb_fold_kernel (one thread per sample) folds the per-depth records backwards (the reference folds radiance
+// on the way back UP its recursion, renderer.cpp:216,248 — kept exact) and converts to XYZ, and
+// ssb_accumulate_kernel (one thread per pixel) adds sample*0.001f to the double XYZA accumulator in sample order
+// (renderer.cpp:292-295): deterministic, no float/double atomics.
 // History (profiles/): a register-resident megakernel reached 154-222 Msamples/s with 9.8 of 32 lanes active
-// and instruction-cache thrash on 131 KB of SASS; the wavefront forms reach 500-600+.
+// and instruction-cache thrash on 131 KB of SASS; the wavefront forms went from 500 to 840+.
 // Path state lives in HBM as 32-byte (one sector) records: recA {origin, ignore | direction, lambda0} feeds the
 // intersect stage, recH {hit point, quad | barycentrics} goes intersect -> shade, recR {PCG32 | sample id} feeds
 // the shade stage.  The scene, materials, spectra, observer/basis tables, filter records and the sRGB LUT are one
