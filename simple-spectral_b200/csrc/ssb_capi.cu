@@ -116,7 +116,6 @@ struct ssb_ctx {
 	size_t wave_bytes = 0;
 	float4* d_samples = nullptr;      // per-sample (X,Y,Z,hit) of the last pass: alias into d_wave (see ssb_render)
 	size_t samples_capacity = 0;      // in float4
-	bool want_samples = false;
 	uint32_t* d_counts = nullptr;     // queue lengths per depth
 	double* d_xyza = nullptr;
 	float4* d_srgba = nullptr;
@@ -801,9 +800,7 @@ int ssb_debug_trace_samples(ssb_ctx* c, const ssb_options* o, uint32_t px, uint3
 	bool had = c->d_accum && c->accum_w == o->width && c->accum_h == o->height;
 	if (had) { saved.resize((size_t)o->width * o->height * 4); if ((rc = ssb_read_accum(c, saved.data())) != SSB_OK) return rc; }
 	uint32_t begin = one.sample_begin;
-	c->want_samples = true;
-	rc = ssb_render(c, &one);
-	c->want_samples = false;
+	rc = ssb_render(c, &one);  // the per-sample values of the (last) pass stay in d_samples until the next render
 	if (rc != SSB_OK) return rc;
 	uint32_t ns = s1 - begin;
 	if ((size_t)ns > c->samples_capacity) return fail(SSB_ERR_UNSUPPORTED, "too many samples for one pass");
