@@ -229,9 +229,18 @@ def main_ours(args, rank, local_rank, world):
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
-    total_spp = SPP * world  # weak scaling: the job is the same frame at spp 64*N
-    opt = host.options_for(color, W, H, total_spp, seed=1, sample_begin=rank * SPP, sample_end=(rank + 1) * SPP,
-                           render_mode=ssb.SSB_RENDER_RGB if VARIANT == "rgb" else ssb.SSB_RENDER_SPECTRAL)
+    rmode = ssb.SSB_RENDER_RGB if VARIANT == "rgb" else ssb.SSB_RENDER_SPECTRAL
+    tiles = args.shard == "tiles" and world > 1
+    if tiles:
+        # option A of SURVEY 8(e): the SAME frame (spp unchanged) split into row bands, strong scaling; the reduce then
+        # sums disjoint pixels (Cornell rows differ in cost, so the bands are not perfectly balanced)
+        sharding = importlib.import_module("simple-spectral_b200.sharding")
+        total_spp = SPP
+        y0, y1 = sharding.tile_shard(rank, world, H)
+        opt = host.options_for(color, W, H, total_spp, seed=1, y0=y0, y1=y1, render_mode=rmode)
+    else:
+        total_spp = SPP * world  # weak scaling: the job is the same frame at spp 64*N
+        opt = host.options_for(color, W, H, total_spp, seed=1, sample_begin=rank * SPP, sample_end=(rank + 1) * SPP, render_mode=rmode)
     npix = W * H
 
     def device_accum_tensor():
@@ -287,7 +296,7 @@ def main_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
     dev_ms, wall_ms = t.tolist()
-    samples_per_step = npix * SPP * world
+    samples_per_step = npix * SPP * (1 if tiles else world)
     value = samples_per_step * args.steps / (dev_ms * 1e-3) / 1e6
 
     # ---------------- e2e: host buffers in, host buffers out, every step
@@ -370,10 +379,10 @@ def main_ours(args, rank, local_rank, world):
                 traffic, issue = None, None
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "reference scene (hard-coded geometry, shipped spectra + 4096^2 sRGB texture); per-sample seeded RNG",
             "config": {"workload": f"{SCENE} {W}x{H} spp{SPP} per GPU (job spp {total_spp}), hero-wavelength x4, variant {VARIANT} (upsampling + observer), "
-                                   f"ELS on, MAX_DEPTH 10", "parallelism": f"sample-sharded x{world}, one NCCL reduce of f64 XYZA" if world > 1 else "single GPU",
+                                   f"ELS on, MAX_DEPTH 10", "parallelism": (f"row-band tiles x{world}, one NCCL reduce of f64 XYZA" if tiles else f"sample-sharded x{world}, one NCCL reduce of f64 XYZA") if world > 1 else "single GPU",
                        "l2": "no flush needed: every step streams ~8 GB of path records / fold records through HBM (>> 126 MB L2)",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
@@ -415,6 +424,8 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--ref-spp", type=int, default=16, help="spp per step of the reference arm (same bounded sample as cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="samples", choices=["samples", "tiles"],
+                    help="multi-GPU decomposition: sample ranges (default, weak scaling) or row bands of the same frame (strong scaling)")
     ap.add_argument("--scene", default=SCENE, choices=sorted(ALGO_BYTES_PER_SAMPLE),
                     help="default = BASELINE configs[1]; the others are SURVEY 8(d) C3-C5 (not the headline)")
     ap.add_argument("--variant", default=VARIANT, choices=["ours1931", "ours2006", "meng", "jh", "rgb"])
