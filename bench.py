@@ -236,8 +236,12 @@ def main_ours(args, rank, local_rank, world):
         # sums disjoint pixels (Cornell rows differ in cost, so the bands are not perfectly balanced)
         sharding = importlib.import_module("simple-spectral_b200.sharding")
         total_spp = SPP
-        y0, y1 = sharding.tile_shard(rank, world, H)
-        opt = host.options_for(color, W, H, total_spp, seed=1, y0=y0, y1=y1, render_mode=rmode)
+        # one contiguous row band per rank (measured at N=2: four interleaved bands per rank balance the load better but
+        # their extra launches cost more: 11.11 vs 10.87 ms/frame); band b belongs to rank b % world
+        nb = 1 * world
+        bands = [sharding.tile_shard(b, nb, H) for b in range(rank, nb, world)]
+        band_opts = [host.options_for(color, W, H, total_spp, seed=1, y0=y0, y1=y1, render_mode=rmode, keep_accumulator=1) for (y0, y1) in bands if y1 > y0]
+        opt = band_opts[0]
     else:
         total_spp = SPP * world  # weak scaling: the job is the same frame at spp 64*N
         opt = host.options_for(color, W, H, total_spp, seed=1, sample_begin=rank * SPP, sample_end=(rank + 1) * SPP, render_mode=rmode)
@@ -250,9 +254,16 @@ def main_ours(args, rank, local_rank, world):
             __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
         return torch.as_tensor(_Arr(), device=f"cuda:{local_rank}")
 
+    def render_part():
+        if tiles:
+            for bo in band_opts:            # this rank's row bands, accumulated into one (cleared) buffer
+                ctx.render(bo)
+        else:
+            ctx.render(opt)                 # trace + in-order accumulate, async on the torch stream
+
     def step_device():
         ctx.clear()
-        ctx.render(opt)                     # trace + in-order accumulate, async on the torch stream
+        render_part()
         if world > 1:
             dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)  # the single exchange step: f64 XYZA accumulators
         if rank == 0:
@@ -289,7 +300,7 @@ def main_ours(args, rank, local_rank, world):
         trace_list.append(st.trace_ms)
         launches_per_render = st.launches
     trace_ms = sum(trace_list) / len(trace_list)
-    launches = (launches_per_render + (1 if rank == 0 else 0)) * args.steps
+    launches = (launches_per_render * (len(band_opts) if tiles else 1) + (1 if rank == 0 else 0)) * args.steps
 
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist:
@@ -326,7 +337,7 @@ def main_ours(args, rank, local_rank, world):
         if world == 1:
             ctx.render_frame(opt, xyza=xyza_np, srgba=srgba_np)
         else:
-            ctx.clear(); ctx.render(opt)
+            ctx.clear(); render_part()
             dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 ctx.resolve(opt, xyza=xyza_np, srgba=srgba_np)

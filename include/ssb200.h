@@ -163,6 +163,9 @@ typedef struct ssb_options {
 	uint32_t render_mode;             /* SSB_RENDER_* */
 	uint32_t n_wavelengths;           /* SAMPLE_WAVELENGTHS (stdafx.hpp:90): 0 = the default 4; 2, 3 or 4 (the sizes of
 	                                   * glm::vec the reference compiles with).  LAMBDA_STEP = (max-min)/n (stdafx.hpp:289) */
+	uint32_t keep_accumulator;        /* 1: do not clear the accumulator although sample_begin == 0 (several pixel
+	                                   * rectangles of one frame rendered by successive ssb_render calls) */
+	uint32_t reserved;                /* must be 0 */
 } ssb_options;
 
 typedef struct ssb_stats {
@@ -196,8 +199,8 @@ int ssb_upload_scene_async(ssb_ctx* ctx, const ssb_scene* scene);
 
 /* Trace the requested samples and ADD each sample's float4 (X,Y,Z,hit)*0.001f, in sample order,
  * to the context's per-pixel double XYZA accumulator (renderer.cpp:292-295; RGB mode: the float4
- * (r,g,b,hit) unscaled, renderer.cpp:301-303).  The accumulator is
- * cleared when sample_begin == 0 or by ssb_clear().  Device-resident; no host transfer. */
+ * (r,g,b,hit) unscaled, renderer.cpp:301-303).  The accumulator is cleared first when sample_begin == 0, unless
+ * keep_accumulator is set, and by ssb_clear().  Device-resident; no host transfer. */
 int ssb_render(ssb_ctx* ctx, const ssb_options* opt);
 int ssb_clear(ssb_ctx* ctx);
 

@@ -516,7 +516,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	if (!rgb && o->upsampling == SSB_UPSAMPLE_JH && !c->jh_res) return fail(SSB_ERR_ARG, "JH upsampling needs the coefficient tables");
 	if (!rgb && o->upsampling == SSB_UPSAMPLE_MENG && !c->have_meng) return fail(SSB_ERR_ARG, "MENG upsampling needs the grid tables");
 	if ((rc = ensure_accum(c, o->width, o->height)) != SSB_OK) return rc;
-	if (o->sample_begin == 0) SSB_CUDA(cudaMemsetAsync(c->d_accum, 0, (size_t)o->width * o->height * 4 * sizeof(double), c->stream));
+	if (o->sample_begin == 0 && !o->keep_accumulator) SSB_CUDA(cudaMemsetAsync(c->d_accum, 0, (size_t)o->width * o->height * 4 * sizeof(double), c->stream));
 
 	const uint32_t rect_w = x1 - o->x0, rect_h = y1 - o->y0;
 	const size_t npix_rect = (size_t)rect_w * rect_h;

@@ -122,27 +122,22 @@ def test_gpu_rejects_unsupported_wavelength_counts():
 
 
 def test_gpu_subsets_compose():
-    """tile rectangles x sample ranges accumulate to the full-frame result (the multi-GPU sharding contract)."""
+    """tile rectangles x sample ranges accumulate to the full-frame result (the multi-GPU sharding contract);
+    keep_accumulator lets several rectangles of the first sample range share one accumulator."""
     flat = pu.load_flat("cornell", "ours1931")
     full = pu.options("ours1931", 40, 30, 6, seed=3)
     with pu.gpu_context(flat) as ctx:
         ctx.render(full)
         want = ctx.read_accum(40, 30)
-        first = True
+        ctx.clear()
         for (s0, s1) in ((0, 2), (2, 6)):
             for (x0, x1) in ((0, 17), (17, 40)):
-                o = pu.options("ours1931", 40, 30, 6, seed=3, x0=x0, x1=x1, sample_begin=s0, sample_end=s1)
-                if s0 == 0 and not first:
-                    # sample_begin == 0 clears the accumulator: carry it over explicitly
-                    keep = ctx.read_accum(40, 30)
-                    ctx.render(o)
-                    got_part = ctx.read_accum(40, 30)
-                    ctx.write_accum(keep + got_part)
-                else:
-                    ctx.render(o)
-                first = False
+                ctx.render(pu.options("ours1931", 40, 30, 6, seed=3, x0=x0, x1=x1, sample_begin=s0, sample_end=s1, keep_accumulator=1))
         got = ctx.read_accum(40, 30)
+        ctx.render(pu.options("ours1931", 40, 30, 6, seed=3, x0=0, x1=17, sample_begin=0, sample_end=2))  # default: clears first
+        part = ctx.read_accum(40, 30)
     assert pu.bits_equal(got, want)
+    assert (part[:, 17:] == 0).all() and part[:, :17].any()
 
 
 def test_gpu_full_size_properties():
