@@ -183,7 +183,15 @@ int build_blob(ssb_ctx* c) {
 	hdr.off_lights = (uint32_t)off; off = align_up(off + c->lights.size() * sizeof(uint32_t), 16);
 	hdr.off_textures = (uint32_t)off; off = align_up(off + texs.size() * sizeof(DevTexture), 16);
 	hdr.off_pool = (uint32_t)off; off = align_up(off + pool.size() * sizeof(float), 16);
-	hdr.off_boxes = (uint32_t)off; off = align_up(off + c->quads.size() * 16 * sizeof(float), 16);
+	// conservative filter tables of scene_intersect (ssb_blob.hpp / ssb_isect.cuh)
+	const FilterTables ft = build_filter_tables(c->quads.data(), c->quads.size(), c->camera.pos);
+	ft.fill_header(hdr);
+	off = align_up(off, 128);
+	hdr.off_fpairs = (uint32_t)off; off = align_up(off + ft.pairs.size() * sizeof(float), 16);
+	hdr.off_planes = (uint32_t)off; off = align_up(off + ft.planes.size() * sizeof(float), 16);
+	hdr.off_entry_quad = (uint32_t)off; off = align_up(off + ft.entry_quad.size() * sizeof(uint32_t), 16);
+	hdr.off_quad_mask = (uint32_t)off; off = align_up(off + ft.quad_mask.size() * sizeof(uint32_t), 16);
+	hdr.off_chunks = (uint32_t)off; off = align_up(off + ft.chunks.size() * sizeof(uint32_t), 16);
 	hdr.total_bytes = (uint32_t)off;
 	if (off > 160 * 1024) return fail(SSB_ERR_UNSUPPORTED, "scene tables (%zu bytes) exceed the shared-memory budget", off);
 
@@ -194,69 +202,11 @@ int build_blob(ssb_ctx* c) {
 	if (!c->lights.empty()) memcpy(blob.data() + hdr.off_lights, c->lights.data(), c->lights.size() * sizeof(uint32_t));
 	if (!texs.empty()) memcpy(blob.data() + hdr.off_textures, texs.data(), texs.size() * sizeof(DevTexture));
 	if (!pool.empty()) memcpy(blob.data() + hdr.off_pool, pool.data(), pool.size() * sizeof(float));
-	{
-		// conservative per-quad bounds for the filter phase of scene_intersect: the plane of the quad and its
-		// bounding rectangle in two in-plane axes, enlarged by 1e-4 of the scene diagonal (>> any rounding of the
-		// watertight test).  Non-planar or degenerate quads get an all-zero record, which the filter always passes.
-		float slo[3] = { INFINITY, INFINITY, INFINITY }, shi[3] = { -INFINITY, -INFINITY, -INFINITY };
-		for (const ssb_quad& q : c->quads)
-			for (int t = 0; t < 2; ++t) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) {
-				slo[k] = std::min(slo[k], q.tri[t].v[v].pos[k]); shi[k] = std::max(shi[k], q.tri[t].v[v].pos[k]);
-			}
-		const double diag = std::sqrt((double)(shi[0] - slo[0]) * (shi[0] - slo[0]) + (double)(shi[1] - slo[1]) * (shi[1] - slo[1]) + (double)(shi[2] - slo[2]) * (shi[2] - slo[2]));
-		const double margin = 1e-4 * diag + 1e-6;
-		DevHeader* h = reinterpret_cast<DevHeader*>(blob.data());
-		h->cull_margin = (float)margin;
-		float* rec = reinterpret_cast<float*>(blob.data() + hdr.off_boxes);
-		for (size_t qi = 0; qi < c->quads.size(); ++qi) {
-			const ssb_quad& q = c->quads[qi];
-			double P[6][3];
-			for (int t = 0; t < 2; ++t) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) P[t * 3 + v][k] = q.tri[t].v[v].pos[k];
-			float* r = rec + 16 * qi;
-			for (int k = 0; k < 16; ++k) r[k] = 0.0f;
-			// plane through tri0 (double precision, from the vertices — not from the stored float normal)
-			double e1[3], e2[3], n[3];
-			for (int k = 0; k < 3; ++k) { e1[k] = P[1][k] - P[0][k]; e2[k] = P[2][k] - P[0][k]; }
-			n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
-			double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), e1l = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
-			if (!(nl > 1e-12 * diag * diag) || !(e1l > 0)) continue;  // degenerate: always a candidate
-			for (int k = 0; k < 3; ++k) n[k] /= nl;
-			double w = n[0] * P[0][0] + n[1] * P[0][1] + n[2] * P[0][2];
-			bool planar = true;
-			for (int v = 0; v < 6; ++v) if (std::fabs(n[0] * P[v][0] + n[1] * P[v][1] + n[2] * P[v][2] - w) > 1e-6 * diag) planar = false;
-			if (!planar) continue;
-			double a[3], b[3];
-			for (int k = 0; k < 3; ++k) a[k] = e1[k] / e1l;
-			b[0] = n[1] * a[2] - n[2] * a[1]; b[1] = n[2] * a[0] - n[0] * a[2]; b[2] = n[0] * a[1] - n[1] * a[0];
-			double ulo = INFINITY, uhi = -INFINITY, vlo = INFINITY, vhi = -INFINITY;
-			for (int v = 0; v < 6; ++v) {
-				double u = a[0] * P[v][0] + a[1] * P[v][1] + a[2] * P[v][2], vv = b[0] * P[v][0] + b[1] * P[v][1] + b[2] * P[v][2];
-				ulo = std::min(ulo, u); uhi = std::max(uhi, u); vlo = std::min(vlo, vv); vhi = std::max(vhi, vv);
-			}
-			double hu = 0.5 * (uhi - ulo) + margin, hv = 0.5 * (vhi - vlo) + margin, cu = 0.5 * (uhi + ulo), cv = 0.5 * (vhi + vlo);
-			r[0] = (float)n[0]; r[1] = (float)n[1]; r[2] = (float)n[2]; r[3] = (float)w;
-			r[4] = (float)(a[0] / hu); r[5] = (float)(a[1] / hu); r[6] = (float)(a[2] / hu); r[7] = (float)(cu / hu);
-			r[8] = (float)(b[0] / hv); r[9] = (float)(b[1] / hv); r[10] = (float)(b[2] / hv); r[11] = (float)(cv / hv);
-			// which triangle: signed distance to the shared diagonal v00-v11 (tri0 = v00,v10,v11; tri1 = v00,v11,v01), in units
-			// of the margin, as a function of the scaled (u,v).  Only when the two triangles really share that diagonal and lie
-			// on opposite sides of it; otherwise the record stays 0 and both triangles are always tested.
-			bool shared = true;
-			for (int k = 0; k < 3; ++k) shared = shared && q.tri[1].v[0].pos[k] == q.tri[0].v[0].pos[k] && q.tri[1].v[1].pos[k] == q.tri[0].v[2].pos[k];
-			auto uv = [&](int v, double& U, double& V) { U = a[0] * P[v][0] + a[1] * P[v][1] + a[2] * P[v][2]; V = b[0] * P[v][0] + b[1] * P[v][1] + b[2] * P[v][2]; };
-			double u00, v00, u10, v10, u11, v11, u01, v01;
-			uv(0, u00, v00); uv(1, u10, v10); uv(2, u11, v11); uv(5, u01, v01);
-			double ex = u11 - u00, ey = v11 - v00, el = std::sqrt(ex * ex + ey * ey);
-			if (shared && el > 0) {
-				double nx2 = ey / el, ny2 = -ex / el;  // unit normal of the diagonal
-				double d10 = nx2 * (u10 - u00) + ny2 * (v10 - v00), d01 = nx2 * (u01 - u00) + ny2 * (v01 - v00);
-				if (d10 < 0) { nx2 = -nx2; ny2 = -ny2; d10 = -d10; d01 = -d01; }
-				if (d10 > margin && d01 < -margin) {
-					r[12] = (float)(nx2 * hu / margin); r[13] = (float)(ny2 * hv / margin);
-					r[14] = (float)((nx2 * (cu - u00) + ny2 * (cv - v00)) / margin);
-				}
-			}
-		}
-	}
+	if (!ft.pairs.empty()) memcpy(blob.data() + hdr.off_fpairs, ft.pairs.data(), ft.pairs.size() * sizeof(float));
+	if (!ft.planes.empty()) memcpy(blob.data() + hdr.off_planes, ft.planes.data(), ft.planes.size() * sizeof(float));
+	if (!ft.entry_quad.empty()) memcpy(blob.data() + hdr.off_entry_quad, ft.entry_quad.data(), ft.entry_quad.size() * sizeof(uint32_t));
+	if (!ft.quad_mask.empty()) memcpy(blob.data() + hdr.off_quad_mask, ft.quad_mask.data(), ft.quad_mask.size() * sizeof(uint32_t));
+	if (!ft.chunks.empty()) memcpy(blob.data() + hdr.off_chunks, ft.chunks.data(), ft.chunks.size() * sizeof(uint32_t));
 
 	if (off > c->blob_capacity) {
 		if (c->d_blob) cudaFree(c->d_blob);

@@ -8,10 +8,11 @@
 // Design (B200-first, not a translation of the reference's recursive std::function): a sorted WAVEFRONT.
 // Per path depth, four launches on one stream (queue lengths stay on the device, no host round trip):
 //   1. ssb_intersect_kernel  — the closest-hit query of every live path (depth 0: also creates the path: camera
-//      ray, per-sample PCG32 seed, hero wavelength).  Small (15 KB of SASS, 64 registers, 32 warps/SM): the
-//      linear scan over the quad list is a conservative plane/rectangle filter run converged by all lanes plus the
-//      exact watertight test on the few surviving candidates.  Writes the hit record, ends paths that miss, and
-//      counts hits per quad (shared-memory histogram, one global atomic per quad per CTA).
+//      ray, per-sample PCG32 seed, hero wavelength).  Small (64 registers, 32 warps/SM): the linear scan over the
+//      quad list (ssb_isect.cuh) is a conservative plane/rectangle filter run converged by all lanes — two filter
+//      entries per packed-fp32 instruction (FFMA2) — plus the exact watertight test on the surviving candidates,
+//      nearest candidate first.  Writes the hit record, ends paths that miss, and counts hits per quad
+//      (shared-memory histogram, one global atomic per quad per CTA).
 //   2. ssb_bin_scan_kernel + 3. ssb_bin_scatter_kernel — counting sort of the hit paths by hit quad.
 //   4. ssb_shade_kernel — everything the reference's lambda L does after the hit (emission, albedo / sRGB texture
 //      upsampling, light sample, shadow query, BSDF sample, fold record), visiting paths grouped by hit quad so
@@ -34,35 +35,13 @@
 #include <cstdint>
 
 #include "../../include/ssb200.h"
+#include "ssb_blob.hpp"
+#include "ssb_isect.cuh"
 #include "ssb_math.cuh"
 
 namespace ssbk {
 
-// ------------------------------------------------------------------ device blob layout
-struct DevSpectrum {  // _Spectrum (spectrum.hpp:12-70), data in the float pool
-	uint32_t offset;    // index of the first sample in the pool
-	uint32_t n_filter;  // n | (nearest ? 1u<<31 : 0)
-	float low;
-	float recip;        // _delta_lambda_recip = float(n-1)/(high-low), spectrum.cpp:22-25
-};
-struct DevMaterial {
-	uint32_t kind, albedo_mode, texture, pad;
-	DevSpectrum albedo, emission;
-	float albedo_rgb[4], emission_rgb[4];  // RENDER_MODE_RGB constants (4th = 0)
-};
-struct DevTexture {
-	const uchar4* rgba;  // RGB8 re-packed to RGBA8 at upload: one aligned 4-byte load per texel
-	uint32_t width, height;
-};
-struct DevHeader {
-	uint32_t nquads, nmaterials, nlights, ntextures;
-	uint32_t off_quads, off_materials, off_lights, off_textures, off_pool;  // byte offsets from blob start
-	uint32_t total_bytes;  // multiple of 16
-	uint32_t off_boxes;    // per quad: 4 x float4 — plane (n,w), scaled in-plane axes (a,ca), (b,cb), diagonal (A,B,C,0)
-	float cull_margin;     // 1e-4 x scene diagonal
-	DevSpectrum xbar, ybar, zbar, basis_r, basis_g, basis_b;
-	float srgb_lut[256];  // Color::srgb_to_lrgb(v/255) for v = 0..255 (color.hpp:91-97), built with the host libm
-};
+// (blob layout: ssb_blob.hpp; shared-memory view, ray/scene intersection: ssb_isect.cuh)
 
 struct KParams {
 	const unsigned char* blob;
@@ -122,12 +101,6 @@ __device__ __forceinline__ float glm_clamp(float x, float lo, float hi) { return
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
 	return (ax * bx + ay * by) + az * bz;
 }
-__device__ __forceinline__ float rcp_approx(float x) {  // 1 ulp MUFU.RCP: culling only, never reference arithmetic
-	float r;
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-	return r;
-}
-__device__ __forceinline__ float sel3(float x, float y, float z, int i) { return i == 0 ? x : (i == 1 ? y : z); }
 
 // ------------------------------------------------------------------ RNG (util/random.hpp:16-78)
 struct Rng { unsigned long long state, inc; };
@@ -183,22 +156,6 @@ __device__ __noinline__ float2 sincosf_x(float x) {  // (sin, cos)
 	ssbm::sincosf_exact(x, &s, &c);
 	return make_float2(s, c);
 }
-
-// ------------------------------------------------------------------ shared-memory view of the blob
-// The blob lives in dynamic shared memory.  It is declared at namespace scope and reached through these accessors
-// (not through generic pointers carried in a struct) so that every load — also inside the non-inlined helpers —
-// is a shared-memory load (LDS) rather than a generic one (ncu on the first wavefront build: LD.E.128 + R2UR
-// in the intersection scan).
-extern __shared__ __align__(128) unsigned char ssb_smem[];
-struct SceneView {
-	__device__ __forceinline__ const DevHeader* hdr() const { return reinterpret_cast<const DevHeader*>(ssb_smem); }
-	__device__ __forceinline__ const ssb_quad* quads() const { return reinterpret_cast<const ssb_quad*>(ssb_smem + hdr()->off_quads); }
-	__device__ __forceinline__ const DevMaterial* materials() const { return reinterpret_cast<const DevMaterial*>(ssb_smem + hdr()->off_materials); }
-	__device__ __forceinline__ const uint32_t* lights() const { return reinterpret_cast<const uint32_t*>(ssb_smem + hdr()->off_lights); }
-	__device__ __forceinline__ const DevTexture* textures() const { return reinterpret_cast<const DevTexture*>(ssb_smem + hdr()->off_textures); }
-	__device__ __forceinline__ const float* pool() const { return reinterpret_cast<const float*>(ssb_smem + hdr()->off_pool); }
-	__device__ __forceinline__ const float4* boxes() const { return reinterpret_cast<const float4*>(ssb_smem + hdr()->off_boxes); }
-};
 
 // _Spectrum::_sample_linear / _sample_nearest (spectrum.cpp:29-60)
 __device__ __forceinline__ float spec_sample(const float* pool, const DevSpectrum& s, float lambda) {
@@ -404,142 +361,6 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 	} else {
 		return meng_upsample(P, r, g, b, lambda_0);
 	}
-}
-
-// ------------------------------------------------------------------ ray / scene intersection
-struct RayConst {  // per-ray constants of the watertight test (geometry.cpp:17-37), hoisted out of the scan
-	int kx, ky, kz;
-	float Sx, Sy, Sz;
-	float okx, oky, okz;  // ray origin permuted
-};
-__device__ __forceinline__ RayConst ray_setup(float ox, float oy, float oz, float dx, float dy, float dz) {
-	RayConst rc;
-	float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-	int kx, ky, kz;
-	if (ax > ay) {
-		if (ax > az) { kz = 0; kx = 1; ky = 2; } else { kz = 2; kx = 0; ky = 1; }
-	} else {
-		if (ay > az) { kz = 1; kx = 2; ky = 0; } else { kz = 2; kx = 0; ky = 1; }
-	}
-	float dkz = sel3(dx, dy, dz, kz);
-	if (dkz < 0.0f) { int t = kx; kx = ky; ky = t; }
-	rc.kx = kx; rc.ky = ky; rc.kz = kz;
-	rc.Sx = sel3(dx, dy, dz, kx) / dkz;
-	rc.Sy = sel3(dx, dy, dz, ky) / dkz;
-	rc.Sz = 1.0f / dkz;
-	rc.okx = sel3(ox, oy, oz, kx); rc.oky = sel3(ox, oy, oz, ky); rc.okz = sel3(ox, oy, oz, kz);
-	return rc;
-}
-
-struct Hit {
-	int quad;  // -1: none
-	int tri;
-	float dist;
-	float bx, by, bz;  // barycentrics (UVW * det_recip)
-};
-
-// PrimTri::intersect (geometry.cpp:12-101); true when the hit record was updated
-__device__ __forceinline__ bool tri_intersect(const ssb_tri& t, const RayConst& rc, float eps, Hit& hit) {
-	// vertices relative to the ray origin, permuted: A = v0 - orig etc. (geometry.cpp:40-47)
-	float Akx = t.v[0].pos[rc.kx] - rc.okx, Aky = t.v[0].pos[rc.ky] - rc.oky, Akz = t.v[0].pos[rc.kz] - rc.okz;
-	float Bkx = t.v[1].pos[rc.kx] - rc.okx, Bky = t.v[1].pos[rc.ky] - rc.oky, Bkz = t.v[1].pos[rc.kz] - rc.okz;
-	float Ckx = t.v[2].pos[rc.kx] - rc.okx, Cky = t.v[2].pos[rc.ky] - rc.oky, Ckz = t.v[2].pos[rc.kz] - rc.okz;
-	float Ax = Akx - rc.Sx * Akz, Bx = Bkx - rc.Sx * Bkz, Cx = Ckx - rc.Sx * Ckz;
-	float Ay = Aky - rc.Sy * Akz, By = Bky - rc.Sy * Bkz, Cy = Cky - rc.Sy * Ckz;
-	// UVW = cross(ABCy, ABCx)
-	float U = By * Cx - Bx * Cy;
-	float V = Cy * Ax - Cx * Ay;
-	float W = Ay * Bx - Ax * By;
-	if (U != 0.0f && V != 0.0f && W != 0.0f) {
-		if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-	} else {
-		double Ud = (double)By * (double)Cx - (double)Bx * (double)Cy;
-		double Vd = (double)Cy * (double)Ax - (double)Cx * (double)Ay;
-		double Wd = (double)Ay * (double)Bx - (double)Ax * (double)By;
-		if ((Ud < 0.0 || Vd < 0.0 || Wd < 0.0) && (Ud > 0.0 || Vd > 0.0 || Wd > 0.0)) return false;
-		U = (float)Ud; V = (float)Vd; W = (float)Wd;
-	}
-	float det = (U + V) + W;
-	if (!(fabsf(det) > eps)) return false;
-	float T = (U * (rc.Sz * Akz) + V * (rc.Sz * Bkz)) + W * (rc.Sz * Ckz);
-	if (((__float_as_uint(det) ^ __float_as_uint(T)) & 0x80000000u) != 0u) return false;
-	float det_recip = 1.0f / det;
-	float dist = T * det_recip;
-	if (dist >= eps && dist < hit.dist) {
-		hit.dist = dist;
-		hit.bx = U * det_recip; hit.by = V * det_recip; hit.bz = W * det_recip;
-		return true;
-	}
-	return false;
-}
-
-// Scene::intersect (scene.cpp:433-445) + PrimQuad::intersect (geometry.cpp:128-139).
-//
-// The reference scans every primitive with the full watertight test.  Here the scan is split in two
-// phases that give the SAME hit record:
-//   1. a conservative filter per quad, run converged by all lanes (quad data is a shared-memory broadcast):
-//      intersect the ray with the quad's plane, and test the plane point against the quad's bounding rectangle
-//      in the plane's own axes, enlarged by 1e-4 of the scene diagonal — orders of magnitude more than the
-//      rounding of the watertight test or of this filter, so it can only reject quads the exact test would
-//      reject.  The side of the quad's diagonal (again with that margin) tells which of its two triangles can be
-//      hit.  Rays (nearly) parallel to the plane and non-planar quads always pass.  The result is a per-lane bit
-//      mask of candidate triangles: almost always just the one that is hit.
-//   2. the exact test (tri0, then tri1) only for the lane's candidates, in list order (lowest bit first), so
-//      ties and the `ignore` rule resolve exactly as in the reference.
-// The filter arithmetic (explicit fma, approximate reciprocal) is not part of the reference's arithmetic and
-// never touches the hit record.
-#ifndef SSB_CULL
-#define SSB_CULL 1
-#endif
-__device__ __noinline__ void scene_intersect(const SceneView& S, float eps, int ignore, Hit& hit,
-                                             float ox, float oy, float oz, float dx, float dy, float dz) {
-	const RayConst rc = ray_setup(ox, oy, oz, dx, dy, dz);
-	hit.quad = -1; hit.tri = 0; hit.dist = __int_as_float(0x7f800000);
-	hit.bx = hit.by = hit.bz = 0.0f;
-	const int nq = (int)S.hdr()->nquads;
-#if SSB_CULL
-	const float tmargin = S.hdr()->cull_margin;
-	for (int base = 0; base < nq; base += 32) {
-		const int cnt = min(32, nq - base);
-		unsigned cand0 = 0u, cand1 = 0u;  // quads whose tri0 / tri1 may be hit
-		for (int j = 0; j < cnt; ++j) {
-			const float4* rec = S.boxes() + 4 * (base + j);
-			const float4 pl = rec[0], ua = rec[1], vb = rec[2], dg = rec[3];
-			const float nd = __fmaf_rn(pl.x, dx, __fmaf_rn(pl.y, dy, pl.z * dz));
-			const float no = __fmaf_rn(pl.x, ox, __fmaf_rn(pl.y, oy, pl.z * oz));
-			const float tp = (pl.w - no) * rcp_approx(nd);
-			const float px = __fmaf_rn(tp, dx, ox), py = __fmaf_rn(tp, dy, oy), pz = __fmaf_rn(tp, dz, oz);
-			const float u = __fmaf_rn(ua.x, px, __fmaf_rn(ua.y, py, __fmaf_rn(ua.z, pz, -ua.w)));
-			const float v = __fmaf_rn(vb.x, px, __fmaf_rn(vb.y, py, __fmaf_rn(vb.z, pz, -vb.w)));
-			const float sd = __fmaf_rn(dg.x, u, __fmaf_rn(dg.y, v, dg.z));  // signed distance to the diagonal / margin
-			// written so that any NaN keeps the quad (comparisons with NaN are false)
-			const bool par = !(fabsf(nd) >= 1e-6f);  // (nearly) parallel to the plane, or all-zero record: keep both
-			const bool out = (tp < -tmargin) | (fabsf(u) > 1.0f) | (fabsf(v) > 1.0f);
-			const bool keep0 = par | (!out & !(sd < -1.0f));  // tri0 lies on the sd >= 0 side of the diagonal
-			const bool keep1 = par | (!out & !(sd > 1.0f));
-			cand0 |= keep0 ? (1u << j) : 0u;
-			cand1 |= keep1 ? (1u << j) : 0u;
-		}
-		if (ignore >= base && ignore < base + 32) { cand0 &= ~(1u << (ignore - base)); cand1 &= ~(1u << (ignore - base)); }
-		// one exact triangle test per iteration: (quad, tri0) before (quad, tri1), quads in list order; tri1 is skipped when
-		// tri0 was hit (PrimQuad::intersect, geometry.cpp:131-133)
-		while (cand0 | cand1) {
-			const unsigned bit = (cand0 | cand1) & (0u - (cand0 | cand1));
-			const int q = base + (__ffs(bit) - 1);
-			const int tt = (cand0 & bit) ? 0 : 1;
-			cand0 &= ~bit;
-			if (tt == 1) cand1 &= ~bit;
-			if (tri_intersect(S.quads()[q].tri[tt], rc, eps, hit)) { hit.quad = q; hit.tri = tt; cand1 &= ~bit; }
-		}
-	}
-#else
-	for (int q = 0; q < nq; ++q) {
-		if (q == ignore) continue;
-		const ssb_quad& quad = S.quads()[q];
-		if (tri_intersect(quad.tri[0], rc, eps, hit)) { hit.quad = q; hit.tri = 0; }
-		else if (tri_intersect(quad.tri[1], rc, eps, hit)) { hit.quad = q; hit.tri = 1; }
-	}
-#endif
 }
 
 // ------------------------------------------------------------------ light sampling
