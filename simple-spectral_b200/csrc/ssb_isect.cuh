@@ -195,6 +195,11 @@ SSB_ISECT_FN void filter_chunk(const float4* rec, int npairs, float margin_rneg,
 	const float2 ox2 = make_float2(ox, ox), oy2 = make_float2(oy, oy), oz2 = make_float2(oz, oz);
 	const float2 one2 = make_float2(1.0f, 1.0f), mr2 = make_float2(margin_rneg, margin_rneg), tk2 = make_float2(tmax_k, tmax_k);
 	const float nanv = __int_as_float(0x7fffffff);
+#ifndef SSB_FILTER_UNROLL
+#define SSB_FILTER_UNROLL 1
+#endif
+	constexpr int kUnroll = SSB_FILTER_UNROLL;
+#pragma unroll kUnroll
 	for (int i = npairs - 1; i >= 0; --i) {
 		const float4* r = rec + 8 * i;
 		const float4 a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3], a4 = r[4], a5 = r[5], a6 = r[6], a7 = r[7];

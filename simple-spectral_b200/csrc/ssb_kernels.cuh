@@ -102,6 +102,16 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 	return (ax * bx + ay * by) + az * bz;
 }
 
+// a / b, exactly — with the one case that is both frequent and trivially known kept away from the IEEE division's slow
+// path: a zero numerator over a positive (finite or infinite) denominator is that same zero.  (Channels of a hero sample
+// that fall outside a measured spectrum — the Cornell box's albedos end at 700 nm — are exactly 0; ncu: the slow-path
+// subroutine was entered from these quotients ~0.5 M times per launch.)  Lanes taking the shortcut divide 1 by 1.
+__device__ __forceinline__ float div_or_zero(float a, float b) {
+	const bool zero = (a == 0.0f) && (b > 0.0f);
+	const float q = (zero ? 1.0f : a) / (zero ? 1.0f : b);
+	return zero ? a : q;
+}
+
 // ------------------------------------------------------------------ RNG (util/random.hpp:16-78)
 struct Rng { unsigned long long state, inc; };
 __device__ __forceinline__ uint32_t rng_next(Rng& r) {
@@ -489,6 +499,29 @@ __device__ __forceinline__ void stage_blob(unsigned char* smem, const unsigned c
 	}
 }
 
+// ---- per-thread software pipeline of path records (cp.async / LDGSTS, 16 bytes each, L1 bypassed): the records of the
+// NEXT grid-stride iteration are copied into the thread's own shared-memory slot while the current iteration computes.
+// ncu on the unpipelined kernels: ~20 % (intersect) and ~25 % (shade) of all warp time was `long_scoreboard` at the
+// record loads at the top of each iteration (two dependent round trips in the shade stage: order[] -> records).  With the
+// pipeline that stall is gone (2.0 -> 0.5 cycles per issue in the intersect stage); the frame gains only ~0.5 %, the
+// stages being bound by dependent-issue latency and the phase barriers rather than by that wait (profiles/README.md).
+// Each thread reads back only what its own copies wrote, so cp.async.wait_group is the only synchronisation needed.
+#ifndef SSB_PIPELINE
+#define SSB_PIPELINE 1
+#endif
+#ifndef SSB_PIPELINE_ISECT
+#define SSB_PIPELINE_ISECT SSB_PIPELINE
+#endif
+#ifndef SSB_PIPELINE_SHADE
+#define SSB_PIPELINE_SHADE SSB_PIPELINE
+#endif
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 #ifndef SSB_INTERSECT_THREADS
 #define SSB_INTERSECT_THREADS 256
 #endif
@@ -530,10 +563,32 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 	__shared__ uint32_t s_bins[SSB_MAX_QUADS];
 	for (uint32_t q = threadIdx.x; q < SSB_MAX_QUADS; q += blockDim.x) s_bins[q] = 0;
 	__syncthreads();
+#if SSB_PIPELINE_ISECT
+	// [stage][record: recA.0, recA.1, recR.1][thread]
+	__shared__ float4 s_pipe[FIRST ? 1 : 2][FIRST ? 1 : 3][FIRST ? 1 : SSB_INTERSECT_THREADS];
+	auto prefetch = [&](uint32_t it, int stage) {
+		if (!FIRST && it < n_in) {
+			cp_async16(&s_pipe[stage][0][threadIdx.x], &P.recA[pin][2 * (size_t)it]);
+			cp_async16(&s_pipe[stage][1][threadIdx.x], &P.recA[pin][2 * (size_t)it + 1]);
+			cp_async16(&s_pipe[stage][2][threadIdx.x], &P.recR[pin][2 * (size_t)it + 1]);
+		}
+		cp_async_commit();
+	};
+	if (!FIRST) prefetch(blockIdx.x * blockDim.x + threadIdx.x, 0);
+	int stage = 0;
+#endif
 
 	for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += nthreads) {
 		const bool valid = item < n_in;
 		uint32_t hq = 0xffffffffu;
+#if SSB_PIPELINE_ISECT
+		const int cur = stage;  // the slot of this iteration stays intact until the next iteration's prefetch
+		if (!FIRST) {
+			prefetch(item + nthreads, stage ^ 1);
+			cp_async_wait<1>();
+			stage ^= 1;
+		}
+#endif
 		if (valid) {
 			float ox, oy, oz, dx, dy, dz;
 			int ignore = -1;
@@ -571,7 +626,11 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				                                          __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32)));
 				P.recR[0][2 * (size_t)item + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
 			} else {
+#if SSB_PIPELINE_ISECT
+				const float4 a = s_pipe[cur][0][threadIdx.x], b = s_pipe[cur][1][threadIdx.x];
+#else
 				const float4 a = P.recA[pin][2 * (size_t)item], b = P.recA[pin][2 * (size_t)item + 1];
+#endif
 				ox = a.x; oy = a.y; oz = a.z; ignore = __float_as_int(a.w);
 				dx = b.x; dy = b.y; dz = b.z;
 			}
@@ -585,7 +644,11 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				P.recH[2 * (size_t)item + 1] = make_float4(hit.bx, hit.by, hit.bz, 0.f);
 			} else {
 				// miss: L() returns 0 (renderer.cpp:161-163 with no hit); hit_anything only if an earlier depth hit
+#if SSB_PIPELINE_ISECT
+				const float4 r1 = FIRST ? P.recR[pin][2 * (size_t)item + 1] : s_pipe[cur][2][threadIdx.x];
+#else
 				const float4 r1 = P.recR[pin][2 * (size_t)item + 1];
+#endif
 				const uint32_t id = __float_as_uint(r1.x);
 				P.leaf[id] = make_float4(0.f, 0.f, 0.f, 0.f);
 				P.meta[id] = make_float2(r1.y, __int_as_float(depth | (FIRST ? 0 : (1 << 16))));
@@ -689,8 +752,41 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 	const bool more_depth = (uint32_t)depth + 1u < P.max_depth;
 	const bool light_phase = more_depth && els && (!P.indirect_only || !FIRST);
 
+#if SSB_PIPELINE_SHADE
+	// order[] is read two iterations ahead (a register), the records it points at one iteration ahead (cp.async into the
+	// thread's slot: [stage][recH.0, recH.1, recR.0, recR.1][thread])
+	__shared__ float4 s_pipe[2][4][SSB_SHADE_THREADS];
+	auto prefetch = [&](uint32_t it, bool ok, int stage) {
+		if (ok) {
+			cp_async16(&s_pipe[stage][0][threadIdx.x], &P.recH[2 * (size_t)it]);
+			cp_async16(&s_pipe[stage][1][threadIdx.x], &P.recH[2 * (size_t)it + 1]);
+			cp_async16(&s_pipe[stage][2][threadIdx.x], &P.recR[pin][2 * (size_t)it]);
+			cp_async16(&s_pipe[stage][3][threadIdx.x], &P.recR[pin][2 * (size_t)it + 1]);
+		}
+		cp_async_commit();
+	};
+	int stage = 0;
+	uint32_t item_cur, item_nxt;
+	{
+		const uint32_t s0 = blockIdx.x * blockDim.x + threadIdx.x;
+		item_cur = s0 < n_in ? P.order[s0] : 0u;
+		item_nxt = (s0 < n_in && nthreads < n_in - s0) ? P.order[s0 + nthreads] : 0u;
+		prefetch(item_cur, s0 < n_in, 0);
+	}
+#endif
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += nthreads) {
 		const bool valid = slot < n_in;
+#if SSB_PIPELINE_SHADE
+		const int cur = stage;
+		uint32_t item_nn = 0u;
+		{
+			const uint32_t left = valid ? n_in - slot : 0u;  // slots from this one to the end of the queue
+			prefetch(item_nxt, nthreads < left, stage ^ 1);
+			if (nthreads < left && nthreads < left - nthreads) item_nn = P.order[slot + 2u * nthreads];
+			cp_async_wait<1>();
+			stage ^= 1;
+		}
+#endif
 		bool cont = false;  // path continues to depth+1
 		float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, lambda_0 = 0;
 		int ignore = -1;
@@ -705,9 +801,15 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 
 		// ---- phase 0: gather the path, emission, albedo (renderer.cpp:165-175; material.cpp:120-143)
 		if (valid) {
+#if SSB_PIPELINE_SHADE
+			item = item_cur;
+			const float4 h0 = s_pipe[cur][0][threadIdx.x], h1 = s_pipe[cur][1][threadIdx.x];
+			const float4 r0 = s_pipe[cur][2][threadIdx.x], r1 = s_pipe[cur][3][threadIdx.x];
+#else
 			item = P.order[slot];
 			const float4 h0 = P.recH[2 * (size_t)item], h1 = P.recH[2 * (size_t)item + 1];
 			const float4 r0 = P.recR[pin][2 * (size_t)item], r1 = P.recR[pin][2 * (size_t)item + 1];
+#endif
 			hx = h0.x; hy = h0.y; hz = h0.z;  // hit position
 			const uint32_t hq = __float_as_uint(h0.w);
 			id = __float_as_uint(r1.x);
@@ -733,7 +835,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 				f_s = material_albedo<UPS>(P, S, m, st_x, st_y, lambda_0);
 				if (mat_kind == SSB_MATERIAL_LAMBERT) {
 #pragma unroll
-					for (int c = 0; c < 4; ++c) f_s.v[c] = f_s.v[c] / SSB_PI_F;
+					for (int c = 0; c < 4; ++c) f_s.v[c] = div_or_zero(f_s.v[c], SSB_PI_F);
 				}
 			}
 		}
@@ -765,7 +867,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
 					float fe = (mat_kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;  // MaterialMirror::evaluate_bsdf = 0
-					local.v[c] = local.v[c] + ((emitted.v[c] * l_ndl) * fe) / pdf;
+					local.v[c] = local.v[c] + div_or_zero((emitted.v[c] * l_ndl) * fe, pdf);
 				}
 			}
 		}
@@ -857,6 +959,9 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 				P.recR[pout][2 * (size_t)o + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
 			}
 		}
+#if SSB_PIPELINE_SHADE
+		item_cur = item_nxt; item_nxt = item_nn;
+#endif
 		SSB_PHASE_BARRIER();
 	}
 }
