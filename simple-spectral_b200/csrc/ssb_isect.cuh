@@ -286,28 +286,32 @@ SSB_ISECT_NOINLINE void scene_intersect(const SceneView& S, float eps, int ignor
 				if (cand == 0u) return;
 				const float inf = __int_as_float(0x7f800000);
 				float t1 = inf, t2 = inf;
-				int e1 = 0;
-				for (unsigned m = cand; m != 0u; m &= m - 1u) {
+				int e1 = __ffs(cand) - 1, e2 = -1;
+				// (a single candidate needs no ordering: most shadow rays only have the light's entry)
+				for (unsigned m = (cand & (cand - 1u)) ? cand : 0u; m != 0u; m &= m - 1u) {
 					const int e = __ffs(m) - 1;
 					const float key = entry_plane_key(S.planes()[e], ox, oy, oz, dx, dy, dz);
-					const bool lt1 = key < t1;
-					t2 = lt1 ? t1 : (key < t2 ? key : t2);
+					const bool lt1 = key < t1, lt2 = key < t2;
+					e2 = lt1 ? e1 : (lt2 ? e : e2);
+					t2 = lt1 ? t1 : (lt2 ? key : t2);
 					e1 = lt1 ? e : e1;
 					t1 = lt1 ? key : t1;
 				}
-				// exact tests: e1 first; the others (list order) only if the second-nearest plane distance does not already
-				// rule them out, and then each one only if its own plane distance does not
+				// exact tests: the nearest entry e1; then, unless the second-nearest plane distance t2 already rules everything
+				// else out, the second-nearest e2; then (rarely) the rest in list order, each unless its own plane distance rules it out
 				int best_e = -1;  // entry of the current hit (-1: none, so that `e < best_e` never allows an equal distance)
 				int e = e1;
 				unsigned rest = cand & ~(1u << e1);
-				bool first = true;
+				int step = 0;
 				for (;;) {
 					const int q = (int)entry_quad[e], tt = (int)((candB >> e) & 1u);
-					SSB_STAT(exact_tests, 1); if (!first) SSB_STAT(fast_more, 1);
+					SSB_STAT(exact_tests, 1); if (step) SSB_STAT(fast_more, 1);
 					if (tri_intersect(S.quads()[q].tri[tt], rc, eps, hit, e < best_e)) { hit.quad = q; hit.tri = tt; best_e = e; }
-					if (first) {
-						first = false;
-						if (t2 - margin > hit.dist) break;
+					if (rest == 0u) break;
+					if (step < 2) {
+						if (t2 - margin > hit.dist) break;  // every remaining entry has a plane distance >= t2
+						if (step == 0 && e2 >= 0 && ((rest >> e2) & 1u)) { step = 1; e = e2; rest &= ~(1u << e2); continue; }
+						step = 2;
 					}
 					bool found = false;
 					while (rest != 0u) {

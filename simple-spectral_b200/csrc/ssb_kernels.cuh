@@ -733,6 +733,15 @@ __global__ void __launch_bounds__(256) ssb_bin_scatter_kernel(const __grid_const
 #else
 #define SSB_PHASE_BARRIER() ((void)0)
 #endif
+// Which of the four barriers of an iteration are kept (bit k = the barrier after phase k).  Measured (profiles/
+// r3c_ab_pipeline_unroll_barriers.txt): all four 896.8 Msamples/s; only the one before the long light-sampling phase and the
+// one at the end of the iteration (mask 9) 910.7; without the barrier after the shadow query (mask 11) 907; only the
+// end-of-iteration one (8) 905; only the one after light sampling (2) 869; none 841.  The barrier after the shadow query
+// was where warps waited longest (ncu: 10 % of all warp time) — that phase's length varies with the exact tests a warp runs.
+#ifndef SSB_SHADE_SYNC_MASK
+#define SSB_SHADE_SYNC_MASK 9
+#endif
+#define SSB_PHASE_BARRIER_AT(k) do { if ((SSB_SHADE_SYNC_MASK >> (k)) & 1) SSB_PHASE_BARRIER(); } while (0)
 template <bool FIRST, int UPS>
 __global__ void __launch_bounds__(SSB_SHADE_THREADS, SSB_SHADE_MIN_BLOCKS)
 ssb_shade_kernel(const __grid_constant__ KParams P) {
@@ -839,7 +848,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 				}
 			}
 		}
-		SSB_PHASE_BARRIER();
+		SSB_PHASE_BARRIER_AT(0);
 
 		// ---- phase 1: light sample (renderer.cpp:182-191; Scene::get_rand_toward_light, scene.cpp:417-431)
 		float sx = 0, sy = 0, sz = 1, pdf = 1.0f, l_ndl = 0.0f;
@@ -855,7 +864,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			pdf /= (float)S.hdr()->nlights;
 			l_ndl = dot3(sx, sy, sz, nx, ny, nz);
 		}
-		SSB_PHASE_BARRIER();
+		SSB_PHASE_BARRIER_AT(1);
 
 		// ---- phase 2: shadow query + direct contribution (renderer.cpp:192-218)
 		if (valid && light_phase && l_ndl > 0.0f) {
@@ -871,7 +880,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 				}
 			}
 		}
-		SSB_PHASE_BARRIER();
+		SSB_PHASE_BARRIER_AT(2);
 
 		// ---- phase 3: interact_bsdf + recursion decision + records (renderer.cpp:222-251)
 		if (valid) {
@@ -962,7 +971,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 #if SSB_PIPELINE_SHADE
 		item_cur = item_nxt; item_nxt = item_nn;
 #endif
-		SSB_PHASE_BARRIER();
+		SSB_PHASE_BARRIER_AT(3);
 	}
 }
 
