@@ -726,6 +726,24 @@ int ssb_debug_eval_math(ssb_ctx* c, uint32_t fn, const float* x_host, float arg,
 	if (!c || !x_host || !out_host) return fail(SSB_ERR_ARG, "ssb_debug_eval_math: NULL argument");
 	if (n == 0) return SSB_OK;
 	SSB_CUDA(cudaSetDevice(c->device));
+	if (fn == 8) {  // out[0] = lanes (of 2 x 2^32) in which the paired acosf differs from the scalar one, evaluated on the device;
+		            // out[1..] = up to (n-1)/3 offending (argument, paired result, scalar result) triples
+		unsigned long long* dbad = nullptr;
+		float* dex = nullptr;
+		const uint32_t nex = (uint32_t)((n - 1) / 3);
+		SSB_CUDA(cudaMalloc(&dbad, 2 * sizeof(unsigned long long)));
+		SSB_CUDA(cudaMemsetAsync(dbad, 0, 2 * sizeof(unsigned long long), c->stream));
+		if (nex) { SSB_CUDA(cudaMalloc(&dex, 3 * nex * sizeof(float))); SSB_CUDA(cudaMemsetAsync(dex, 0, 3 * nex * sizeof(float), c->stream)); }
+		ssb_acos_pair_check_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(dbad, dex, nex);
+		unsigned long long bad = ~0ull;
+		cudaError_t e = cudaStreamSynchronize(c->stream);
+		if (e == cudaSuccess) e = cudaMemcpy(&bad, dbad, sizeof(bad), cudaMemcpyDeviceToHost);
+		if (e == cudaSuccess && nex) e = cudaMemcpy(out_host + 1, dex, 3 * nex * sizeof(float), cudaMemcpyDeviceToHost);
+		cudaFree(dbad); cudaFree(dex);
+		if (e != cudaSuccess) return fail(SSB_ERR_DATA, "ssb_debug_eval_math: %s", cudaGetErrorString(e));
+		out_host[0] = (float)bad;
+		return SSB_OK;
+	}
 	float *dx = nullptr, *dout = nullptr;
 	SSB_CUDA(cudaMalloc(&dx, n * sizeof(float)));
 	SSB_CUDA(cudaMalloc(&dout, n * sizeof(float)));

@@ -156,6 +156,18 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 // Single, non-inlined copies of the exact libm restatements: the trace kernel calls them from ~20 sites and its
 // instruction footprint must stay inside the instruction cache (ncu: `stalled_no_instruction` dominated v1).
 __device__ __noinline__ float acosf_x(float x) { return ssbm::acosf_exact(x); }
+// two arc cosines per call, evaluated with packed-fp32 instructions (ssbm::acosf_exact2: bit-identical per lane, ~45 % of
+// the instructions of two scalar calls)
+#ifndef SSB_ACOS_PAIRS
+#define SSB_ACOS_PAIRS 1
+#endif
+__device__ __noinline__ float2 acosf2_x(float x0, float x1) {
+#if SSB_ACOS_PAIRS
+	return ssbm::acosf_exact2(make_float2(x0, x1));
+#else
+	return make_float2(ssbm::acosf_exact(x0), ssbm::acosf_exact(x1));
+#endif
+}
 __device__ __noinline__ float sinf_x(float x) { return ssbm::sinf_exact(x); }
 __device__ __noinline__ float cosf_x(float x) { return ssbm::cosf_exact(x); }
 // sin and cos of the same argument share glibc's argument reduction (ssbm::sincosf_exact): each result is the scalar
@@ -404,8 +416,9 @@ __device__ __noinline__ void sample_spherical_triangle(int light_quad, int light
 	float cos_a = glm_clamp(dot3(Bx, By, Bz, Cx, Cy, Cz), -1.0f, 1.0f);
 	float cos_b = glm_clamp(dot3(Ax, Ay, Az, Cx, Cy, Cz), -1.0f, 1.0f);
 	float cos_c = glm_clamp(dot3(Ax, Ay, Az, Bx, By, Bz), -1.0f, 1.0f);
-	float a = glm_clamp(acosf_x(cos_a), 0.0f, underestimate_pi());
-	float b = glm_clamp(acosf_x(cos_b), 0.0f, underestimate_pi());
+	const float2 acos_ab = acosf2_x(cos_a, cos_b);
+	float a = glm_clamp(acos_ab.x, 0.0f, underestimate_pi());
+	float b = glm_clamp(acos_ab.y, 0.0f, underestimate_pi());
 	float c = glm_clamp(acosf_x(cos_c), 0.0f, underestimate_pi());
 	float sin_a = sinf_x(a), sin_b = sinf_x(b), sin_c = sinf_x(c);
 	float numer0 = cos_a - cos_b * cos_c;
@@ -418,8 +431,9 @@ __device__ __noinline__ void sample_spherical_triangle(int light_quad, int light
 		cos_alpha = glm_clamp(numer0 / denom0, -1.0f, 1.0f);
 		float cos_beta = glm_clamp(numer1 / denom1, -1.0f, 1.0f);
 		float cos_gamma = glm_clamp(numer2 / denom2, -1.0f, 1.0f);
-		alpha = glm_clamp(acosf_x(cos_alpha), 0.0f, underestimate_pi());
-		float beta = glm_clamp(acosf_x(cos_beta), 0.0f, underestimate_pi());
+		const float2 acos_albe = acosf2_x(cos_alpha, cos_beta);
+		alpha = glm_clamp(acos_albe.x, 0.0f, underestimate_pi());
+		float beta = glm_clamp(acos_albe.y, 0.0f, underestimate_pi());
 		float gamma = glm_clamp(acosf_x(cos_gamma), 0.0f, underestimate_pi());
 		surface_area = ((alpha + beta) + gamma) - SSB_PI_F;
 		if (!(surface_area >= 0)) surface_area = 0;
@@ -1113,9 +1127,31 @@ __global__ void ssb_eval_math_kernel(uint32_t fn, const float* __restrict__ x, f
 		case 2: r = ssbm::acosf_exact(v); break;
 		case 4: { float s, c; ssbm::sincosf_exact(v, &s, &c); r = s; break; }  // the paired form used by the kernels
 		case 5: { float s, c; ssbm::sincosf_exact(v, &s, &c); r = c; break; }
+		case 6: r = acosf2_x(v, __uint_as_float(__float_as_uint(v) * 2654435761u)).x; break;  // the paired acosf, either lane
+		case 7: r = acosf2_x(__uint_as_float(__float_as_uint(v) * 2654435761u), v).y; break;
 		default: r = ssbm::powf_exact(v, arg); break;
 	}
 	out[i] = r;
+}
+
+// acosf_exact2 against acosf_exact over ALL 2^32 arguments in either lane (the other lane gets a permutation of the
+// argument): counts lanes whose bits differ (two NaNs count as equal)
+__global__ void ssb_acos_pair_check_kernel(unsigned long long* mismatches, float* examples, uint32_t max_examples) {
+	unsigned long long bad = 0;
+	const unsigned long long total = 1ull << 32, stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+		const float x0 = __uint_as_float((uint32_t)i), x1 = __uint_as_float((uint32_t)i * 2654435761u + 12345u);
+		const float2 got = acosf2_x(x0, x1);  // the non-inlined function the shade stage calls
+		const float w0 = ssbm::acosf_exact(x0), w1 = ssbm::acosf_exact(x1);
+		const bool b0 = __float_as_uint(got.x) != __float_as_uint(w0) && !(got.x != got.x && w0 != w0);
+		const bool b1 = __float_as_uint(got.y) != __float_as_uint(w1) && !(got.y != got.y && w1 != w1);
+		bad += (b0 ? 1u : 0u) + (b1 ? 1u : 0u);
+		if ((b0 || b1) && examples) {  // a few offending arguments, for the failure message: (argument, paired result, scalar result)
+			const unsigned long long k = atomicAdd(mismatches + 1, 1ull);
+			if (k < max_examples) { examples[3 * k] = b0 ? x0 : x1; examples[3 * k + 1] = b0 ? got.x : got.y; examples[3 * k + 2] = b0 ? w0 : w1; }
+		}
+	}
+	if (bad) atomicAdd(mismatches, bad);
 }
 
 }  // namespace ssbk

@@ -39,6 +39,25 @@ def test_device_math_bit_exact(fn, lo, hi):
     assert pu.bits_equal(got, want), f"{(got.view(np.uint32) != want.view(np.uint32)).sum()} mismatches"
 
 
+def test_device_paired_acosf_equals_scalar_exhaustively():
+    """The packed two-argument acosf the light-sampling code calls (ssbm::acosf_exact2: FMUL2/FADD2/FFMA2, hand-expanded
+    division and square root) against the scalar acosf_exact — itself pinned to glibc over all 2^32 inputs on the CPU
+    (tests/test_math_exhaustive.py) and on samples above — for ALL 2^32 arguments in either lane, evaluated on the device."""
+    flat = pu.load_flat("cornell", "ours1931")
+    with pu.gpu_context(flat) as ctx:
+        bad = ctx.eval_math(8, np.zeros(1 + 3 * 8, np.float32))
+        assert bad[0] == 0.0, f"{bad[0]:.0f} lanes differ, e.g. (argument, paired, scalar) bits: " + \
+            ", ".join(f"({a:#010x}, {b:#010x}, {c:#010x})" for a, b, c in bad[1:].view(np.uint32).reshape(-1, 3) if a or b or c)
+        # and a direct spot check of both lanes against the host libm
+        rng = np.random.default_rng(77)
+        x = np.concatenate([rng.uniform(-1.0, 1.0, 1 << 18), np.array([0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 1e-20, -1e-20, 0.49999997, 0.50000006])]).astype(np.float32)
+        import ctypes as C
+        want = np.empty_like(x)
+        pu.oracle().ssb_oracle_eval_math(2, x.ctypes.data_as(C.POINTER(C.c_float)), 0.0, want.ctypes.data_as(C.POINTER(C.c_float)), x.size)
+        for fn in (6, 7):
+            assert pu.bits_equal(ctx.eval_math(fn, x), want)
+
+
 @pytest.mark.parametrize("y", [2.4, 1.0 / 2.4])
 def test_device_powf_bit_exact(y):
     rng = np.random.default_rng(5)
