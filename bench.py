@@ -240,11 +240,13 @@ def main_ours(args, rank, local_rank, world):
         # their extra launches cost more: 11.11 vs 10.87 ms/frame); band b belongs to rank b % world
         nb = 1 * world
         bands = [sharding.tile_shard(b, nb, H) for b in range(rank, nb, world)]
-        band_opts = [host.options_for(color, W, H, total_spp, seed=1, y0=y0, y1=y1, render_mode=rmode, keep_accumulator=1) for (y0, y1) in bands if y1 > y0]
+        band_opts = [host.options_for(color, W, H, total_spp, seed=1, y0=y0, y1=y1, render_mode=rmode, keep_accumulator=1,
+                                      prebaked_textures=int(args.prebake)) for (y0, y1) in bands if y1 > y0]
         opt = band_opts[0]
     else:
         total_spp = SPP * world  # weak scaling: the job is the same frame at spp 64*N
-        opt = host.options_for(color, W, H, total_spp, seed=1, sample_begin=rank * SPP, sample_end=(rank + 1) * SPP, render_mode=rmode)
+        opt = host.options_for(color, W, H, total_spp, seed=1, sample_begin=rank * SPP, sample_end=(rank + 1) * SPP, render_mode=rmode,
+                               prebaked_textures=int(args.prebake))
     npix = W * H
 
     def device_accum_tensor():
@@ -393,7 +395,7 @@ def main_ours(args, rank, local_rank, world):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "reference scene (hard-coded geometry, shipped spectra + 4096^2 sRGB texture); per-sample seeded RNG",
             "config": {"workload": f"{SCENE} {W}x{H} spp{SPP} per GPU (job spp {total_spp}), hero-wavelength x4, variant {VARIANT} (upsampling + observer), "
-                                   f"ELS on, MAX_DEPTH 10", "parallelism": (f"row-band tiles x{world}, one NCCL reduce of f64 XYZA" if tiles else f"sample-sharded x{world}, one NCCL reduce of f64 XYZA") if world > 1 else "single GPU",
+                                   f"ELS on, MAX_DEPTH 10" + (", prebaked JH coefficient textures" if args.prebake else ""), "parallelism": (f"row-band tiles x{world}, one NCCL reduce of f64 XYZA" if tiles else f"sample-sharded x{world}, one NCCL reduce of f64 XYZA") if world > 1 else "single GPU",
                        "l2": "no flush needed: every step streams ~8 GB of path records / fold records through HBM (>> 126 MB L2)",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
@@ -439,6 +441,8 @@ def main():
                     help="multi-GPU decomposition: sample ranges (default, weak scaling) or row bands of the same frame (strong scaling)")
     ap.add_argument("--scene", default=SCENE, choices=sorted(ALGO_BYTES_PER_SAMPLE),
                     help="default = BASELINE configs[1]; the others are SURVEY 8(d) C3-C5 (not the headline)")
+    ap.add_argument("--prebake", action="store_true",
+                    help="variant jh only: ssb_options.prebaked_textures (Jakob-Hanika coefficient textures, baked once per upload)")
     ap.add_argument("--variant", default=VARIANT, choices=["ours1931", "ours2006", "meng", "jh", "rgb"])
     args = ap.parse_args()
     SCENE, VARIANT = args.scene, args.variant

@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 2u /* 2: RGB render mode (ssb_material.*_rgb, ssb_options.render_mode), n_wavelengths */
+#define SSB_ABI_VERSION 3u /* 2: RGB render mode (ssb_material.*_rgb, ssb_options.render_mode), n_wavelengths;
+                           * 3: ssb_options.prebaked_textures (was `reserved`) */
 
 #define SSB_OK 0
 #define SSB_ERR_DATA (-1)
@@ -165,7 +166,11 @@ typedef struct ssb_options {
 	                                   * glm::vec the reference compiles with).  LAMBDA_STEP = (max-min)/n (stdafx.hpp:289) */
 	uint32_t keep_accumulator;        /* 1: do not clear the accumulator although sample_begin == 0 (several pixel
 	                                   * rectangles of one frame rendered by successive ssb_render calls) */
-	uint32_t reserved;                /* must be 0 */
+	uint32_t prebaked_textures;       /* JH upsampling only (ignored otherwise).  1: rgb2spec_fetch (rgb2spec.c:77-118) runs ONCE per
+	                                   * texel into a 32-bit coefficient texture kept by the context, and shading only evaluates
+	                                   * the polynomial — the pre-process Jakob & Hanika intend, which the reference describes but
+	                                   * does not implement (color.cpp:204-216,222-223).  The coefficients are the same floats the
+	                                   * per-lookup form computes, so results do not change by a bit; costs 16 B/texel of HBM. */
 } ssb_options;
 
 typedef struct ssb_stats {

@@ -49,9 +49,21 @@ typedef struct ssbh_renderer_options {
 	const char* data_root;
 	uint32_t render_mode; /* SSB_RENDER_SPECTRAL | SSB_RENDER_RGB (RENDER_MODE_RGB, stdafx.hpp:62-90) */
 	uint32_t n_wavelengths; /* SAMPLE_WAVELENGTHS (stdafx.hpp:90): 0 = 4; 2, 3 or 4 */
+	uint32_t prebaked_textures; /* ssb_options.prebaked_textures (JH coefficient textures, color.cpp:204-216) */
+	uint32_t progressive; /* 1: render in sample slices 1,1,2,4,... and refresh the framebuffer after each (the live
+	                       * preview of the reference's window, main.cpp:316-323); the final image is unchanged */
 } ssbh_renderer_options;
 int ssbh_renderer_new(const ssbh_renderer_options* options, ssbh_renderer** out);
 int ssbh_renderer_render(ssbh_renderer* r); /* render_start() + render_wait() */
+/* The reference's asynchronous life cycle (renderer.hpp:71-81; main.cpp:313-327): start returns at once, a caller polls
+ * is_rendering / snapshot (what the reference's display loop does with framebuffer.draw()), stop asks the render to end
+ * after the slice in flight, wait joins, reports the render's error and saves the image to output_path. */
+int ssbh_renderer_start(ssbh_renderer* r);
+void ssbh_renderer_stop(ssbh_renderer* r);
+int ssbh_renderer_wait(ssbh_renderer* r);
+int ssbh_renderer_is_rendering(const ssbh_renderer* r);
+/* thread-safe copy of the current framebuffer (width*height*4 sRGBA; may be NULL) -> samples per pixel behind it */
+uint32_t ssbh_renderer_snapshot(const ssbh_renderer* r, float* srgba);
 const float* ssbh_renderer_framebuffer(const ssbh_renderer* r); /* width*height*4 sRGBA, row 0 = bottom */
 const double* ssbh_renderer_xyza(const ssbh_renderer* r);
 int ssbh_renderer_stats(const ssbh_renderer* r, ssb_stats* out);

@@ -69,7 +69,7 @@ class ssb_options(C.Structure):
                 ("max_depth", C.c_uint32), ("explicit_light_sampling", C.c_uint32),
                 ("flat_field_correction", C.c_uint32), ("eps", C.c_float), ("seed", C.c_uint64),
                 ("render_mode", C.c_uint32), ("n_wavelengths", C.c_uint32),
-                ("keep_accumulator", C.c_uint32), ("reserved", C.c_uint32)]
+                ("keep_accumulator", C.c_uint32), ("prebaked_textures", C.c_uint32)]
 
 
 class ssb_stats(C.Structure):

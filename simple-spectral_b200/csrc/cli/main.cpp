@@ -3,11 +3,15 @@
 // so that `simple_spectral_b200 --scene=cornell-srgb -w=512 -h=512 -spp=64 --output=out.png` is a drop-in for the
 // reference binary, rendering on the GPU through the Renderer façade.  The reference's compile-time variants are
 // extra, optional flags here: --variant=ours1931|ours2006|meng|jh|rgb  --seed=<n>  --device=<n>  --data-root=<dir>
-// (default data root: the current directory, like the reference's cwd-relative "data/..." paths).
+// (default data root: the current directory, like the reference's cwd-relative "data/..." paths), --prebake (Jakob-Hanika
+// coefficient textures), and --progressive [--preview=<path>]: the headless stand-in for the reference's window
+// (main.cpp:313-327) — the frame refines in sample slices and the preview file is rewritten after each one.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../host/ssb_host.hpp"
@@ -25,7 +29,9 @@ void print_usage() {
 		"    --indirect-only/-io\n"
 		"    --variant=ours1931|ours2006|meng|jh|rgb   (the reference's compile-time modes)\n"
 		"    --wavelengths=2|3|4                       (SAMPLE_WAVELENGTHS, default 4)\n"
-		"    --seed=<n>  --device=<n>  --data-root=<dir containing data/>\n");
+		"    --seed=<n>  --device=<n>  --data-root=<dir containing data/>\n"
+		"    --prebake                                 (variant jh: texel -> coefficient textures, once)\n"
+		"    --progressive [--preview=<path>]          (refine in sample slices; rewrite <path> after each)\n");
 }
 
 struct Args {
@@ -59,6 +65,7 @@ unsigned to_pos(std::string const& s) {  // util/string.hpp:55-59
 
 int main(int argc, char* argv[]) {
 	ssbh::RendererOptions o;
+	std::string preview_path;
 	try {
 		Args a;
 		for (int i = 1; i < argc; ++i) a.rest.emplace_back(argv[i]);
@@ -96,6 +103,9 @@ int main(int argc, char* argv[]) {
 		try { o.seed = std::strtoull(a.get("--seed", "--seed").c_str(), nullptr, 10); } catch (int code) { if (code != -2) throw; }
 		try { o.device = std::atoi(a.get("--device", "--device").c_str()); } catch (int code) { if (code != -2) throw; }
 		try { o.data_root = a.get("--data-root", "--data-root"); } catch (int code) { if (code != -2) throw; }
+		try { a.get("--prebake", "--prebake"); o.prebaked_textures = true; } catch (int code) { if (code != -2) throw; }
+		try { a.get("--progressive", "--progressive"); o.progressive = true; } catch (int code) { if (code != -2) throw; }
+		try { preview_path = a.get("--preview", "--preview"); o.progressive = true; } catch (int code) { if (code != -2) throw; }
 		if (!a.rest.empty()) {
 			std::fprintf(stderr, "Warning: ignoring extraneous argument(s):\n");
 			for (auto const& s : a.rest) std::fprintf(stderr, "  \"%s\"\n", s.c_str());
@@ -107,6 +117,16 @@ int main(int argc, char* argv[]) {
 	try {
 		ssbh::Renderer renderer(o);
 		renderer.render_start();
+		// the reference's display loop (main.cpp:316-323), headless: poll, and write each new preview to a file
+		if (!preview_path.empty()) {
+			ssbh::Framebuffer shot;
+			shot.res[0] = o.res[0]; shot.res[1] = o.res[1];
+			uint32_t shown = 0;
+			while (renderer.is_rendering()) {
+				if (renderer.samples_done() != shown) { shown = renderer.snapshot(shot.pixels); shot.save(preview_path); }
+				std::this_thread::sleep_for(std::chrono::milliseconds(2));
+			}
+		}
 		renderer.render_wait();
 		std::printf("%.3f Mpath-samples/s on the device (%llu samples, %.3f ms)\n",
 		            renderer.last_stats.samples / renderer.last_stats.device_ms / 1e3,

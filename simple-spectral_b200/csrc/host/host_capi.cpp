@@ -111,12 +111,32 @@ int ssbh_renderer_new(const ssbh_renderer_options* o, ssbh_renderer** out) {
 		r.render_mode = o->render_mode;
 		r.n_wavelengths = o->n_wavelengths ? o->n_wavelengths : 4u;
 		r.data_root = o->data_root ? o->data_root : ".";
+		r.prebaked_textures = o->prebaked_textures != 0;
+		r.progressive = o->progressive != 0;
 		*out = new ssbh_renderer{ new Renderer(r) };
 	});
 }
 int ssbh_renderer_render(ssbh_renderer* r) {
 	if (!r) { g_err = "ssbh_renderer_render: NULL"; return SSB_ERR_ARG; }
 	return guard([&] { r->r->render_start(); r->r->render_wait(); });
+}
+int ssbh_renderer_start(ssbh_renderer* r) {
+	if (!r) { g_err = "ssbh_renderer_start: NULL"; return SSB_ERR_ARG; }
+	return guard([&] { r->r->render_start(); });
+}
+void ssbh_renderer_stop(ssbh_renderer* r) { if (r) r->r->render_stop(); }
+int ssbh_renderer_wait(ssbh_renderer* r) {
+	if (!r) { g_err = "ssbh_renderer_wait: NULL"; return SSB_ERR_ARG; }
+	return guard([&] { r->r->render_wait(); });
+}
+int ssbh_renderer_is_rendering(const ssbh_renderer* r) { return (r && r->r->is_rendering()) ? 1 : 0; }
+uint32_t ssbh_renderer_snapshot(const ssbh_renderer* r, float* srgba) {
+	if (!r) return 0;
+	if (!srgba) return r->r->samples_done();
+	std::vector<float> tmp;
+	const uint32_t done = r->r->snapshot(tmp);
+	std::memcpy(srgba, tmp.data(), tmp.size() * sizeof(float));
+	return done;
 }
 const float* ssbh_renderer_framebuffer(const ssbh_renderer* r) { return r ? r->r->framebuffer.pixels.data() : nullptr; }
 const double* ssbh_renderer_xyza(const ssbh_renderer* r) { return (r && !r->r->xyza.empty()) ? r->r->xyza.data() : nullptr; }

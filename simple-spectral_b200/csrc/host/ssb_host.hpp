@@ -9,9 +9,12 @@
 // tests/test_host_layer.py).
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/ssb200.h"
@@ -140,12 +143,18 @@ struct RendererOptions {
 	uint64_t seed = 1;
 	int device = 0;
 	std::string data_root = ".";
+	// JH only: texel -> coefficient pre-process once per texture (ssb_options.prebaked_textures; color.cpp:204-216)
+	bool prebaked_textures = false;
+	// Progressive preview (what the reference's window shows while its tiles fill in, main.cpp:316-323): the frame is
+	// rendered in sample slices [0,1) [1,2) [2,4) [4,8) ... and `framebuffer` is refreshed after each one with the
+	// average of the samples so far.  The final image does not depend on the slicing (samples are accumulated in order).
+	bool progressive = false;
 };
 
 class Renderer {
 public:
 	RendererOptions const options;
-	Framebuffer framebuffer;
+	Framebuffer framebuffer;  // while is_rendering(): read it through snapshot()
 	ColorData color;
 	Scene scene;
 	std::vector<double> xyza;  // per-pixel double XYZA (the reference's local `avg`, renderer.cpp:292-296)
@@ -155,16 +164,28 @@ public:
 	Renderer(Renderer const&) = delete;
 	Renderer& operator=(Renderer const&) = delete;
 
-	void render_start();  // renders the frame on the GPU (the reference spawns worker threads here)
-	void render_stop() {}
-	void render_wait();   // saves the image like the reference's last worker thread (renderer.cpp:388-394)
-	bool is_rendering() const { return false; }
+	// Same life cycle as the reference (renderer.hpp:71-81, renderer.cpp:396-430): render_start() returns at once —
+	// ONE worker thread feeds the GPU where the reference spawns one thread per core —, render_stop() asks it to
+	// end after the slice in flight, render_wait() joins it, rethrows its error, and saves the image as the
+	// reference's last worker does (renderer.cpp:388-394; an aborted render is saved with what it has).
+	void render_start();
+	void render_stop() { continue_ = false; }
+	void render_wait();
+	bool is_rendering() const { return rendering_; }
+	uint32_t samples_done() const { return done_spp_; }  // spp behind the current framebuffer contents
+	uint32_t snapshot(std::vector<float>& srgba) const;  // thread-safe copy of the framebuffer; returns samples_done()
 	ssb_options make_options() const;
-	ssb_stats last_stats{};
+	ssb_stats last_stats{};  // of the whole frame (summed over slices)
 
 private:
+	void work();
 	ssb_ctx* ctx_ = nullptr;
-	bool rendered_ = false;
+	std::thread worker_;
+	mutable std::mutex fb_mutex_;
+	std::atomic<bool> continue_{ true }, rendering_{ false };
+	std::atomic<uint32_t> done_spp_{ 0 };
+	bool rendered_ = false, failed_ = false;
+	Error error_{ 0, "" };
 };
 
 }  // namespace ssbh

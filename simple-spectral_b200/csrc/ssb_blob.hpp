@@ -24,7 +24,8 @@
 #include "../../include/ssb200.h"
 
 #if !defined(__CUDACC__)
-struct uchar4;  // only pointers to it appear below
+struct uchar4;  // only pointers to them appear below
+struct float4;
 #endif
 
 namespace ssbk {
@@ -43,6 +44,7 @@ struct DevMaterial {
 struct DevTexture {
 	const uchar4* rgba;  // RGB8 re-packed to RGBA8 at upload: one aligned 4-byte load per texel
 	uint32_t width, height;
+	const float4* coef;  // ssb_options.prebaked_textures: Jakob-Hanika coefficients (c0,c1,c2,-) per texel, or nullptr
 };
 struct DevHeader {
 	uint32_t nquads, nmaterials, nlights, ntextures;

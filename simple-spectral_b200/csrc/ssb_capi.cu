@@ -101,6 +101,10 @@ struct ssb_ctx {
 	// device
 	std::vector<uchar4*> d_textures;
 	std::vector<uint32_t> tex_w, tex_h;
+	// ssb_options.prebaked_textures: per-texture Jakob-Hanika coefficient texels, baked on first use by ssb_render
+	std::vector<float4*> d_tex_coef;
+	std::vector<size_t> tex_coef_n;   // texels each buffer was allocated for
+	bool coef_valid = false;          // the buffers hold the coefficients of the current textures and JH tables
 	unsigned char* d_rgb_staging = nullptr;
 	size_t rgb_staging_capacity = 0;
 	unsigned char* d_blob = nullptr;
@@ -129,6 +133,8 @@ namespace {
 [[maybe_unused]] void free_textures(ssb_ctx* c) {
 	for (uchar4* p : c->d_textures) cudaFree(p);
 	c->d_textures.clear(); c->tex_w.clear(); c->tex_h.clear();
+	for (float4* p : c->d_tex_coef) cudaFree(p);
+	c->d_tex_coef.clear(); c->tex_coef_n.clear(); c->coef_valid = false;
 }
 
 DevSpectrum pack_spectrum(const HostSpectrum& s, std::vector<float>& pool) {
@@ -175,7 +181,10 @@ int build_blob(ssb_ctx* c) {
 		mats[m].albedo_rgb[3] = mats[m].emission_rgb[3] = 0.0f;
 	}
 	std::vector<DevTexture> texs(c->d_textures.size());
-	for (size_t t = 0; t < texs.size(); ++t) { texs[t].rgba = c->d_textures[t]; texs[t].width = c->tex_w[t]; texs[t].height = c->tex_h[t]; }
+	for (size_t t = 0; t < texs.size(); ++t) {
+		texs[t].rgba = c->d_textures[t]; texs[t].width = c->tex_w[t]; texs[t].height = c->tex_h[t];
+		texs[t].coef = t < c->d_tex_coef.size() ? c->d_tex_coef[t] : nullptr;
+	}
 
 	size_t off = align_up(sizeof(DevHeader), 16);
 	hdr.off_quads = (uint32_t)off; off = align_up(off + c->quads.size() * sizeof(ssb_quad), 16);
@@ -393,6 +402,7 @@ static int upload_scene_impl(ssb_ctx* c, const ssb_scene* scene, bool async) {
 	c->materials.swap(mats);
 	c->lights.swap(lights);
 	c->have_scene = true; c->blob_dirty = true;
+	c->coef_valid = false;  // new texels: re-baked by the next ssb_render that asks for prebaked textures
 	return SSB_OK;
 }
 
@@ -432,6 +442,7 @@ int ssb_upload_color(ssb_ctx* c, const ssb_color* color) {
 		c->have_meng = true;
 	}
 	c->have_color = true; c->blob_dirty = true;
+	c->coef_valid = false;  // the JH tables may have changed
 	return SSB_OK;
 }
 
@@ -465,6 +476,41 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	}
 	if (!rgb && o->upsampling == SSB_UPSAMPLE_JH && !c->jh_res) return fail(SSB_ERR_ARG, "JH upsampling needs the coefficient tables");
 	if (!rgb && o->upsampling == SSB_UPSAMPLE_MENG && !c->have_meng) return fail(SSB_ERR_ARG, "MENG upsampling needs the grid tables");
+	// prebaked JH coefficient textures: (re)allocate before the blob is built (it carries the pointers), bake after
+	// (the bake kernel reads the sRGB LUT from the blob)
+	const bool prebaked = !rgb && o->upsampling == SSB_UPSAMPLE_JH && o->prebaked_textures && !c->d_textures.empty();
+	uint32_t bake_launches = 0;
+	if (prebaked && !c->coef_valid) {
+		while (c->d_tex_coef.size() > c->d_textures.size()) {  // the scene was replaced by one with fewer textures
+			SSB_CUDA(cudaStreamSynchronize(c->stream));
+			cudaFree(c->d_tex_coef.back()); c->d_tex_coef.pop_back(); c->tex_coef_n.pop_back();
+			c->blob_dirty = true;
+		}
+		c->d_tex_coef.resize(c->d_textures.size(), nullptr);
+		c->tex_coef_n.resize(c->d_textures.size(), 0);
+		for (size_t t = 0; t < c->d_textures.size(); ++t) {
+			const size_t n = (size_t)c->tex_w[t] * c->tex_h[t];
+			if (c->d_tex_coef[t] && c->tex_coef_n[t] == n) continue;
+			SSB_CUDA(cudaStreamSynchronize(c->stream));  // an earlier render may still read the old buffer
+			cudaFree(c->d_tex_coef[t]); c->d_tex_coef[t] = nullptr; c->tex_coef_n[t] = 0;
+			SSB_CUDA(cudaMalloc(&c->d_tex_coef[t], n * sizeof(float4)));
+			c->tex_coef_n[t] = n;
+			c->blob_dirty = true;
+		}
+		if (c->blob_dirty && (rc = build_blob(c)) != SSB_OK) return rc;
+		if (c->tex_pending) {  // the texels of an ssb_upload_scene_async must have arrived
+			SSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tex_ready, 0));
+			c->tex_pending = false;
+		}
+		for (size_t t = 0; t < c->d_textures.size(); ++t) {
+			const size_t n = c->tex_coef_n[t];
+			const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 32);
+			ssb_bake_jh_kernel<<<grid, 256, 0, c->stream>>>(c->d_textures[t], c->d_tex_coef[t], n, c->d_blob, c->d_jh_scale, c->d_jh_data, c->jh_res);
+			SSB_CUDA(cudaGetLastError());
+			++bake_launches;
+		}
+		c->coef_valid = true;
+	}
 	if ((rc = ensure_accum(c, o->width, o->height)) != SSB_OK) return rc;
 	if (o->sample_begin == 0 && !o->keep_accumulator) SSB_CUDA(cudaMemsetAsync(c->d_accum, 0, (size_t)o->width * o->height * 4 * sizeof(double), c->stream));
 
@@ -538,6 +584,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	memcpy(P.cam_pos, c->camera.pos, sizeof(P.cam_pos));
 	memcpy(P.cam_dir, c->camera.dir, sizeof(P.cam_dir));
 	P.jh_scale = c->d_jh_scale; P.jh_data = c->d_jh_data; P.jh_res = c->jh_res;
+	P.jh_prebaked = prebaked ? 1u : 0u;
 	P.meng_grid = c->d_meng_grid; P.meng_points = c->d_meng_points;
 	P.meng_grid_w = c->meng.grid_w; P.meng_grid_h = c->meng.grid_h; P.meng_npoints = c->meng.npoints; P.meng_nsamples = c->meng.nsamples;
 	memcpy(P.meng_xy_to_uv, c->meng.xy_to_uv, sizeof(P.meng_xy_to_uv));
@@ -564,7 +611,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	const uint32_t nquads = (uint32_t)c->quads.size();
 
 	SSB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
-	uint32_t launches = 0, passes = 0;
+	uint32_t launches = bake_launches, passes = 0;
 	for (uint32_t k0 = 0; k0 < nsamp_total; k0 += chunk) {
 		const uint32_t ns = std::min(chunk, nsamp_total - k0);
 		P.sample_begin = o->sample_begin + k0;

@@ -83,6 +83,7 @@ struct KParams {
 	const float* jh_scale;
 	const float* jh_data;
 	uint32_t jh_res;
+	uint32_t jh_prebaked;  // every DevTexture::coef is valid and holds the texels' JH coefficients
 	const int32_t* meng_grid;
 	const float* meng_points;
 	uint32_t meng_grid_w, meng_grid_h, meng_npoints, meng_nsamples;
@@ -232,21 +233,20 @@ __device__ __forceinline__ int jh_find_interval(const float* values, int size_, 
 	}
 	return left < last_interval ? left : last_interval;
 }
-__device__ __noinline__ Hero jh_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
-	// rgb2spec_fetch (rgb2spec.c:77-118) + rgb2spec_eval_precise (:129-133), no FMA (parity build)
+// rgb2spec_fetch (rgb2spec.c:77-118), no FMA (parity build): l-RGB -> the three polynomial coefficients
+__device__ __forceinline__ void jh_fetch(const float* __restrict__ jh_scale, const float* __restrict__ d, int res,
+                                         float r, float g, float b, float coeff[3]) {
 	float rgb[3] = { r, g, b };
-	int i = 0, res = (int)P.jh_res;
+	int i = 0;
 	for (int j = 1; j < 3; ++j) if (rgb[j] >= rgb[i]) i = j;
 	float z = rgb[i], scale = (float)(res - 1) / z;
 	float x = rgb[(i + 1) % 3] * scale, y = rgb[(i + 2) % 3] * scale;
 	uint32_t xu = (x != x) ? 0u : (uint32_t)x, yu = (y != y) ? 0u : (uint32_t)y;  // see oracle note on NaN
 	uint32_t xi = min(xu, (uint32_t)(res - 2)), yi = min(yu, (uint32_t)(res - 2));
-	uint32_t zi = (uint32_t)jh_find_interval(P.jh_scale, res, z);
+	uint32_t zi = (uint32_t)jh_find_interval(jh_scale, res, z);
 	uint32_t offset = (((i * res + zi) * res + yi) * res + xi) * 3, dx = 3, dy = 3 * res, dz = 3 * res * res;
 	float x1 = x - (float)xi, x0 = 1.f - x1, y1 = y - (float)yi, y0 = 1.f - y1;
-	float z1 = (z - P.jh_scale[zi]) / (P.jh_scale[zi + 1] - P.jh_scale[zi]), z0 = 1.f - z1;
-	const float* d = P.jh_data;
-	float coeff[3];
+	float z1 = (z - jh_scale[zi]) / (jh_scale[zi + 1] - jh_scale[zi]), z0 = 1.f - z1;
 	for (int j = 0; j < 3; ++j) {
 		coeff[j] = ((__ldg(d + offset) * x0 + __ldg(d + offset + dx) * x1) * y0 +
 		            (__ldg(d + offset + dy) * x0 + __ldg(d + offset + dy + dx) * x1) * y1) * z0 +
@@ -254,15 +254,28 @@ __device__ __noinline__ Hero jh_upsample(const KParams& P, float r, float g, flo
 		            (__ldg(d + offset + dz + dy) * x0 + __ldg(d + offset + dz + dy + dx) * x1) * y1) * z1;
 		offset++;
 	}
+}
+// rgb2spec_eval_precise (rgb2spec.c:129-133) at the hero wavelengths, no FMA (parity build)
+__device__ __forceinline__ Hero jh_eval(const KParams& P, float c0, float c1, float c2, float lambda_0) {
 	Hero h;
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
 		float lambda = lambda_0 + (float)k * P.lambda_step;
-		float xx = (coeff[0] * lambda + coeff[1]) * lambda + coeff[2];
+		float xx = (c0 * lambda + c1) * lambda + c2;
 		float yy = 1.f / sqrtf(xx * xx + 1.f);
 		h.v[k] = (uint32_t)k < P.n_wavelengths ? (.5f * xx) * yy + .5f : 0.0f;
 	}
 	return h;
+}
+// Color::lrgb_to_specrefl, JH build (color.cpp:202-232): both steps per lookup, as the reference does
+__device__ __noinline__ Hero jh_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
+	float coeff[3];
+	jh_fetch(P.jh_scale, P.jh_data, (int)P.jh_res, r, g, b, coeff);
+	return jh_eval(P, coeff[0], coeff[1], coeff[2], lambda_0);
+}
+// the second step alone, on coefficients fetched once per texel by ssb_bake_jh_kernel (ssb_options.prebaked_textures)
+__device__ __noinline__ Hero jh_eval_baked(const KParams& P, float4 cf, float lambda_0) {
+	return jh_eval(P, cf.x, cf.y, cf.z, lambda_0);
 }
 // spectrum_xyz_to_p (meng-et-al.-2015/spectrum_grid.h:13-137)
 __device__ __noinline__ float meng_xyz_to_p(const KParams& P, float lambda, const float* xyz) {
@@ -364,7 +377,10 @@ __device__ __forceinline__ Hero material_albedo(const KParams& P, const SceneVie
 	int i = (int)floorf(index_x), j = (int)floorf(index_y);
 	i = max(i, 0); i = min(i, (int)tex.width - 1);
 	j = max(j, 0); j = min(j, (int)tex.height - 1);
-	uchar4 px = __ldg(tex.rgba + ((size_t)j * tex.width + (size_t)i));
+	const size_t texel = (size_t)j * tex.width + (size_t)i;
+	if (UPS == SSB_UPSAMPLE_JH && P.jh_prebaked)  // uniform: the texel's coefficients were fetched once, at bake time
+		return jh_eval_baked(P, __ldg(tex.coef + texel), lambda_0);
+	uchar4 px = __ldg(tex.rgba + texel);
 	float r = S.hdr()->srgb_lut[px.x], g = S.hdr()->srgb_lut[px.y], b = S.hdr()->srgb_lut[px.z];
 	if (UPS == SSB_UPS_RGB) {  // material.cpp:64-66: the texel's l-RGB is the reflectance
 		Hero h; h.v[0] = r; h.v[1] = g; h.v[2] = b; h.v[3] = 0.0f;
@@ -1115,6 +1131,21 @@ __global__ void ssb_repack_rgb8_kernel(const unsigned char* __restrict__ rgb, uc
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	rgba[i] = make_uchar4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 255);
+}
+
+// ssb_options.prebaked_textures: the first step of Color::lrgb_to_specrefl's JH build (texel -> sRGB LUT -> rgb2spec_fetch,
+// material.cpp:51-55 + color.cpp:218-220) once per texel; the 32-bit coefficient texture the reference's comment
+// (color.cpp:204-216,222-223) describes.  Same device function as the per-lookup path: the same floats.
+__global__ void __launch_bounds__(256) ssb_bake_jh_kernel(const uchar4* __restrict__ rgba, float4* __restrict__ coef, size_t n,
+                                                          const unsigned char* __restrict__ blob, const float* __restrict__ jh_scale,
+                                                          const float* __restrict__ jh_data, uint32_t jh_res) {
+	const float* lut = reinterpret_cast<const DevHeader*>(blob)->srgb_lut;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const uchar4 px = rgba[i];
+		float c[3];
+		jh_fetch(jh_scale, jh_data, (int)jh_res, __ldg(lut + px.x), __ldg(lut + px.y), __ldg(lut + px.z), c);
+		coef[i] = make_float4(c[0], c[1], c[2], 0.0f);
+	}
 }
 
 __global__ void ssb_eval_math_kernel(uint32_t fn, const float* __restrict__ x, float arg, float* __restrict__ out, size_t n) {

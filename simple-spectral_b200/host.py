@@ -14,14 +14,16 @@ class ssbh_renderer_options(C.Structure):
                 ("indirect_only", C.c_uint32), ("output_path", C.c_char_p), ("observer", C.c_int),
                 ("upsampling", C.c_uint32), ("explicit_light_sampling", C.c_uint32), ("max_depth", C.c_uint32),
                 ("flat_field_correction", C.c_uint32), ("seed", C.c_uint64), ("device", C.c_int),
-                ("data_root", C.c_char_p), ("render_mode", C.c_uint32), ("n_wavelengths", C.c_uint32)]
+                ("data_root", C.c_char_p), ("render_mode", C.c_uint32), ("n_wavelengths", C.c_uint32),
+                ("prebaked_textures", C.c_uint32), ("progressive", C.c_uint32)]
 
 
 HOST_SYMBOLS = (
     "ssbh_last_error", "ssbh_color_init", "ssbh_color_flat", "ssbh_color_query", "ssbh_color_spectrum", "ssbh_color_free",
     "ssbh_scene_new", "ssbh_scene_flat", "ssbh_scene_camera", "ssbh_scene_free", "ssbh_load_png_rgb8", "ssbh_free",
     "ssbh_save_image", "ssbh_renderer_new", "ssbh_renderer_render", "ssbh_renderer_framebuffer", "ssbh_renderer_xyza",
-    "ssbh_renderer_stats", "ssbh_renderer_free",
+    "ssbh_renderer_stats", "ssbh_renderer_free", "ssbh_renderer_start", "ssbh_renderer_stop", "ssbh_renderer_wait",
+    "ssbh_renderer_is_rendering", "ssbh_renderer_snapshot",
 )
 
 
@@ -58,6 +60,16 @@ def hostlib():
     L.ssbh_renderer_stats.argtypes = [C.c_void_p, P(_abi.ssb_stats)]
     L.ssbh_renderer_free.argtypes = [C.c_void_p]
     L.ssbh_renderer_free.restype = None
+    L.ssbh_renderer_start.argtypes = [C.c_void_p]
+    L.ssbh_renderer_start.restype = C.c_int
+    L.ssbh_renderer_stop.argtypes = [C.c_void_p]
+    L.ssbh_renderer_stop.restype = None
+    L.ssbh_renderer_wait.argtypes = [C.c_void_p]
+    L.ssbh_renderer_wait.restype = C.c_int
+    L.ssbh_renderer_is_rendering.argtypes = [C.c_void_p]
+    L.ssbh_renderer_is_rendering.restype = C.c_int
+    L.ssbh_renderer_snapshot.argtypes = [C.c_void_p, P(C.c_float)]
+    L.ssbh_renderer_snapshot.restype = C.c_uint32
     for n in ("ssbh_color_init", "ssbh_color_query", "ssbh_color_spectrum", "ssbh_scene_new", "ssbh_scene_camera",
               "ssbh_load_png_rgb8", "ssbh_save_image", "ssbh_renderer_new", "ssbh_renderer_render", "ssbh_renderer_stats"):
         getattr(L, n).restype = C.c_int
@@ -183,19 +195,44 @@ class Renderer:
 
     def __init__(self, scene_name, width, height, spp, output_path=None, indirect_only=False, variant="ours1931",
                  explicit_light_sampling=True, max_depth=10, flat_field_correction=True, seed=1, device=0, data_root=None,
-                 n_wavelengths=4):
+                 n_wavelengths=4, prebaked_textures=False, progressive=False):
         obs, ups = VARIANTS[variant]
         self._keep = (scene_name.encode(), output_path.encode() if output_path else None, (data_root or find_data_root()).encode())
         o = ssbh_renderer_options(self._keep[0], width, height, spp, int(indirect_only), self._keep[1], obs, ups,
                                   int(explicit_light_sampling), max_depth, int(flat_field_correction), seed, device, self._keep[2],
-                                  _abi.SSB_RENDER_RGB if variant == "rgb" else _abi.SSB_RENDER_SPECTRAL, n_wavelengths)
+                                  _abi.SSB_RENDER_RGB if variant == "rgb" else _abi.SSB_RENDER_SPECTRAL, n_wavelengths,
+                                  int(prebaked_textures), int(progressive))
         self._h = C.c_void_p()
         self.width, self.height = width, height
         _check(hostlib().ssbh_renderer_new(C.byref(o), C.byref(self._h)))
 
-    def render(self):
+    # the reference's asynchronous life cycle (renderer.hpp:71-81): start / poll / stop / wait
+    def start(self):
+        _check(hostlib().ssbh_renderer_start(self._h))
+
+    def stop(self):
+        hostlib().ssbh_renderer_stop(self._h)
+
+    def wait(self):
+        _check(hostlib().ssbh_renderer_wait(self._h))
+        return self._results()
+
+    def is_rendering(self):
+        return bool(hostlib().ssbh_renderer_is_rendering(self._h))
+
+    def snapshot(self):
+        """(samples per pixel behind the image, sRGBA copy of the framebuffer) — safe while rendering."""
         import numpy as np
+        fb = np.empty((self.height, self.width, 4), np.float32)
+        done = hostlib().ssbh_renderer_snapshot(self._h, fb.ctypes.data_as(C.POINTER(C.c_float)))
+        return done, fb
+
+    def render(self):
         _check(hostlib().ssbh_renderer_render(self._h))
+        return self._results()
+
+    def _results(self):
+        import numpy as np
         n = self.width * self.height * 4
         fb = np.ctypeslib.as_array(hostlib().ssbh_renderer_framebuffer(self._h), shape=(n,)).reshape(self.height, self.width, 4).copy()
         xyza = np.ctypeslib.as_array(hostlib().ssbh_renderer_xyza(self._h), shape=(n,)).reshape(self.height, self.width, 4).copy()

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_defaults():
     L = ssb.lib()
-    assert L.ssb_abi_version() == 2  # 2: RGB render mode fields
+    assert L.ssb_abi_version() == 3  # 3: ssb_options.prebaked_textures
     o = ssb.ssb_options()
     L.ssb_default_options(C.byref(o), 512, 512, 64)
     d = ssb.default_options(512, 512, 64)

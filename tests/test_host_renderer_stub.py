@@ -1,0 +1,167 @@
+"""CPU: the Renderer facade of the C++ host layer (csrc/host/host_renderer.cpp; reference src/renderer.hpp:71-81,
+renderer.cpp:396-430, main.cpp:313-327) with the device layer answered by the oracle (tests/stub/ssb_device_stub.c —
+test infrastructure, never shipped).  What is checked is the HOST logic: the worker thread's life cycle
+(start / is_rendering / stop / wait), the progressive sample slices and their previews, that slicing does not change the
+finished frame by a bit, error propagation out of the worker, and the image written at the end.
+The same life cycle runs against the CUDA path in tests/test_zz_gpu_prebake_progressive.py."""
+import ctypes as C
+import glob
+import os
+import subprocess
+import time
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+from importlib import import_module
+
+host = import_module("simple-spectral_b200.host")
+ROOT = pu.ROOT
+
+
+@pytest.fixture(scope="module")
+def stub(tmp_path_factory):
+    if not pu.have_assets():
+        pytest.skip("data files not staged (assets/data)")
+    out = str(tmp_path_factory.mktemp("stub") / "libssbh_stub.so")
+    hdir = os.path.join(ROOT, "simple-spectral_b200", "csrc", "host")
+    odir = os.path.join(ROOT, "oracle")
+    obj = out + ".stub.o"
+    subprocess.run(["gcc", "-std=c11", "-O1", "-fPIC", "-c", os.path.join(ROOT, "tests", "stub", "ssb_device_stub.c"), "-o", obj], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-o", out,
+                    *sorted(glob.glob(os.path.join(hdir, "*.cpp"))), obj, "-L", odir, "-lssb_oracle", "-lz",
+                    f"-Wl,-rpath,{odir}"], check=True)
+    L = C.CDLL(out)
+    P = C.POINTER
+    L.ssbh_last_error.restype = C.c_char_p
+    L.ssbh_renderer_new.argtypes = [P(host.ssbh_renderer_options), P(C.c_void_p)]
+    for n in ("ssbh_renderer_render", "ssbh_renderer_start", "ssbh_renderer_wait", "ssbh_renderer_is_rendering"):
+        getattr(L, n).argtypes = [C.c_void_p]
+        getattr(L, n).restype = C.c_int
+    L.ssbh_renderer_stop.argtypes = [C.c_void_p]
+    L.ssbh_renderer_stop.restype = None
+    L.ssbh_renderer_snapshot.argtypes = [C.c_void_p, P(C.c_float)]
+    L.ssbh_renderer_snapshot.restype = C.c_uint32
+    L.ssbh_renderer_framebuffer.argtypes = [C.c_void_p]
+    L.ssbh_renderer_framebuffer.restype = P(C.c_float)
+    L.ssbh_renderer_xyza.argtypes = [C.c_void_p]
+    L.ssbh_renderer_xyza.restype = P(C.c_double)
+    L.ssbh_renderer_stats.argtypes = [C.c_void_p, P(pu.abi.ssb_stats)]
+    L.ssbh_renderer_free.argtypes = [C.c_void_p]
+    L.ssbh_renderer_free.restype = None
+    return L
+
+
+W, H = 16, 12
+
+
+def _new(L, spp, progressive, output=None, scene=b"cornell"):
+    keep = (scene, output.encode() if output else None, pu.data_root().encode())
+    o = host.ssbh_renderer_options(keep[0], W, H, spp, 0, keep[1], 1931, pu.abi.SSB_UPSAMPLE_OURS, 1, 10, 1, 7, 0, keep[2],
+                                   pu.abi.SSB_RENDER_SPECTRAL, 4, 0, int(progressive))
+    h = C.c_void_p()
+    rc = L.ssbh_renderer_new(C.byref(o), C.byref(h))
+    assert rc == 0, L.ssbh_last_error()
+    h._keep = keep
+    return h
+
+
+def _results(L, h):
+    n = W * H * 4
+    fb = np.ctypeslib.as_array(L.ssbh_renderer_framebuffer(h), shape=(n,)).reshape(H, W, 4).copy()
+    xyza = np.ctypeslib.as_array(L.ssbh_renderer_xyza(h), shape=(n,)).reshape(H, W, 4).copy()
+    st = pu.abi.ssb_stats()
+    assert L.ssbh_renderer_stats(h, C.byref(st)) == 0
+    return xyza, fb, st
+
+
+def test_progressive_slices_do_not_change_the_frame(stub):
+    L = stub
+    spp = 11  # slices [0,1) [1,2) [2,4) [4,8) [8,11)
+    one = _new(L, spp, False)
+    assert L.ssbh_renderer_render(one) == 0, L.ssbh_last_error()
+    x1, f1, s1 = _results(L, one)
+    L.ssbh_renderer_free(one)
+    assert s1.launches == 1 and s1.samples == W * H * spp
+    prog = _new(L, spp, True)
+    assert L.ssbh_renderer_start(prog) == 0
+    seen = set()
+    snap = np.empty((H, W, 4), np.float32)
+    while L.ssbh_renderer_is_rendering(prog):
+        seen.add(L.ssbh_renderer_snapshot(prog, snap.ctypes.data_as(C.POINTER(C.c_float))))
+        time.sleep(0.0005)
+    assert L.ssbh_renderer_wait(prog) == 0, L.ssbh_last_error()
+    assert L.ssbh_renderer_snapshot(prog, None) == spp
+    x2, f2, s2 = _results(L, prog)
+    L.ssbh_renderer_free(prog)
+    assert seen <= {0, 1, 2, 4, 8, 11}, seen  # only whole slices are ever shown
+    assert s2.launches == 5 and s2.samples == W * H * spp
+    assert pu.bits_equal(x1, x2) and pu.bits_equal(f1, f2)
+    # ... and the frame is what the checker computes directly from the reference's dumped tables
+    flat = pu.load_flat("cornell", "ours1931")
+    opt = pu.options("ours1931", W, H, spp, seed=7)
+    xo, so = pu.oracle_resolve(flat, opt, pu.oracle_render(flat, opt)[0])
+    assert pu.bits_equal(x2, xo) and pu.bits_equal(f2, so)
+
+
+def test_preview_is_the_average_of_the_samples_so_far(stub):
+    """After the slice ending at sample n the framebuffer is the spp = n frame (renderer.cpp:296 with spp = n)."""
+    L = stub
+    full = _new(L, 2, True)  # slices [0,1) [1,2): stop after the first one is visible
+    first = _new(L, 1, False)
+    assert L.ssbh_renderer_render(first) == 0
+    _, f_first, _ = _results(L, first)
+    L.ssbh_renderer_free(first)
+    assert L.ssbh_renderer_start(full) == 0
+    snap = np.empty((H, W, 4), np.float32)
+    got_first = False
+    while L.ssbh_renderer_is_rendering(full):
+        if L.ssbh_renderer_snapshot(full, snap.ctypes.data_as(C.POINTER(C.c_float))) == 1:
+            got_first = True
+            assert pu.bits_equal(snap, f_first)
+            break
+        time.sleep(0.0002)
+    assert L.ssbh_renderer_wait(full) == 0
+    L.ssbh_renderer_free(full)
+    if not got_first:
+        pytest.skip("the two slices finished between two polls")
+
+
+def test_stop_ends_the_render_after_the_slice_in_flight_and_saves(stub, tmp_path):
+    L = stub
+    out = str(tmp_path / "aborted.pfm")
+    spp = 1 << 14  # would take minutes on the CPU checker
+    h = _new(L, spp, True, output=out)
+    assert L.ssbh_renderer_start(h) == 0
+    assert L.ssbh_renderer_start(h) == pu.abi.SSB_ERR_ARG  # one render at a time
+    t0 = time.time()
+    while L.ssbh_renderer_snapshot(h, None) < 2 and time.time() - t0 < 60:
+        time.sleep(0.001)
+    L.ssbh_renderer_stop(h)
+    assert L.ssbh_renderer_wait(h) == 0, L.ssbh_last_error()
+    assert not L.ssbh_renderer_is_rendering(h)
+    done = L.ssbh_renderer_snapshot(h, None)
+    assert 2 <= done < spp and done & (done - 1) == 0
+    x, f, st = _results(L, h)
+    assert st.samples == W * H * done
+    # the aborted render is saved with what it has (renderer.cpp:388-394), and that is the spp = done frame
+    ref = _new(L, done, False)
+    assert L.ssbh_renderer_render(ref) == 0
+    xr, fr, _ = _results(L, ref)
+    L.ssbh_renderer_free(ref)
+    assert pu.bits_equal(x, xr) and pu.bits_equal(f, fr)
+    assert os.path.getsize(out) > W * H * 12
+    # the renderer can be started again
+    L.ssbh_renderer_stop(h)
+    L.ssbh_renderer_free(h)
+
+
+def test_worker_errors_surface_in_wait(stub):
+    L = stub
+    h = _new(L, 0x7fffffff, False)  # the stub's ssb_render fails for this spp
+    assert L.ssbh_renderer_start(h) == 0
+    rc = L.ssbh_renderer_wait(h)
+    assert rc == pu.abi.SSB_ERR_DATA and b"injected" in L.ssbh_last_error()
+    assert not L.ssbh_renderer_is_rendering(h)
+    L.ssbh_renderer_free(h)
