@@ -498,17 +498,19 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			c->blob_dirty = true;
 		}
 		if (c->blob_dirty && (rc = build_blob(c)) != SSB_OK) return rc;
-		if (c->tex_pending) {  // the texels of an ssb_upload_scene_async must have arrived
-			SSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tex_ready, 0));
-			c->tex_pending = false;
-		}
+		// After an ssb_upload_scene_async the bake follows the texel copies on the COPY stream, so that it still overlaps
+		// the camera-ray stage; the first shade stage then waits for texels and coefficients together (ev_tex_ready is
+		// recorded again behind the bake).  That stream is already ordered after the last render that read the old
+		// coefficients (the upload made it wait for ev_tex_free), and the blob it reads was copied synchronously.
+		cudaStream_t bake_stream = c->tex_pending ? c->copy_stream : c->stream;
 		for (size_t t = 0; t < c->d_textures.size(); ++t) {
 			const size_t n = c->tex_coef_n[t];
 			const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 32);
-			ssb_bake_jh_kernel<<<grid, 256, 0, c->stream>>>(c->d_textures[t], c->d_tex_coef[t], n, c->d_blob, c->d_jh_scale, c->d_jh_data, c->jh_res);
+			ssb_bake_jh_kernel<<<grid, 256, 0, bake_stream>>>(c->d_textures[t], c->d_tex_coef[t], n, c->d_blob, c->d_jh_scale, c->d_jh_data, c->jh_res);
 			SSB_CUDA(cudaGetLastError());
 			++bake_launches;
 		}
+		if (c->tex_pending) SSB_CUDA(cudaEventRecord(c->ev_tex_ready, bake_stream));
 		c->coef_valid = true;
 	}
 	if ((rc = ensure_accum(c, o->width, o->height)) != SSB_OK) return rc;

@@ -159,3 +159,25 @@ def test_cli_progressive_preview(tmp_path):
     assert open(a, "rb").read() == open(b, "rb").read()
     if os.path.exists(prev):  # at least one preview was caught by the polling loop
         assert os.path.getsize(prev) == os.path.getsize(b)
+
+
+def test_spectra_on_different_grids_take_the_general_path():
+    """The observer's three spectra normally share one grid and are sampled with shared index arithmetic in the fold
+    stage (spec_sample3); tables on DIFFERENT grids (other length / range / filter; the basis' too) must take the
+    per-spectrum form and still equal the oracle."""
+    _need_assets()
+    flat = pu.load_flat("cornell-srgb", "ours1931")
+    opt = pu.options("ours1931", 24, 20, 3, seed=31)
+    same, _ = pu.oracle_resolve(flat, opt, pu.oracle_render(flat, opt)[0])
+    for name, cut, filt in (("ybar", 3, 0), ("basis_g", 5, 0), ("zbar", 0, abi.SSB_FILTER_NEAREST)):
+        s = getattr(flat.color, name)
+        data = np.ctypeslib.as_array(s.data, shape=(s.n,)).copy()
+        step = (s.high - s.low) / (s.n - 1)
+        setattr(flat.color, name, flat.spectrum(data[:s.n - cut], s.low, s.high - cut * step, filt))
+    acc_o = pu.oracle_render(flat, opt)[0]
+    xo, so = pu.oracle_resolve(flat, opt, acc_o)
+    assert not pu.bits_equal(xo, same)
+    with pu.gpu_context(flat) as ctx:
+        xg, sg = ctx.render_frame(opt)
+        acc_g = ctx.read_accum(24, 20)
+    assert pu.bits_equal(acc_g, acc_o) and pu.bits_equal(xg, xo) and pu.bits_equal(sg, so)
