@@ -71,6 +71,16 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+struct ssb_ctx;
+namespace {
+// Host -> device copy ordered on the context's stream, complete on return.  (Not cudaMemcpy: for pageable host memory
+// that returns once the data is STAGED, "the DMA to final destination may not have completed", and the context's
+// stream is non-blocking, i.e. not ordered after the legacy default stream cudaMemcpy works on.  A kernel launched
+// right after could read the tail of the previous contents — observed on the B200 in ssb_debug_eval_math: the last
+// partial block of a batch evaluated the previous batch's arguments, profiles/r4d_diag_eval_math_race.txt.)
+cudaError_t copy_to_device(ssb_ctx* c, void* dst, const void* src, size_t bytes);
+}  // namespace
+
 struct ssb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;      // the stream every kernel / copy of this context is issued on
@@ -129,6 +139,11 @@ struct ssb_ctx {
 };
 
 namespace {
+
+cudaError_t copy_to_device(ssb_ctx* c, void* dst, const void* src, size_t bytes) {
+	cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+	return e != cudaSuccess ? e : cudaStreamSynchronize(c->stream);
+}
 
 [[maybe_unused]] void free_textures(ssb_ctx* c) {
 	for (uchar4* p : c->d_textures) cudaFree(p);
@@ -425,8 +440,8 @@ int ssb_upload_color(ssb_ctx* c, const ssb_color* color) {
 		size_t res = color->jh_res, nd = 3 * res * res * res * 3;
 		SSB_CUDA(cudaMalloc(&c->d_jh_scale, res * sizeof(float)));
 		SSB_CUDA(cudaMalloc(&c->d_jh_data, nd * sizeof(float)));
-		SSB_CUDA(cudaMemcpy(c->d_jh_scale, color->jh_scale, res * sizeof(float), cudaMemcpyHostToDevice));
-		SSB_CUDA(cudaMemcpy(c->d_jh_data, color->jh_data, nd * sizeof(float), cudaMemcpyHostToDevice));
+		SSB_CUDA(copy_to_device(c, c->d_jh_scale, color->jh_scale, res * sizeof(float)));
+		SSB_CUDA(copy_to_device(c, c->d_jh_data, color->jh_data, nd * sizeof(float)));
 		c->jh_res = color->jh_res;
 	}
 	cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points); c->d_meng_grid = nullptr; c->d_meng_points = nullptr; c->have_meng = false;
@@ -436,8 +451,8 @@ int ssb_upload_color(ssb_ctx* c, const ssb_color* color) {
 		size_t ng = (size_t)m.grid_w * m.grid_h * 8, np = (size_t)m.npoints * (5 + m.nsamples);
 		SSB_CUDA(cudaMalloc(&c->d_meng_grid, ng * sizeof(int32_t)));
 		SSB_CUDA(cudaMalloc(&c->d_meng_points, np * sizeof(float)));
-		SSB_CUDA(cudaMemcpy(c->d_meng_grid, m.grid, ng * sizeof(int32_t), cudaMemcpyHostToDevice));
-		SSB_CUDA(cudaMemcpy(c->d_meng_points, m.points, np * sizeof(float), cudaMemcpyHostToDevice));
+		SSB_CUDA(copy_to_device(c, c->d_meng_grid, m.grid, ng * sizeof(int32_t)));
+		SSB_CUDA(copy_to_device(c, c->d_meng_points, m.points, np * sizeof(float)));
 		c->meng = m; c->meng.grid = nullptr; c->meng.points = nullptr;
 		c->have_meng = true;
 	}
@@ -796,7 +811,7 @@ int ssb_debug_eval_math(ssb_ctx* c, uint32_t fn, const float* x_host, float arg,
 	float *dx = nullptr, *dout = nullptr;
 	SSB_CUDA(cudaMalloc(&dx, n * sizeof(float)));
 	SSB_CUDA(cudaMalloc(&dout, n * sizeof(float)));
-	SSB_CUDA(cudaMemcpy(dx, x_host, n * sizeof(float), cudaMemcpyHostToDevice));
+	SSB_CUDA(copy_to_device(c, dx, x_host, n * sizeof(float)));
 	ssb_eval_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(fn, dx, arg, dout, n);
 	cudaError_t e = cudaStreamSynchronize(c->stream);
 	if (e == cudaSuccess) e = cudaMemcpy(out_host, dout, n * sizeof(float), cudaMemcpyDeviceToHost);
