@@ -7,6 +7,9 @@ oracle/build_ref.py from /root/reference).  Run here (the reference cannot trave
   xyza_<scene>_<variant>_<W>x<H>_spp<N>_seed<S>.npy
                                        per-pixel double XYZA of the reference at per-sample seeding
   golden_index.json                    sha256 of larger reference renders (BASELINE config 1)
+  refout_cornell_ours1931_32x24_spp4_seed7.{pfm,hdr,csv,png}
+                                       the image FILES the reference itself writes (Framebuffer::save,
+                                       framebuffer.cpp:39-176) for the small case, one per supported extension
 """
 import hashlib
 import json
@@ -52,6 +55,16 @@ def run_ref(scene, variant, w, h, spp, seed, tables=None, indirect_only=False):
         return np.fromfile(os.path.join(tmp, "xyza.bin"), dtype=np.float64).reshape(h, w, 4)
 
 
+def run_ref_outputs():
+    """The reference's own output files (--output=<path>, format by extension) at per-sample seeding."""
+    exe = os.path.join(REFBIN, "simple_spectral_ours1931_hooked")
+    for ext in ("pfm", "hdr", "csv", "png"):
+        out = os.path.join(HERE, f"refout_cornell_ours1931_{SMALL['w']}x{SMALL['h']}_spp{SMALL['spp']}_seed{SMALL['seed']}.{ext}")
+        subprocess.run([exe, "--scene=cornell", f"-w={SMALL['w']}", f"-h={SMALL['h']}", f"-spp={SMALL['spp']}", f"--output={out}"],
+                       cwd=DATA_ROOT, env=dict(os.environ, SSB_SEED=str(SMALL["seed"])), check=True, stdout=subprocess.DEVNULL)
+        print("wrote", os.path.basename(out), os.path.getsize(out), "bytes")
+
+
 def main():
     index = {}
     only = sys.argv[1:]  # optional: regenerate only these variants (the others are left untouched)
@@ -77,6 +90,8 @@ def main():
                           pixel_64_64=list(x[64, 64]))
         print(key, index[key]["sha256"])
     json.dump(index, open(os.path.join(HERE, "golden_index.json"), "w"), indent=1)
+    if not only or "ours1931" in only or "refout" in only:
+        run_ref_outputs()
 
 
 if __name__ == "__main__":

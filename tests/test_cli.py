@@ -44,3 +44,5 @@ def test_cli_renders_the_oracle_image(tmp_path, variant):
     want = str(tmp_path / "w.pfm")
     host.save_image(want, srgba)
     assert open(out, "rb").read() == open(want, "rb").read()
+    if variant == "ours1931":  # ... and the file the real reference wrote for this command line (tests/golden/refout_*)
+        assert open(out, "rb").read() == open(os.path.join(pu.GOLDEN, "refout_cornell_ours1931_32x24_spp4_seed7.pfm"), "rb").read()

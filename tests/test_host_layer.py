@@ -160,3 +160,22 @@ def test_image_writers_roundtrip(tmp_path):
     assert len(open(tmp_path / "a.csv").read().strip().split("\n")) == 6
     host.save_image(str(tmp_path / "a.hdr"), img)
     assert open(tmp_path / "a.hdr", "rb").read().startswith(b"#?RADIANCE\n")
+
+
+def test_image_writers_match_the_reference_files(tmp_path):
+    """Framebuffer::save (framebuffer.cpp:39-176) against the files the REAL reference wrote for the small golden case
+    (tests/golden/refout_*, generated by make_golden.py): PFM / HDR / CSV byte for byte, PNG pixel for pixel (the
+    reference compresses with lodepng, this layer with zlib)."""
+    flat = pu.load_flat("cornell", "ours1931")
+    opt = pu.options("ours1931", 32, 24, 4, seed=7)
+    _, srgba = pu.oracle_resolve(flat, opt, pu.oracle_render(flat, opt)[0])
+    for ext in ("pfm", "hdr", "csv", "png"):
+        ours = str(tmp_path / f"o.{ext}")
+        host.save_image(ours, srgba)
+        ref = os.path.join(pu.GOLDEN, f"refout_cornell_ours1931_32x24_spp4_seed7.{ext}")
+        if ext == "png":
+            from PIL import Image
+            a, b = Image.open(ours), Image.open(ref)
+            assert a.mode == b.mode and np.array_equal(np.asarray(a), np.asarray(b))
+        else:
+            assert open(ours, "rb").read() == open(ref, "rb").read(), ext

@@ -32,7 +32,12 @@ def stub(tmp_path_factory):
     subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-o", out,
                     *sorted(glob.glob(os.path.join(hdir, "*.cpp"))), obj, "-L", odir, "-lssb_oracle", "-lz",
                     f"-Wl,-rpath,{odir}"], check=True)
+    # the command-line front end, linked against the same stub (test_cli_stub_*)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-pthread", "-o", out[:-3] + "_cli",
+                    os.path.join(ROOT, "simple-spectral_b200", "csrc", "cli", "main.cpp"), out, f"-Wl,-rpath,{os.path.dirname(out)}",
+                    f"-Wl,-rpath,{odir}"], check=True)
     L = C.CDLL(out)
+    L._cli = out[:-3] + "_cli"
     P = C.POINTER
     L.ssbh_last_error.restype = C.c_char_p
     L.ssbh_renderer_new.argtypes = [P(host.ssbh_renderer_options), P(C.c_void_p)]
@@ -165,3 +170,22 @@ def test_worker_errors_surface_in_wait(stub):
     assert rc == pu.abi.SSB_ERR_DATA and b"injected" in L.ssbh_last_error()
     assert not L.ssbh_renderer_is_rendering(h)
     L.ssbh_renderer_free(h)
+
+
+def test_cli_writes_the_files_the_reference_writes(stub, tmp_path):
+    """The whole drop-in chain above the device layer on the CPU: command line -> host scene / colour construction ->
+    Renderer worker -> (oracle instead of the GPU) -> Framebuffer::save, against the files the REAL reference wrote for
+    the same command line at the same seed (tests/golden/refout_*): PFM / HDR / CSV byte for byte, PNG pixel for pixel.
+    Progressive slices + a preview file must not change them."""
+    from PIL import Image
+    base = [stub._cli, "--scene=cornell", "-w=32", "-h=24", "-spp=4", "--seed=7", f"--data-root={pu.data_root()}"]
+    for ext, extra in (("pfm", []), ("hdr", []), ("csv", ["--progressive"]), ("png", [f"--preview={tmp_path}/prev.png"])):
+        out = str(tmp_path / f"o.{ext}")
+        r = subprocess.run([*base, f"--output={out}", *extra], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Render completed in" in r.stdout
+        ref = os.path.join(pu.GOLDEN, f"refout_cornell_ours1931_32x24_spp4_seed7.{ext}")
+        if ext == "png":
+            assert np.array_equal(np.asarray(Image.open(out)), np.asarray(Image.open(ref)))
+        else:
+            assert open(out, "rb").read() == open(ref, "rb").read(), ext
