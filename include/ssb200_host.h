@@ -22,6 +22,12 @@ const ssb_color* ssbh_color_flat(const ssbh_color* color);
 int ssbh_color_query(const ssbh_color* color, float* lambda_min_max2, float* d65_orig_xyz3, float* d65_rad_xyz3,
                      float* lrgb_to_xyz9, float* xyz_to_lrgb9);
 int ssbh_color_spectrum(const ssbh_color* color, const char* name, ssb_spectrum* out); /* D65_orig, D65_rad, xbar, ... */
+/* Color::round_trip_srgb (color.cpp:259-294, OURS tables only): sRGB -> spectrum -> XYZ under D65 -> sRGB */
+int ssbh_color_round_trip_srgb(const ssbh_color* color, const float* srgb3, float* srgb_out3);
+/* The reference's round-trip self-test (main.cpp:246-262) for the red levels [r_begin, r_end): running_max[k] = the
+ * maximum |error| after level r_begin+k, starting from start_max.  Over 0..255 the reference documents 1.851469e-5. */
+int ssbh_color_round_trip_running_max(const ssbh_color* color, uint32_t r_begin, uint32_t r_end, float start_max,
+                                      float* running_max, uint32_t threads);
 void ssbh_color_free(ssbh_color* color);
 
 /* Scene::get_new_cornell / _cornell_srgb / _plane_srgb (scene.cpp:32-415); unknown name: -3 */

@@ -50,6 +50,11 @@ VARIANTS = {
     # MAX_DEPTH (stdafx.hpp:47) 3 instead of 10
     "ours1931_d3": dict(alg=1, observer=1931, max_depth=3),
 }
+# Not a render variant: the reference's own round-trip self-test (main.cpp:184-264, compiled out with `#if 0` upstream),
+# switched on in the scratch copy.  Built only on request (`build_ref.py roundtrip`); it prints the running maximum of the
+# sRGB -> spectrum -> sRGB error after every red level — the source of tests/golden/roundtrip_running_max.json and of the
+# one number the reference documents, 1.851469e-5 (main.cpp:242-245).
+TOOLS = {"roundtrip": dict(alg=1, observer=1931)}
 CXX_SOURCES = [
     "main.cpp", "renderer.cpp", "scene.cpp", "geometry.cpp", "material.cpp", "spectrum.cpp",
     "framebuffer.cpp", "util/color.cpp", "util/random.cpp", "util/spherical-tri.cpp",
@@ -129,7 +134,19 @@ def patch_hooks(src_dir):
     open(p, "w", encoding="utf-8").write(t)
 
 
-def build_one(tmp, name, alg, observer, hooked, lodepng_obj, **variant_kw):
+def patch_roundtrip(src_dir):
+    p = os.path.join(src_dir, "main.cpp")
+    t = open(p, encoding="utf-8-sig").read()
+    t = sub_once(t, r"#if 0 && defined RENDER_MODE_SPECTRAL", "#if 1 && defined RENDER_MODE_SPECTRAL", "round-trip block")
+    t = sub_once(t, r"#if 0(\s+float max_error = 0\.0f;)", r"#if 1\1", "round-trip loop")
+    old_print = 'printf("\\r%d (%e)   ",r,static_cast<double>(max_error));'
+    if t.count(old_print) != 1:
+        raise SystemExit("oracle/build_ref.py: patch point not found: round-trip print")
+    t = t.replace(old_print, 'printf("RUNNING %d %.9e\\n",r,static_cast<double>(max_error)); fflush(stdout);')
+    open(p, "w", encoding="utf-8").write(t)
+
+
+def build_one(tmp, name, alg, observer, hooked, lodepng_obj, roundtrip=False, **variant_kw):
     tag = name + ("_hooked" if hooked else "")
     src_dir = os.path.join(tmp, tag, "src")
     shutil.copytree(os.path.join(REF, "src"), src_dir, ignore=shutil.ignore_patterns("lodepng*"))
@@ -140,7 +157,9 @@ def build_one(tmp, name, alg, observer, hooked, lodepng_obj, **variant_kw):
     patch_variant(src_dir, alg, observer, **variant_kw)
     if hooked:
         patch_hooks(src_dir)
-    flags = FLAGS_HOOKED if hooked else FLAGS_PRISTINE
+    if roundtrip:
+        patch_roundtrip(src_dir)
+    flags = FLAGS_HOOKED if (hooked or roundtrip) else FLAGS_PRISTINE
     inc = ["-I", SHIM, "-I", os.path.join(REF, "src")]  # lodepng.h is found through the original tree
     objs = []
     for s in CXX_SOURCES:
@@ -172,6 +191,9 @@ def main():
         jobs = []
         with ThreadPoolExecutor(max_workers=4) as ex:
             for name in which:
+                if name in TOOLS:
+                    jobs.append(ex.submit(build_one, tmp, name, TOOLS[name]["alg"], TOOLS[name]["observer"], False, lodepng_obj, roundtrip=True))
+                    continue
                 v = VARIANTS[name]
                 for hooked in (False, True):
                     kw = {k: v[k] for k in ("no_els", "no_ffc", "rgb", "nw", "max_depth") if k in v}

@@ -55,6 +55,15 @@ int ssbh_color_spectrum(const ssbh_color* c, const char* name, ssb_spectrum* out
 	return SSB_OK;
 }
 
+int ssbh_color_round_trip_srgb(const ssbh_color* c, const float* srgb3, float* out3) {
+	if (!c || !srgb3 || !out3) { g_err = "ssbh_color_round_trip_srgb: NULL argument"; return SSB_ERR_ARG; }
+	return guard([&] { c->data.round_trip_srgb(srgb3, out3); });
+}
+int ssbh_color_round_trip_running_max(const ssbh_color* c, uint32_t r_begin, uint32_t r_end, float start_max, float* running_max, uint32_t threads) {
+	if (!c || !running_max || r_begin > r_end || r_end > 256) { g_err = "ssbh_color_round_trip_running_max: bad argument"; return SSB_ERR_ARG; }
+	return guard([&] { c->data.round_trip_running_max(r_begin, r_end, start_max, running_max, threads); });
+}
+
 int ssbh_scene_new(const char* name, const char* data_root, const ssbh_color* color, int explicit_light_sampling, ssbh_scene** out) {
 	if (!name || !data_root || !color || !out) { g_err = "ssbh_scene_new: NULL argument"; return SSB_ERR_ARG; }
 	*out = nullptr;

@@ -1,5 +1,6 @@
 // host_color.cpp — Color::init (reference src/util/color.cpp:26-155): observer, D65 (radiometric scaling via
 // Planck), basis / JH / Meng tables, RGB<->XYZ matrices.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -148,6 +149,53 @@ ssb_color ColorData::flat() const {
 		c.meng = m;
 	}
 	return c;
+}
+
+// ---- the reference's round-trip self-test (color.cpp:259-294, main.cpp:184-264)
+namespace {
+float srgb_to_lrgb_c(float c) { return c < 0.04045f ? c / 12.92f : std::pow((c + 0.055f) / 1.055f, 2.4f); }            // color.hpp:91-97
+float lrgb_to_srgb_c(float c) { return c < 0.0031308f ? 12.92f * c : 1.055f * std::pow(c, 1.0f / 2.4f) - 0.055f; }    // color.hpp:84-90
+}  // namespace
+
+void ColorData::round_trip_lrgb(const float lrgb[3], float out[3]) const {
+	if (basis_r.data.empty()) throw Error{ -3, "round_trip_lrgb needs the basis spectra (RENDER_MODE_SPECTRAL_OURS)" };
+	Spectrum reflectance = basis_r * lrgb[0] + basis_g * lrgb[1] + basis_b * lrgb[2];
+	Spectrum flux = D65_rad * reflectance;  // FLAT_FIELD_CORRECTION: flux = radiance (color.cpp:275-279)
+	float xyz[3] = { Spectrum::integrate(flux, std_obs_xbar), Spectrum::integrate(flux, std_obs_ybar), Spectrum::integrate(flux, std_obs_zbar) };  // color.hpp:106-111
+	const float* m = matr_xyz_to_lrgb;  // column-major; glm mat3 * vec3
+	for (int r = 0; r < 3; ++r) out[r] = m[0 + r] * xyz[0] + m[3 + r] * xyz[1] + m[6 + r] * xyz[2];
+}
+void ColorData::round_trip_srgb(const float srgb[3], float out[3]) const {
+	float lin[3] = { srgb_to_lrgb_c(srgb[0]), srgb_to_lrgb_c(srgb[1]), srgb_to_lrgb_c(srgb[2]) }, back[3];
+	round_trip_lrgb(lin, back);
+	for (int c = 0; c < 3; ++c) out[c] = lrgb_to_srgb_c(back[c]);
+}
+void ColorData::round_trip_running_max(uint32_t r_begin, uint32_t r_end, float start_max, float* running_max, unsigned threads) const {
+	if (threads == 0) threads = 1;
+	float max_error = start_max;
+	for (uint32_t r = r_begin; r < r_end; ++r) {
+		std::vector<float> part(threads, 0.0f);
+		std::vector<Error> errors(threads, Error{ 0, "" });
+		std::vector<std::thread> pool;
+		for (unsigned t = 0; t < threads; ++t)
+			pool.emplace_back([&, t] {
+				try {
+					for (uint32_t g = t; g <= 255; g += threads)
+						for (uint32_t b = 0; b <= 255; ++b) {
+							// sRGB_F32(u8 r, u8 g, u8 b) * (1.0f/255.0f)   (main.cpp:250-255)
+							float in[3] = { static_cast<float>(r) * (1.0f / 255.0f), static_cast<float>(g) * (1.0f / 255.0f), static_cast<float>(b) * (1.0f / 255.0f) }, out[3];
+							round_trip_srgb(in, out);
+							for (int c = 0; c < 3; ++c) part[t] = std::max(part[t], std::fabs(out[c] - in[c]));
+						}
+				} catch (Error const& e) { errors[t] = e; }
+			});
+		for (auto& th : pool) th.join();
+		for (unsigned t = 0; t < threads; ++t) {
+			if (errors[t].code != 0) throw errors[t];
+			max_error = std::max(max_error, part[t]);
+		}
+		running_max[r - r_begin] = max_error;
+	}
 }
 
 }  // namespace ssbh

@@ -41,6 +41,23 @@ Spectrum Spectrum::operator*(float sc) const {  // spectrum.cpp:69-73
 	for (float& f : r.data) f *= sc;
 	return r;
 }
+namespace {
+template <class Op> Spectrum combine(Spectrum const& a, Spectrum const& b, Op op) {  // spectrum.cpp:74-118
+	float lo = std::max(a.low, b.low), hi = std::min(a.high, b.high);
+	// the reference asserts equal steps and aligned ranges ("other cases are valid, but not implemented")
+	if (a.delta_lambda != b.delta_lambda || std::fmod(a.low - lo, a.delta_lambda) != 0.0f || std::fmod(b.low - lo, b.delta_lambda) != 0.0f ||
+	    std::fmod(a.high - hi, a.delta_lambda) != 0.0f || std::fmod(b.high - hi, b.delta_lambda) != 0.0f)
+		throw Error{ -3, "Spectrum arithmetic on spectra with different or misaligned sample grids is not implemented!" };
+	std::vector<float> data(static_cast<size_t>((hi - lo) / a.delta_lambda + 1));
+	for (size_t i = 0; i < data.size(); ++i) {
+		float lambda = lo + a.delta_lambda * static_cast<float>(i);
+		data[i] = op(a.sample_nearest(lambda), b.sample_nearest(lambda));
+	}
+	return Spectrum(data, lo, hi);
+}
+}  // namespace
+Spectrum Spectrum::operator*(Spectrum const& other) const { return combine(*this, other, [](float x, float y) { return x * y; }); }
+Spectrum Spectrum::operator+(Spectrum const& other) const { return combine(*this, other, [](float x, float y) { return x + y; }); }
 float Spectrum::integrate(Spectrum const& spec) {  // spectrum.cpp:120-133
 	float result = 0.0f;
 	for (float v : spec.data) result += v;

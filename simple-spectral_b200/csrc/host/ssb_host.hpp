@@ -41,6 +41,8 @@ struct Spectrum {
 	float sample_nearest(float lambda) const;
 	float sample_linear(float lambda) const;
 	Spectrum operator*(float sc) const;
+	Spectrum operator*(Spectrum const& other) const;  // spectrum.cpp:74-96 (sample-wise, on the common range)
+	Spectrum operator+(Spectrum const& other) const;  // spectrum.cpp:97-118
 	static float integrate(Spectrum const& spec);
 	static float integrate(Spectrum const& spec0, Spectrum const& spec1);
 	ssb_spectrum flat() const;
@@ -75,6 +77,16 @@ struct ColorData {
 	bool have_meng = false;
 
 	ssb_color flat() const;  // pointers into this object
+
+	// Color::round_trip_lrgb / round_trip_srgb (color.cpp:259-294, OURS only): colour -> spectrum by the basis ->
+	// D65 reflected off it -> XYZ by integration against the observer -> colour.  The reference's self-test
+	// (main.cpp:184-264) documents its maximum error over all 2^24 sRGB values: 1.851469e-5.
+	void round_trip_lrgb(const float lrgb[3], float out[3]) const;
+	void round_trip_srgb(const float srgb[3], float out[3]) const;
+	// the self-test's loop for red levels [r_begin, r_end): running_max[k] = the maximum error after level r_begin + k,
+	// starting from `start_max` (main.cpp:246-262); green levels are spread over `threads` threads (a maximum does not
+	// depend on the order)
+	void round_trip_running_max(uint32_t r_begin, uint32_t r_end, float start_max, float* running_max, unsigned threads) const;
 };
 // Color::init(): observer 1931|2006, upsampling SSB_UPSAMPLE_*; data_root contains "data/"
 ColorData color_init(std::string const& data_root, int observer, uint32_t upsampling);

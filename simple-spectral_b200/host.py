@@ -23,7 +23,7 @@ HOST_SYMBOLS = (
     "ssbh_scene_new", "ssbh_scene_flat", "ssbh_scene_camera", "ssbh_scene_free", "ssbh_load_png_rgb8", "ssbh_free",
     "ssbh_save_image", "ssbh_renderer_new", "ssbh_renderer_render", "ssbh_renderer_framebuffer", "ssbh_renderer_xyza",
     "ssbh_renderer_stats", "ssbh_renderer_free", "ssbh_renderer_start", "ssbh_renderer_stop", "ssbh_renderer_wait",
-    "ssbh_renderer_is_rendering", "ssbh_renderer_snapshot",
+    "ssbh_renderer_is_rendering", "ssbh_renderer_snapshot", "ssbh_color_round_trip_srgb", "ssbh_color_round_trip_running_max",
 )
 
 
@@ -39,6 +39,10 @@ def hostlib():
     L.ssbh_color_flat.restype = P(_abi.ssb_color)
     L.ssbh_color_query.argtypes = [C.c_void_p] + [P(C.c_float)] * 5
     L.ssbh_color_spectrum.argtypes = [C.c_void_p, C.c_char_p, P(_abi.ssb_spectrum)]
+    L.ssbh_color_round_trip_srgb.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
+    L.ssbh_color_round_trip_srgb.restype = C.c_int
+    L.ssbh_color_round_trip_running_max.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, P(C.c_float), C.c_uint32]
+    L.ssbh_color_round_trip_running_max.restype = C.c_int
     L.ssbh_color_free.argtypes = [C.c_void_p]
     L.ssbh_color_free.restype = None
     L.ssbh_scene_new.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, P(C.c_void_p)]
@@ -121,6 +125,20 @@ class Color:
         s = _abi.ssb_spectrum()
         _check(hostlib().ssbh_color_spectrum(self._h, name.encode(), C.byref(s)))
         return np.ctypeslib.as_array(s.data, shape=(s.n,)).copy(), s.low, s.high
+
+    def round_trip_srgb(self, srgb):
+        """Color::round_trip_srgb (color.cpp:290-294)."""
+        a, out = (C.c_float * 3)(*srgb), (C.c_float * 3)()
+        _check(hostlib().ssbh_color_round_trip_srgb(self._h, a, out))
+        return tuple(out)
+
+    def round_trip_running_max(self, r_begin, r_end, start_max=0.0, threads=0):
+        """The reference's round-trip self-test (main.cpp:246-262) for red levels [r_begin, r_end)."""
+        import numpy as np
+        out = np.empty(r_end - r_begin, np.float32)
+        _check(hostlib().ssbh_color_round_trip_running_max(self._h, r_begin, r_end, start_max, out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                           threads or (os.cpu_count() or 1)))
+        return out
 
     def close(self):
         if self._h:

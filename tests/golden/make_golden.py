@@ -7,6 +7,11 @@ oracle/build_ref.py from /root/reference).  Run here (the reference cannot trave
   xyza_<scene>_<variant>_<W>x<H>_spp<N>_seed<S>.npy
                                        per-pixel double XYZA of the reference at per-sample seeding
   golden_index.json                    sha256 of larger reference renders (BASELINE config 1)
+  roundtrip_running_max.json           the reference's OWN round-trip self-test (main.cpp:184-264, `#if 0` upstream,
+                                       enabled by `oracle/build_ref.py roundtrip`): running maximum of the
+                                       sRGB -> spectrum -> sRGB error after each of the 256 red levels; its last value
+                                       is the one number the reference documents (1.851469e-5, main.cpp:242-245).
+                                       Takes ~8 minutes: only with `make_golden.py roundtrip`
   refout_cornell_ours1931_32x24_spp4_seed7.{pfm,hdr,csv,png}
                                        the image FILES the reference itself writes (Framebuffer::save,
                                        framebuffer.cpp:39-176) for the small case, one per supported extension
@@ -65,7 +70,31 @@ def run_ref_outputs():
         print("wrote", os.path.basename(out), os.path.getsize(out), "bytes")
 
 
+def run_ref_roundtrip():
+    exe = os.path.join(REFBIN, "simple_spectral_roundtrip")
+    if not os.path.exists(exe):
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "build_ref.py"), "roundtrip"], check=True)
+    if os.environ.get("SSB_ROUNDTRIP_LOG"):  # stdout of an earlier run of that binary
+        out = open(os.environ["SSB_ROUNDTRIP_LOG"]).read()
+    else:
+        with tempfile.TemporaryDirectory() as tmp:
+            out = subprocess.run([exe, "--scene=cornell", "-w=4", "-h=4", "-spp=1", f"--output={tmp}/o.pfm"], cwd=DATA_ROOT,
+                                 check=True, capture_output=True, text=True).stdout
+    vals = {}
+    for line in out.split("\n"):
+        if line.startswith("RUNNING "):
+            _, r, v = line.split()
+            vals[int(r)] = v
+    assert sorted(vals) == list(range(256)), "incomplete round-trip log"
+    json.dump({"source": "reference src/main.cpp:246-262 (round-trip self-test), CIE 1931, OURS, g++ -O2 -ffp-contract=off",
+               "running_max": [vals[r] for r in range(256)]},
+              open(os.path.join(HERE, "roundtrip_running_max.json"), "w"), indent=0)
+    print("wrote roundtrip_running_max.json, final", vals[255])
+
+
 def main():
+    if sys.argv[1:] == ["roundtrip"]:
+        return run_ref_roundtrip()
     index = {}
     only = sys.argv[1:]  # optional: regenerate only these variants (the others are left untouched)
     if only and os.path.exists(os.path.join(HERE, "golden_index.json")):

@@ -179,3 +179,26 @@ def test_image_writers_match_the_reference_files(tmp_path):
             assert a.mode == b.mode and np.array_equal(np.asarray(a), np.asarray(b))
         else:
             assert open(ours, "rb").read() == open(ref, "rb").read(), ext
+
+
+def test_round_trip_self_test_reproduces_the_reference_and_its_documented_number():
+    """The reference's one documented number: the sRGB -> spectrum -> sRGB round trip over all 2^24 colours has a maximum
+    error of 1.851469e-5 (main.cpp:242-245).  tests/golden/roundtrip_running_max.json holds what the REAL reference prints
+    when that self-test (main.cpp:246-262, compiled out upstream) is switched on: the running maximum after each red level.
+    The host layer's Color::init tables + _Spectrum arithmetic + integrate + round_trip_srgb must reproduce it bit for bit:
+    the first levels from scratch, and every level at which the maximum rises (continued from the reference's previous
+    value).  SSB_FULL_ROUNDTRIP=1 runs all 256 levels (~3 minutes)."""
+    import json
+    ref = np.array([float(v) for v in json.load(open(os.path.join(pu.GOLDEN, "roundtrip_running_max.json")))["running_max"]], np.float32)
+    assert ref.size == 256 and f"{ref[-1]:.6e}" == "1.851469e-05"
+    color = host.Color(pu.data_root(), 1931, ssb.SSB_UPSAMPLE_OURS)
+    assert pu.bits_equal(np.array(color.round_trip_srgb((1.0, 1.0, 1.0)), np.float32), np.array([0.99999994, 0.9999998, 0.9999998], np.float32))
+    if os.environ.get("SSB_FULL_ROUNDTRIP"):
+        assert pu.bits_equal(color.round_trip_running_max(0, 256), ref)
+        return
+    assert pu.bits_equal(color.round_trip_running_max(0, 3), ref[:3])
+    rises = [r for r in range(3, 256) if ref[r] != ref[r - 1]]
+    assert rises, "the reference's maximum never rises after level 2?"
+    for r in rises + [200]:
+        got = color.round_trip_running_max(r, r + 1, start_max=float(ref[r - 1]))
+        assert pu.bits_equal(got, ref[r:r + 1]), r
