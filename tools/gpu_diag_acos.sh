@@ -1,4 +1,7 @@
 #!/bin/bash
+# On the GPU box: tools/diag_acos_pairs.py on the current build, the rest of tests/test_gpu_parity.py, and the same diagnosis on a
+# prebuilt scalar-acosf variant (variants/libssb200_pairs0.so from `tools/ab.py build pairs0=SSB_ACOS_PAIRS=0`).
+# This is the call that showed the r4d stream-ordering race (profiles/r4d_diag_eval_math_race.txt).
 set -u
 TAG=${1:-fin4}; OUT=gpurun_out; mkdir -p $OUT
 timeout 40 python tools/diag_acos_pairs.py > $OUT/${TAG}_diag_cur.txt 2>&1; echo "diag rc=$?"; cat $OUT/${TAG}_diag_cur.txt | cut -c1-300

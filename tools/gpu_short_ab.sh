@@ -1,7 +1,7 @@
 #!/bin/bash
 # On the GPU box (short slot): A/B of prebuilt variants (frame checksum per variant), the newest GPU tests, and the
 # Jakob-Hanika config with prebaked textures (end-to-end leg: bake on the copy stream).
-# Usage: tools/gpu_final2.sh <tag> <variant names...>
+# Usage: tools/gpu_short_ab.sh <tag> <variant names...>
 set -u
 TAG=${1:-fin2}; shift; OUT=gpurun_out; mkdir -p $OUT
 timeout 150 python tools/ab.py run "$@" 2>&1 | tee $OUT/${TAG}_ab.txt

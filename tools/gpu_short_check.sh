@@ -1,7 +1,7 @@
 #!/bin/bash
 # On the GPU box, for a SHORT slot (a few minutes): the newest GPU tests + a representative slice of the parity suites,
 # the headline bench line, and the Jakob-Hanika config with and without prebaked coefficient textures.  Most important first.
-# Usage: tools/gpu_final.sh <tag>      outputs -> gpurun_out/<tag>_*
+# Usage: tools/gpu_short_check.sh <tag>      outputs -> gpurun_out/<tag>_*
 set -u
 TAG=${1:-fin}; OUT=gpurun_out; mkdir -p $OUT
 timeout 200 python -m pytest tests/test_zz_gpu_prebake_progressive.py tests/test_gpu_options.py \
