@@ -539,7 +539,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 
 	// ---- size one pass: N = npix_rect * chunk samples share the wavefront buffers
 	const uint32_t nrec_depths = o->max_depth > 1 ? o->max_depth - 1 : 1;
-	const size_t bytes_per_sample = 2 * (32 + 32) + 32 + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (4 + 4);
+	const size_t bytes_per_sample = 2 * (32 + 32) + 32 + (SSB_FUSED_TRACE ? 32 : 0) + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (4 + 4);
 	size_t budget = kWaveBudgetBytes;
 	if (const char* e = getenv("SSB_WAVE_BUDGET_MB")) {  // tests force multi-pass rendering with a tiny budget
 		long mb = atol(e);
@@ -554,6 +554,9 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	const size_t o_a0 = off; off += up(N * 32); const size_t o_a1 = off; off += up(N * 32);
 	const size_t o_r0 = off; off += up(N * 32); const size_t o_r1 = off; off += up(N * 32);
 	const size_t o_h = off; off += up(N * 32);
+#if SSB_FUSED_TRACE
+	const size_t o_h2 = off; off += up(N * 32);  // closest-hit records ping-pong (ssb_shade_trace_kernel)
+#endif
 	const size_t o_sl = off; off += up(N * nrec_depths * 16);
 	const size_t o_sf = off; off += up(N * nrec_depths * 16);
 	const size_t o_sn = off; off += up(N * nrec_depths * 8);
@@ -577,6 +580,9 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.recA[0] = reinterpret_cast<float4*>(wv + o_a0); P.recA[1] = reinterpret_cast<float4*>(wv + o_a1);
 	P.recR[0] = reinterpret_cast<float4*>(wv + o_r0); P.recR[1] = reinterpret_cast<float4*>(wv + o_r1);
 	P.recH = reinterpret_cast<float4*>(wv + o_h);
+#if SSB_FUSED_TRACE
+	P.recH2 = reinterpret_cast<float4*>(wv + o_h2);
+#endif
 	P.stk_local = reinterpret_cast<float4*>(wv + o_sl); P.stk_f = reinterpret_cast<float4*>(wv + o_sf);
 	P.stk_np = reinterpret_cast<float2*>(wv + o_sn);
 	P.leaf = reinterpret_cast<float4*>(wv + o_leaf); P.meta = reinterpret_cast<float2*>(wv + o_meta);
@@ -616,6 +622,14 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 		case SSB_UPSAMPLE_JH: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_JH>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_JH>; break;
 		default: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_MENG>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_MENG>; break;
 	}
+#if SSB_FUSED_TRACE
+	switch (rgb ? (uint32_t)SSB_UPS_RGB : o->upsampling) {  // the experiment's stage: shading + the next depth's closest-hit queries
+		case SSB_UPS_RGB: k_shade_first = ssb_shade_trace_kernel<true, SSB_UPS_RGB>; k_shade_next = ssb_shade_trace_kernel<false, SSB_UPS_RGB>; break;
+		case SSB_UPSAMPLE_OURS: k_shade_first = ssb_shade_trace_kernel<true, SSB_UPSAMPLE_OURS>; k_shade_next = ssb_shade_trace_kernel<false, SSB_UPSAMPLE_OURS>; break;
+		case SSB_UPSAMPLE_JH: k_shade_first = ssb_shade_trace_kernel<true, SSB_UPSAMPLE_JH>; k_shade_next = ssb_shade_trace_kernel<false, SSB_UPSAMPLE_JH>; break;
+		default: k_shade_first = ssb_shade_trace_kernel<true, SSB_UPSAMPLE_MENG>; k_shade_next = ssb_shade_trace_kernel<false, SSB_UPSAMPLE_MENG>; break;
+	}
+#endif
 	kfn k_isect_first = ssb_intersect_kernel<true>, k_isect_next = ssb_intersect_kernel<false>;
 	int occ_sf = 0, occ_sn = 0, occ_if = 0, occ_in = 0;
 	for (kfn k : { k_shade_first, k_shade_next, k_isect_first, k_isect_next })
@@ -647,6 +661,9 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			const unsigned long long want_s = (P.total_work + SSB_SHADE_THREADS - 1) / SSB_SHADE_THREADS;
 			const unsigned grid_i = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_if : occ_in), want_i);
 			const unsigned grid_s = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_sf : occ_sn), want_s);
+#if SSB_FUSED_TRACE
+			if (d == 0)  // depths >= 1: the previous depth's fused stage already produced the closest-hit records
+#endif
 			(d == 0 ? k_isect_first : k_isect_next)<<<grid_i, SSB_INTERSECT_THREADS, smem, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
 			if (c->tex_pending) {  // texels are first read by the shade stage: the camera-ray queries overlap the upload
@@ -660,7 +677,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			SSB_CUDA(cudaGetLastError());
 			(d == 0 ? k_shade_first : k_shade_next)<<<grid_s, SSB_SHADE_THREADS, smem, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
-			launches += 4;
+			launches += (SSB_FUSED_TRACE && d > 0) ? 3 : 4;
 		}
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes + 1], c->stream));
 		ssb_fold_kernel<<<(unsigned)((P.total_work + 255) / 256), 256, 0, c->stream>>>(P);
