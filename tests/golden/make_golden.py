@@ -110,7 +110,9 @@ def main():
     if not only or "ours1931" in only:
         x = run_ref("cornell-srgb", "ours1931", indirect_only=True, **SMALL)
         np.save(os.path.join(HERE, f"xyza_cornell-srgb_ours1931_indirect_{SMALL['w']}x{SMALL['h']}_spp{SMALL['spp']}_seed{SMALL['seed']}.npy"), x)
-    for scene, variant in (("cornell-srgb", "ours1931"), ("cornell", "ours1931"), ("cornell-srgb", "rgb")):
+    # BASELINE.json configs[0]'s size for its own variant, the RGB build, and the variants of configs[2..4]
+    for scene, variant in (("cornell-srgb", "ours1931"), ("cornell", "ours1931"), ("cornell-srgb", "rgb"),
+                           ("cornell", "ours2006"), ("plane-srgb", "jh"), ("cornell-srgb", "meng")):
         if only and variant not in only:
             continue
         x = run_ref(scene, variant, **C1)

@@ -69,6 +69,20 @@ def test_oracle_rgb_config1_sha():
     assert hashlib.sha256(avg.tobytes()).hexdigest() == idx["sha256"]
 
 
+@pytest.mark.parametrize("scene,variant", [("cornell", "ours2006"), ("plane-srgb", "jh"), ("cornell-srgb", "meng")])
+def test_oracle_config1_size_sha_of_the_other_baseline_variants(scene, variant):
+    """The variants BASELINE.json configs[2..4] are quoted on (CIE 2006 observer, Jakob-Hanika, Meng et al.) at
+    configs[0]'s size, 128x128 spp16: sha256 of the real reference's XYZA buffer."""
+    if pu.needs_assets(scene, variant) and not pu.have_assets():
+        pytest.skip("data files not staged")
+    idx = json.load(open(os.path.join(pu.GOLDEN, "golden_index.json")))[f"{scene}_{variant}_128x128_spp16_seed1"]
+    flat = pu.load_flat(scene, variant)
+    opt = pu.options(variant, 128, 128, 16, seed=1)
+    acc, _, _ = pu.oracle_render(flat, opt)
+    xyza, _ = pu.oracle_resolve(flat, opt, acc)
+    assert hashlib.sha256(xyza.tobytes()).hexdigest() == idx["sha256"]
+
+
 def test_sample_subsets_compose():
     """Tiles and sample ranges accumulate to the same buffer as one full render (multi-GPU sharding)."""
     flat = pu.load_flat("cornell", "ours1931")

@@ -181,3 +181,19 @@ def test_spectra_on_different_grids_take_the_general_path():
         xg, sg = ctx.render_frame(opt)
         acc_g = ctx.read_accum(24, 20)
     assert pu.bits_equal(acc_g, acc_o) and pu.bits_equal(xg, xo) and pu.bits_equal(sg, so)
+
+
+@pytest.mark.parametrize("scene,variant", [("cornell", "ours2006"), ("plane-srgb", "jh"), ("cornell-srgb", "meng")])
+def test_config1_size_sha_of_the_other_baseline_variants(scene, variant):
+    """128x128 spp16 frames of the variants BASELINE.json configs[2..4] are quoted on: sha256 of the XYZA buffer the REAL
+    reference produced (tests/golden/golden_index.json; the oracle is pinned to the same hashes on the CPU).  JH: also
+    with prebaked coefficient textures."""
+    import hashlib
+    import json
+    _need_assets()
+    want = json.load(open(os.path.join(pu.GOLDEN, "golden_index.json")))[f"{scene}_{variant}_128x128_spp16_seed1"]["sha256"]
+    flat = pu.load_flat(scene, variant)
+    with pu.gpu_context(flat) as ctx:
+        for prebaked in ((0, 1) if variant == "jh" else (0,)):
+            x, _ = ctx.render_frame(pu.options(variant, 128, 128, 16, seed=1, prebaked_textures=prebaked))
+            assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() == want, (variant, prebaked)
