@@ -461,9 +461,17 @@ SSB_ISECT_FN void resolve_single_chunk(const SceneView& S, float eps, int ignore
 	}
 }
 
+#ifndef SSB_ISECT2_INLINE
+#define SSB_ISECT2_INLINE 0  // 1: inline scene_intersect2 into its (single) call site instead of calling it
+#endif
+#if SSB_ISECT2_INLINE
+#define SSB_ISECT2_ATTR SSB_ISECT_FN
+#else
+#define SSB_ISECT2_ATTR SSB_ISECT_NOINLINE
+#endif
 // Closest hits of two rays that share origin and `ignore` (act0 / act1: whether each ray exists; the filter is evaluated
 // for both regardless, converged).  Each hit record is scene_intersect's for that ray, bit for bit (tools/isect_check.cpp).
-SSB_ISECT_NOINLINE void scene_intersect2(const SceneView& S, float eps, int ignore, Hit& hit0, Hit& hit1, bool act0, bool act1,
+SSB_ISECT2_ATTR void scene_intersect2(const SceneView& S, float eps, int ignore, Hit& hit0, Hit& hit1, bool act0, bool act1,
                                          float ox, float oy, float oz, float d0x, float d0y, float d0z, float d1x, float d1y, float d1z) {
 	const DevHeader* H = S.hdr();
 	const int nent = (int)H->nentries;
