@@ -6,6 +6,8 @@
   box  :  tools/ab.py run [name ...]                         -> per variant: ms/frame of the headline frame (CUDA events,
                                                                median of 7 after 3 warm frames), Msamples/s, and the sha256 of
                                                                the f64 XYZA accumulators — every variant must print the SAME hash
+  box  :  tools/ab.py test name [pytest args ...]            -> the GPU test suite (default: tests -m gpu -x -q) with that variant
+                                                               in place of the library
 The variant is copied over simple-spectral_b200/libssb200.so for its run (each run is its own process); the original is
 restored at the end."""
 import os
@@ -83,7 +85,20 @@ def run(names):
         os.remove(backup)
 
 
+def test(args):
+    name, pytest_args = args[0], (args[1:] or ["tests", "-m", "gpu", "-x", "-q"])
+    backup = LIB + ".orig"
+    shutil.copyfile(LIB, backup)
+    try:
+        shutil.copyfile(os.path.join(VDIR, f"libssb200_{name}.so"), LIB)
+        rc = subprocess.run([sys.executable, "-m", "pytest", *pytest_args], cwd=ROOT).returncode
+    finally:
+        shutil.copyfile(backup, LIB)
+        os.remove(backup)
+    sys.exit(rc)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) < 2 or sys.argv[1] not in ("build", "run"):
+    if len(sys.argv) < 2 or sys.argv[1] not in ("build", "run", "test") or (sys.argv[1] == "test" and len(sys.argv) < 3):
         sys.exit(__doc__)
-    (build if sys.argv[1] == "build" else run)(sys.argv[2:])
+    {"build": build, "run": run, "test": test}[sys.argv[1]](sys.argv[2:])
