@@ -10,7 +10,7 @@ unpinned dependency (cmake/FindGLM.cmake) and is not installed.  We compile agai
 oracle/glm_shim (our restatement of GLM 0.9.9 scalar semantics for the ~20 functions
 the reference uses).  The reference's CMake build is NOT run.
 
-Outputs (per variant v in ours1931, ours2006, meng, jh, ours1931_noels, rgb, ours1931_nw3, meng_nw2, ours1931_d3):
+Outputs (per variant v in ours1931, ours2006, meng, jh, ours1931_noels, ours1931_noffc, rgb, ours1931_nw3, meng_nw2, ours1931_d3):
   oracle/_ref/simple_spectral_<v>          pristine sources, -O3 -march=x86-64-v3 -DNDEBUG
                                             (CPU timing arm; multi-threaded, nondeterministic)
   oracle/_ref/simple_spectral_<v>_hooked   sources + oracle/ref_hooks.hpp spliced into
@@ -42,6 +42,11 @@ VARIANTS = {
     # on every hit (renderer.cpp:167-175).  (FLAT_FIELD_CORRECTION cannot be compiled out in this mode: the reference's
     # own color.cpp:275-279 then refers to an undeclared `flux`.)
     "ours1931_noels": dict(alg=1, observer=1931, no_els=True),
+    # FLAT_FIELD_CORRECTION compiled out (stdafx.hpp:55): flux = radiance * dot(camera ray, camera dir), renderer.cpp:262-266.
+    # The reference does not compile as shipped in this configuration — Color::round_trip_lrgb (color.cpp:275-279, a
+    # self-test helper that is NOT on the render path) then uses an undeclared `flux` —, so the scratch copy of color.cpp
+    # gets the one declaration that function lacks; renderer.cpp is untouched.
+    "ours1931_noffc": dict(alg=1, observer=1931, no_ffc=True),
     # RENDER_MODE_RGB (stdafx.hpp:62-90 `#if 1` -> `#if 0`): the three-channel comparison renderer
     "rgb": dict(alg=1, observer=1931, rgb=True),
     # SAMPLE_WAVELENGTHS (stdafx.hpp:90) other than 4: glm::vec<N,float> exists for N = 2, 3 (not 1 without extra headers)
@@ -88,6 +93,10 @@ def patch_variant(src_dir, alg, observer, no_els=False, no_ffc=False, rgb=False,
         t = sub_once(t, r"^#define EXPLICIT_LIGHT_SAMPLING$", "//#define EXPLICIT_LIGHT_SAMPLING", "ELS")
     if no_ffc:
         t = sub_once(t, r"^#define FLAT_FIELD_CORRECTION$", "//#define FLAT_FIELD_CORRECTION", "FFC")
+        pc = os.path.join(src_dir, "util", "color.cpp")
+        tc = open(pc, encoding="utf-8-sig").read()
+        tc = sub_once(tc, r"(#else\n\t\t)assert\(false\);(\n\t#endif\n\n\t//\tViewer-perceived XYZ)", r"\1SpectralRadiantFlux const& flux = radiance;\2", "FFC (round_trip_lrgb)")
+        open(pc, "w", encoding="utf-8").write(tc)
     if max_depth != 10:
         t = sub_once(t, r"#define MAX_DEPTH 10u", f"#define MAX_DEPTH {max_depth}u", "MAX_DEPTH")
     if nw != 4:

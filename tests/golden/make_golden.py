@@ -37,6 +37,8 @@ CASES = [  # (scene, variant)
     ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
     # EXPLICIT_LIGHT_SAMPLING compiled out: MaterialMirror on the plane (scene.cpp:346-355), emission on every hit
     ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels"),
+    # FLAT_FIELD_CORRECTION compiled out (renderer.cpp:262-266; see oracle/build_ref.py on how that build is made to compile)
+    ("cornell", "ours1931_noffc"), ("cornell-srgb", "ours1931_noffc"),
     # RENDER_MODE_RGB: the three-channel comparison renderer (the stored "xyza" is the l-RGB+alpha average)
     ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb"),
     # SAMPLE_WAVELENGTHS 3 (OURS) and 2 (Meng)

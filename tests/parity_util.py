@@ -20,6 +20,7 @@ VARIANT_OPTS = {  # compile-time variants of the reference (stdafx.hpp:66,81) as
     "jh": dict(upsampling=abi.SSB_UPSAMPLE_JH, lambda_min=380.0, lambda_max=780.0),
     "meng": dict(upsampling=abi.SSB_UPSAMPLE_MENG, lambda_min=380.0, lambda_max=780.0),
     "ours1931_noels": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, explicit_light_sampling=0),
+    "ours1931_noffc": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, flat_field_correction=0),
     "rgb": dict(render_mode=abi.SSB_RENDER_RGB),  # RENDER_MODE_RGB (stdafx.hpp:62-90)
     # SAMPLE_WAVELENGTHS 3 / 2 (stdafx.hpp:90)
     "ours1931_nw3": dict(upsampling=abi.SSB_UPSAMPLE_OURS, lambda_min=380.0, lambda_max=780.0, n_wavelengths=3),

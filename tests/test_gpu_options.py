@@ -44,8 +44,8 @@ def test_max_depth(depth, els):
 
 
 def test_flat_field_correction_off():
-    """renderer.cpp:262-266: flux = radiance * dot(camera ray, camera dir) (the reference's own build of this
-    configuration does not compile, color.cpp:275-279, so this option is checked oracle-vs-CUDA only)."""
+    """renderer.cpp:262-266: flux = radiance * dot(camera ray, camera dir) — here CUDA vs oracle with per-sample values;
+    the frame of the real reference's build of this configuration: tests/test_zz_gpu_prebake_progressive.py."""
     flat = pu.load_flat("cornell", "ours1931")
     on = _compare(flat, pu.options("ours1931", 24, 20, 3, seed=11))
     off = _compare(flat, pu.options("ours1931", 24, 20, 3, seed=11, flat_field_correction=0), pixels=((12, 10),))

@@ -13,6 +13,7 @@ SMALL = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("plane-srgb", "
          ("cornell", "ours2006"), ("cornell-srgb", "ours2006"),
          ("cornell-srgb", "jh"), ("plane-srgb", "jh"), ("cornell-srgb", "meng"), ("plane-srgb", "meng"),
          ("plane-srgb", "ours1931_noels"), ("cornell", "ours1931_noels"),
+         ("cornell", "ours1931_noffc"), ("cornell-srgb", "ours1931_noffc"),  # FLAT_FIELD_CORRECTION off
          ("cornell", "rgb"), ("cornell-srgb", "rgb"), ("plane-srgb", "rgb"),  # RENDER_MODE_RGB
          ("cornell-srgb", "ours1931_nw3"), ("plane-srgb", "ours1931_nw3"), ("cornell-srgb", "meng_nw2"),  # SAMPLE_WAVELENGTHS 3 / 2
          ("cornell-srgb", "ours1931_d3")]  # MAX_DEPTH 3

@@ -197,3 +197,18 @@ def test_config1_size_sha_of_the_other_baseline_variants(scene, variant):
         for prebaked in ((0, 1) if variant == "jh" else (0,)):
             x, _ = ctx.render_frame(pu.options(variant, 128, 128, 16, seed=1, prebaked_textures=prebaked))
             assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() == want, (variant, prebaked)
+
+
+@pytest.mark.parametrize("scene", ["cornell", "cornell-srgb"])
+def test_flat_field_correction_off_equals_the_reference_build(scene):
+    """FLAT_FIELD_CORRECTION compiled out (renderer.cpp:262-266): the frame of the real reference's build of that
+    configuration (tests/golden/xyza_*_ours1931_noffc_*; oracle/build_ref.py explains the one declaration the reference
+    needs to compile it — outside the render path)."""
+    if scene != "cornell":
+        _need_assets()
+    flat = pu.load_flat(scene, "ours1931_noffc")
+    opt = pu.options("ours1931_noffc", 32, 24, 4, seed=7)
+    ref = np.load(os.path.join(pu.GOLDEN, f"xyza_{scene}_ours1931_noffc_32x24_spp4_seed7.npy"))
+    with pu.gpu_context(flat) as ctx:
+        x, _ = ctx.render_frame(opt)
+    assert pu.bits_equal(x, ref)
