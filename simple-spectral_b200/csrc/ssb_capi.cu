@@ -89,6 +89,9 @@ struct ssb_ctx {
 	// ssb_upload_scene_async: texture copies run on their own stream and overlap the first kernels of the next render
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t ev_tex_ready = nullptr, ev_tex_free = nullptr;  // copy finished / last render that read the textures finished
+	cudaEvent_t ev_accum_ready = nullptr;  // ssb_accum_merge: the source context's accumulator is complete
+	double* d_peer_staging = nullptr;      // ssb_accum_merge without peer access: the source accumulator, copied over
+	size_t peer_staging_count = 0;
 	bool tex_pending = false, tex_in_use = false;
 	std::vector<cudaEvent_t> ev_pass;   // (t0,t1) pairs around each trace-kernel launch of the last ssb_render
 	uint32_t passes = 0;
@@ -306,22 +309,27 @@ int ssb_create(int device, ssb_ctx** out) {
 		return fail(SSB_ERR_DATA, "ssb_create: no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
 	if (device < 0 || device >= count) return fail(SSB_ERR_ARG, "ssb_create: device %d out of range [0,%d)", device, count);
 	SSB_CUDA(cudaSetDevice(device));
-	ssb_ctx* c = new ssb_ctx();
-	c->device = device;
 	cudaDeviceProp prop{};
 	SSB_CUDA(cudaGetDeviceProperties(&prop, device));
-	c->sm_count = prop.multiProcessorCount;
-	if (prop.major < 10) {
-		delete c;
+	if (prop.major < 10)
 		return fail(SSB_ERR_UNSUPPORTED, "ssb_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-	}
-	SSB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	ssb_ctx* c = new ssb_ctx();
+	c->device = device;
+	c->sm_count = prop.multiProcessorCount;
+	// every failure from here on releases what was created so far (ssb_destroy accepts a partially built context)
+	cudaError_t e2 = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
 	c->stream = c->own_stream;
-	SSB_CUDA(cudaEventCreate(&c->ev_begin)); SSB_CUDA(cudaEventCreate(&c->ev_end));
-	SSB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-	SSB_CUDA(cudaEventCreateWithFlags(&c->ev_tex_ready, cudaEventDisableTiming));
-	SSB_CUDA(cudaEventCreateWithFlags(&c->ev_tex_free, cudaEventDisableTiming));
-	SSB_CUDA(cudaMalloc(&c->d_counts, kCounterWords * sizeof(uint32_t)));
+	if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_begin);
+	if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev_end);
+	if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+	if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->ev_tex_ready, cudaEventDisableTiming);
+	if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->ev_tex_free, cudaEventDisableTiming);
+	if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->ev_accum_ready, cudaEventDisableTiming);
+	if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_counts, kCounterWords * sizeof(uint32_t));
+	if (e2 != cudaSuccess) {
+		ssb_destroy(c);
+		return fail(SSB_ERR_DATA, "ssb_create: CUDA error %s while creating the context of device %d", cudaGetErrorString(e2), device);
+	}
 	*out = c;
 	return SSB_OK;
 }
@@ -335,9 +343,14 @@ void ssb_destroy(ssb_ctx* c) {
 	cudaFree(c->d_blob); cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points);
 	cudaFree(c->d_accum); cudaFree(c->d_counts); cudaFree(c->d_wave); cudaFree(c->d_xyza); cudaFree(c->d_srgba);
 	cudaFree(c->d_rgb_staging);
+	cudaFree(c->d_peer_staging);
 	if (c->ev_begin) cudaEventDestroy(c->ev_begin);
 	if (c->ev_end) cudaEventDestroy(c->ev_end);
+	if (c->ev_tex_ready) cudaEventDestroy(c->ev_tex_ready);
+	if (c->ev_tex_free) cudaEventDestroy(c->ev_tex_free);
+	if (c->ev_accum_ready) cudaEventDestroy(c->ev_accum_ready);
 	for (cudaEvent_t e : c->ev_pass) cudaEventDestroy(e);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -539,7 +552,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 
 	// ---- size one pass: N = npix_rect * chunk samples share the wavefront buffers
 	const uint32_t nrec_depths = o->max_depth > 1 ? o->max_depth - 1 : 1;
-	const size_t bytes_per_sample = 2 * (32 + 32) + 32 + (SSB_FUSED_TRACE ? 32 : 0) + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (4 + 4);
+	const size_t bytes_per_sample = 2 * (32 + 32) + 32 + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (4 + 4);
 	size_t budget = kWaveBudgetBytes;
 	if (const char* e = getenv("SSB_WAVE_BUDGET_MB")) {  // tests force multi-pass rendering with a tiny budget
 		long mb = atol(e);
@@ -554,9 +567,6 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	const size_t o_a0 = off; off += up(N * 32); const size_t o_a1 = off; off += up(N * 32);
 	const size_t o_r0 = off; off += up(N * 32); const size_t o_r1 = off; off += up(N * 32);
 	const size_t o_h = off; off += up(N * 32);
-#if SSB_FUSED_TRACE
-	const size_t o_h2 = off; off += up(N * 32);  // closest-hit records ping-pong (ssb_shade_trace_kernel)
-#endif
 	const size_t o_sl = off; off += up(N * nrec_depths * 16);
 	const size_t o_sf = off; off += up(N * nrec_depths * 16);
 	const size_t o_sn = off; off += up(N * nrec_depths * 8);
@@ -580,9 +590,6 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.recA[0] = reinterpret_cast<float4*>(wv + o_a0); P.recA[1] = reinterpret_cast<float4*>(wv + o_a1);
 	P.recR[0] = reinterpret_cast<float4*>(wv + o_r0); P.recR[1] = reinterpret_cast<float4*>(wv + o_r1);
 	P.recH = reinterpret_cast<float4*>(wv + o_h);
-#if SSB_FUSED_TRACE
-	P.recH2 = reinterpret_cast<float4*>(wv + o_h2);
-#endif
 	P.stk_local = reinterpret_cast<float4*>(wv + o_sl); P.stk_f = reinterpret_cast<float4*>(wv + o_sf);
 	P.stk_np = reinterpret_cast<float2*>(wv + o_sn);
 	P.leaf = reinterpret_cast<float4*>(wv + o_leaf); P.meta = reinterpret_cast<float2*>(wv + o_meta);
@@ -622,14 +629,6 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 		case SSB_UPSAMPLE_JH: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_JH>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_JH>; break;
 		default: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_MENG>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_MENG>; break;
 	}
-#if SSB_FUSED_TRACE
-	switch (rgb ? (uint32_t)SSB_UPS_RGB : o->upsampling) {  // the experiment's stage: shading + the next depth's closest-hit queries
-		case SSB_UPS_RGB: k_shade_first = ssb_shade_trace_kernel<true, SSB_UPS_RGB>; k_shade_next = ssb_shade_trace_kernel<false, SSB_UPS_RGB>; break;
-		case SSB_UPSAMPLE_OURS: k_shade_first = ssb_shade_trace_kernel<true, SSB_UPSAMPLE_OURS>; k_shade_next = ssb_shade_trace_kernel<false, SSB_UPSAMPLE_OURS>; break;
-		case SSB_UPSAMPLE_JH: k_shade_first = ssb_shade_trace_kernel<true, SSB_UPSAMPLE_JH>; k_shade_next = ssb_shade_trace_kernel<false, SSB_UPSAMPLE_JH>; break;
-		default: k_shade_first = ssb_shade_trace_kernel<true, SSB_UPSAMPLE_MENG>; k_shade_next = ssb_shade_trace_kernel<false, SSB_UPSAMPLE_MENG>; break;
-	}
-#endif
 	kfn k_isect_first = ssb_intersect_kernel<true>, k_isect_next = ssb_intersect_kernel<false>;
 	int occ_sf = 0, occ_sn = 0, occ_if = 0, occ_in = 0;
 	for (kfn k : { k_shade_first, k_shade_next, k_isect_first, k_isect_next })
@@ -661,9 +660,6 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			const unsigned long long want_s = (P.total_work + SSB_SHADE_THREADS - 1) / SSB_SHADE_THREADS;
 			const unsigned grid_i = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_if : occ_in), want_i);
 			const unsigned grid_s = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_sf : occ_sn), want_s);
-#if SSB_FUSED_TRACE
-			if (d == 0)  // depths >= 1: the previous depth's fused stage already produced the closest-hit records
-#endif
 			(d == 0 ? k_isect_first : k_isect_next)<<<grid_i, SSB_INTERSECT_THREADS, smem, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
 			if (c->tex_pending) {  // texels are first read by the shade stage: the camera-ray queries overlap the upload
@@ -677,7 +673,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			SSB_CUDA(cudaGetLastError());
 			(d == 0 ? k_shade_first : k_shade_next)<<<grid_s, SSB_SHADE_THREADS, smem, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
-			launches += (SSB_FUSED_TRACE && d > 0) ? 3 : 4;
+			launches += 4;
 		}
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes + 1], c->stream));
 		ssb_fold_kernel<<<(unsigned)((P.total_work + 255) / 256), 256, 0, c->stream>>>(P);

@@ -256,6 +256,27 @@ SSB_ISECT_FN float entry_plane_key(const float4 pl, float ox, float oy, float oz
 	return (fabsf(nd) >= SSB_GRAZE) ? tp : -__int_as_float(0x7f800000);
 }
 
+// Conservative in-plane test of one filter entry (pair record `rec`, lane `odd`): true when the half-line
+// {(u_o, v_o) + t (u_d, v_d), t >= 0} — the ray projected onto the entry's plane, in the entry's scaled rectangle
+// coordinates — misses the square [-1,1]^2 (the bounding rectangle enlarged by the margin).  Separating axes of a line
+// and a box in 2-D: u, v, and the normal of the line.  The rectangle's enlargement (>= 1e-4 of the scene extent) is
+// orders of magnitude more than the rounding of these few fused multiply-adds.  An all-zero (degenerate) entry gives
+// 0 > 0 everywhere: never rejected.
+SSB_ISECT_FN bool entry_missed_in_plane(const float4* rec, int odd, float ox, float oy, float oz, float dx, float dy, float dz) {
+	const float4 a2 = rec[2], a3 = rec[3], a4 = rec[4], a5 = rec[5];
+	const float uax = odd ? a2.y : a2.x, uay = odd ? a2.w : a2.z, uaz = odd ? a3.y : a3.x, uaw = odd ? a3.w : a3.z;
+	const float vbx = odd ? a4.y : a4.x, vby = odd ? a4.w : a4.z, vbz = odd ? a5.y : a5.x, vbw = odd ? a5.w : a5.z;
+	const float uo = __fmaf_rn(uax, ox, __fmaf_rn(uay, oy, __fmaf_rn(uaz, oz, uaw)));
+	const float vo = __fmaf_rn(vbx, ox, __fmaf_rn(vby, oy, __fmaf_rn(vbz, oz, vbw)));
+	const float ud = __fmaf_rn(uax, dx, __fmaf_rn(uay, dy, uaz * dz));
+	const float vd = __fmaf_rn(vbx, dx, __fmaf_rn(vby, dy, vbz * dz));
+	const bool sep_u = (uo > 1.0f && ud >= 0.0f) || (uo < -1.0f && ud <= 0.0f);
+	const bool sep_v = (vo > 1.0f && vd >= 0.0f) || (vo < -1.0f && vd <= 0.0f);
+	const float cr = __fmaf_rn(ud, vo, -(vd * uo));  // cross((u_d, v_d), (0,0) - (u_o, v_o)), up to sign
+	const bool sep_n = fabsf(cr) > (fabsf(ud) + fabsf(vd)) * 1.0001f;
+	return sep_u || sep_v || sep_n;
+}
+
 SSB_ISECT_NOINLINE void scene_intersect(const SceneView& S, float eps, int ignore, Hit& hit,
                                         float ox, float oy, float oz, float dx, float dy, float dz) {
 	hit.quad = -1; hit.tri = 0; hit.dist = __int_as_float(0x7f800000);
@@ -327,6 +348,16 @@ SSB_ISECT_NOINLINE void scene_intersect(const SceneView& S, float eps, int ignor
 		}
 #endif
 		// ---- phase 3: the reference's own order (one exact test per iteration keeps lanes with different candidates together)
+		// Entries that kept BOTH triangles are mostly planes the ray runs (nearly) parallel to, with the origin close to the
+		// plane — every shadow ray from the Cornell box's ceiling towards the coplanar light keeps the four other ceiling
+		// pieces and the light this way, ten exact tests at one or two lanes.  For those the filter could not place the
+		// ray/plane point, but the PROJECTION of the ray onto the plane is well conditioned whatever the angle: a hit point
+		// o + t d (t >= eps > 0) has the in-plane coordinates (u_o + t u_d, v_o + t v_d), so an entry whose enlarged
+		// rectangle the projected half-line misses cannot be hit.
+		for (unsigned m = candA & candB; m != 0u; m &= m - 1u) {
+			const int e = __ffs(m) - 1;
+			if (entry_missed_in_plane(S.fpairs() + 8 * ((base + e) >> 1), (base + e) & 1, ox, oy, oz, dx, dy, dz)) { candA &= ~(1u << e); candB &= ~(1u << e); }
+		}
 		SSB_STAT(queries, base == 0 ? 1 : 0); SSB_STAT(inorder, base == 0 ? 1 : 0); SSB_STAT(candidates, __builtin_popcount(candA) + __builtin_popcount(candB));
 		while (candA | candB) {
 			const unsigned any = candA | candB;
@@ -343,156 +374,6 @@ SSB_ISECT_NOINLINE void scene_intersect(const SceneView& S, float eps, int ignor
 			if (tri_intersect(S.quads()[q].tri[tt], rc, eps, hit, false)) { hit.quad = q; hit.tri = tt; candB &= ~bit; }
 		}
 	}
-}
-
-// ------------------------------------------------------------------ two rays from one origin (experimental, SSB_FUSED_TRACE)
-// The shadow ray and the next path ray of a vertex start at the same point and ignore the same quad.  filter_chunk2 runs
-// the conservative filter for both directions in one pass over the entries: the record loads and every origin-only term
-// (n.o, the origin's height over the plane) are shared.  Each ray's masks are exactly filter_chunk's.
-SSB_ISECT_FN void filter_chunk2(const float4* rec, int npairs, float margin_rneg, float tmax_k, float ox, float oy, float oz,
-                                float d0x, float d0y, float d0z, float d1x, float d1y, float d1z,
-                                unsigned& keepA0, unsigned& keepB0, unsigned& keepA1, unsigned& keepB1) {
-	unsigned rejA0 = 0u, rejB0 = 0u, rejA1 = 0u, rejB1 = 0u;
-	const float2 ox2 = make_float2(ox, ox), oy2 = make_float2(oy, oy), oz2 = make_float2(oz, oz);
-	const float2 one2 = make_float2(1.0f, 1.0f), mr2 = make_float2(margin_rneg, margin_rneg), tk2 = make_float2(tmax_k, tmax_k);
-	const float nanv = __int_as_float(0x7fffffff);
-	for (int i = npairs - 1; i >= 0; --i) {
-		const float4* r = rec + 8 * i;
-		const float4 a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3], a4 = r[4], a5 = r[5], a6 = r[6], a7 = r[7];
-		const float2 plx = make_float2(a0.x, a0.y), ply = make_float2(a0.z, a0.w), plz = make_float2(a1.x, a1.y), plw = make_float2(a1.z, a1.w);
-		const float2 uax = make_float2(a2.x, a2.y), uay = make_float2(a2.z, a2.w), uaz = make_float2(a3.x, a3.y), uaw = make_float2(a3.z, a3.w);
-		const float2 vbx = make_float2(a4.x, a4.y), vby = make_float2(a4.z, a4.w), vbz = make_float2(a5.x, a5.y), vbw = make_float2(a5.z, a5.w);
-		const float2 dgx = make_float2(a6.x, a6.y), dgy = make_float2(a6.z, a6.w), dgz = make_float2(a7.x, a7.y);
-		// origin-only terms, once for both rays
-		const float2 no = __ffma2_rn(plx, ox2, __ffma2_rn(ply, oy2, __fmul2_rn(plz, oz2)));
-		const float2 num = __fadd2_rn(plw, make_float2(-no.x, -no.y));
-		const float2 hk = __fmul2_rn(num, mr2);
-		const float ahx = fabsf(hk.x), ahy = fabsf(hk.y);
-#pragma unroll
-		for (int ray = 0; ray < 2; ++ray) {
-			const float dx = ray ? d1x : d0x, dy = ray ? d1y : d0y, dz = ray ? d1z : d0z;
-			const float2 dx2 = make_float2(dx, dx), dy2 = make_float2(dy, dy), dz2 = make_float2(dz, dz);
-			const float2 nd = __ffma2_rn(plx, dx2, __ffma2_rn(ply, dy2, __fmul2_rn(plz, dz2)));
-			float2 ri;
-			ri.x = (fabsf(nd.x) >= SSB_PAR) ? rcp_approx(nd.x) : nanv;
-			ri.y = (fabsf(nd.y) >= SSB_PAR) ? rcp_approx(nd.y) : nanv;
-			const float2 ndk = __fmul2_rn(nd, tk2);
-			const float2 tp = __fmul2_rn(num, ri);
-			const float2 px = __ffma2_rn(tp, dx2, ox2), py = __ffma2_rn(tp, dy2, oy2), pz = __ffma2_rn(tp, dz2, oz2);
-			const float2 u = __ffma2_rn(uax, px, __ffma2_rn(uay, py, __ffma2_rn(uaz, pz, uaw)));
-			const float2 v = __ffma2_rn(vbx, px, __ffma2_rn(vby, py, __ffma2_rn(vbz, pz, vbw)));
-			const float2 sd = __ffma2_rn(dgx, u, __ffma2_rn(dgy, v, dgz));
-			const float2 q3 = __fmul2_rn(tp, mr2);
-			unsigned rejA = ray ? rejA1 : rejA0, rejB = ray ? rejB1 : rejB0;
-			{
-				const float g = max3_nan_ignoring(fabsf(u.y), fabsf(v.y), q3.y), z = ahy - fabsf(ndk.y);
-				const float2 w = __fadd2_rn(one2, make_float2(-max3_nan_ignoring(g, -sd.y, z), -max3_nan_ignoring(g, sd.y, z)));
-				rejA = __funnelshift_l(__float_as_uint(w.x), rejA, 1);
-				rejB = __funnelshift_l(__float_as_uint(w.y), rejB, 1);
-			}
-			{
-				const float g = max3_nan_ignoring(fabsf(u.x), fabsf(v.x), q3.x), z = ahx - fabsf(ndk.x);
-				const float2 w = __fadd2_rn(one2, make_float2(-max3_nan_ignoring(g, -sd.x, z), -max3_nan_ignoring(g, sd.x, z)));
-				rejA = __funnelshift_l(__float_as_uint(w.x), rejA, 1);
-				rejB = __funnelshift_l(__float_as_uint(w.y), rejB, 1);
-			}
-			if (ray) { rejA1 = rejA; rejB1 = rejB; } else { rejA0 = rejA; rejB0 = rejB; }
-		}
-	}
-	keepA0 = ~rejA0; keepB0 = ~rejB0; keepA1 = ~rejA1; keepB1 = ~rejB1;
-}
-
-// What scene_intersect does with the candidate masks of a scene whose entries fit one chunk (`ignore` already removed
-// from the masks): nearest candidate first when no quad has both triangles as candidates, else the reference's order.
-SSB_ISECT_FN void resolve_single_chunk(const SceneView& S, float eps, int ignore, Hit& hit, const RayConst& rc,
-                                       float ox, float oy, float oz, float dx, float dy, float dz, unsigned candA, unsigned candB, const uint4 cm) {
-	const uint32_t* entry_quad = S.entry_quad();
-	const float margin = S.hdr()->cull_margin;
-	const unsigned both = (candA & candB) | (candA & cm.z & (candB >> 1));
-	if (both == 0u) {
-		unsigned cand = candA | candB;
-		if (cand == 0u) return;
-		const float inf = __int_as_float(0x7f800000);
-		float t1 = inf, t2 = inf;
-		int e1 = __ffs(cand) - 1, e2 = -1;
-		for (unsigned m = (cand & (cand - 1u)) ? cand : 0u; m != 0u; m &= m - 1u) {
-			const int e = __ffs(m) - 1;
-			const float key = entry_plane_key(S.planes()[e], ox, oy, oz, dx, dy, dz);
-			const bool lt1 = key < t1, lt2 = key < t2;
-			e2 = lt1 ? e1 : (lt2 ? e : e2);
-			t2 = lt1 ? t1 : (lt2 ? key : t2);
-			e1 = lt1 ? e : e1;
-			t1 = lt1 ? key : t1;
-		}
-		int best_e = -1;
-		int e = e1;
-		unsigned rest = cand & ~(1u << e1);
-		int step = 0;
-		for (;;) {
-			const int q = (int)entry_quad[e], tt = (int)((candB >> e) & 1u);
-			if (tri_intersect(S.quads()[q].tri[tt], rc, eps, hit, e < best_e)) { hit.quad = q; hit.tri = tt; best_e = e; }
-			if (rest == 0u) break;
-			if (step < 2) {
-				if (t2 - margin > hit.dist) break;
-				if (step == 0 && e2 >= 0 && ((rest >> e2) & 1u)) { step = 1; e = e2; rest &= ~(1u << e2); continue; }
-				step = 2;
-			}
-			bool found = false;
-			while (rest != 0u) {
-				e = __ffs(rest) - 1;
-				rest &= rest - 1u;
-				const float key = entry_plane_key(S.planes()[e], ox, oy, oz, dx, dy, dz);
-				if (!(key - margin > hit.dist)) { found = true; break; }
-			}
-			if (!found) break;
-		}
-		return;
-	}
-	while (candA | candB) {
-		const unsigned any = candA | candB;
-		const unsigned bit = any & (0u - any);
-		const int e = __ffs(bit) - 1;
-		const int q = (int)entry_quad[e];
-		const int tt = (candA & bit) ? 0 : 1;
-		candA &= ~bit;
-		if (tt == 1) candB &= ~bit;
-		if (q == ignore || (tt == 1 && hit.quad == q)) continue;
-		if (tri_intersect(S.quads()[q].tri[tt], rc, eps, hit, false)) { hit.quad = q; hit.tri = tt; candB &= ~bit; }
-	}
-}
-
-#ifndef SSB_ISECT2_INLINE
-#define SSB_ISECT2_INLINE 0  // 1: inline scene_intersect2 into its (single) call site instead of calling it
-#endif
-#if SSB_ISECT2_INLINE
-#define SSB_ISECT2_ATTR SSB_ISECT_FN
-#else
-#define SSB_ISECT2_ATTR SSB_ISECT_NOINLINE
-#endif
-// Closest hits of two rays that share origin and `ignore` (act0 / act1: whether each ray exists; the filter is evaluated
-// for both regardless, converged).  Each hit record is scene_intersect's for that ray, bit for bit (tools/isect_check.cpp).
-SSB_ISECT2_ATTR void scene_intersect2(const SceneView& S, float eps, int ignore, Hit& hit0, Hit& hit1, bool act0, bool act1,
-                                         float ox, float oy, float oz, float d0x, float d0y, float d0z, float d1x, float d1y, float d1z) {
-	const DevHeader* H = S.hdr();
-	const int nent = (int)H->nentries;
-	if (nent > 32) {  // more than one chunk of entries: two independent queries
-		hit0.quad = -1; hit0.tri = 0; hit0.dist = __int_as_float(0x7f800000); hit0.bx = hit0.by = hit0.bz = 0.0f;
-		hit1 = hit0;
-		if (act0) scene_intersect(S, eps, ignore, hit0, ox, oy, oz, d0x, d0y, d0z);
-		if (act1) scene_intersect(S, eps, ignore, hit1, ox, oy, oz, d1x, d1y, d1z);
-		return;
-	}
-	hit0.quad = -1; hit0.tri = 0; hit0.dist = __int_as_float(0x7f800000); hit0.bx = hit0.by = hit0.bz = 0.0f;
-	hit1 = hit0;
-	const float tmax_k = ((fabsf(ox - H->scene_centre[0]) + fabsf(oy - H->scene_centre[1])) + (fabsf(oz - H->scene_centre[2]) + H->scene_radius)) * H->tmax_scale;
-	unsigned cA0, cB0, cA1, cB1;
-	filter_chunk2(S.fpairs(), nent >> 1, H->cull_margin_rneg, tmax_k, ox, oy, oz, d0x, d0y, d0z, d1x, d1y, d1z, cA0, cB0, cA1, cB1);
-	const uint4 cm = S.chunks()[0];
-	unsigned im = 0xffffffffu;
-	if (ignore >= 0) im = ~S.quad_mask()[ignore];
-	cA0 &= cm.x & im; cB0 &= cm.y & im; cA1 &= cm.x & im; cB1 &= cm.y & im;
-	if (act0) resolve_single_chunk(S, eps, ignore, hit0, ray_setup(ox, oy, oz, d0x, d0y, d0z), ox, oy, oz, d0x, d0y, d0z, cA0, cB0, cm);
-	if (act1) resolve_single_chunk(S, eps, ignore, hit1, ray_setup(ox, oy, oz, d1x, d1y, d1z), ox, oy, oz, d1x, d1y, d1z, cA1, cB1, cm);
 }
 
 // The reference's scan, verbatim (no filter): the yardstick of tools/isect_check.cpp

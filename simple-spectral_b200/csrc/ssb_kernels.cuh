@@ -39,13 +39,6 @@
 #include "ssb_isect.cuh"
 #include "ssb_math.cuh"
 
-// EXPERIMENT (default off; the default build's device code is unchanged by it): trace the next path ray inside the shade
-// stage, together with the shadow ray (ssb_isect.cuh: scene_intersect2 — one filter pass for two rays from one origin),
-// instead of in a separate intersect launch per depth.  See ssb_shade_trace_kernel below and DESIGN.md (f).
-#ifndef SSB_FUSED_TRACE
-#define SSB_FUSED_TRACE 0
-#endif
-
 namespace ssbk {
 
 // (blob layout: ssb_blob.hpp; shared-memory view, ray/scene intersection: ssb_isect.cuh)
@@ -96,9 +89,6 @@ struct KParams {
 	uint32_t meng_grid_w, meng_grid_h, meng_npoints, meng_nsamples;
 	float meng_xy_to_uv[6];
 	float meng_sample_min, meng_sample_max;
-#if SSB_FUSED_TRACE
-	float4* recH2;  // second closest-hit record buffer: the fused stage reads depth d's records while it writes depth d+1's
-#endif
 };
 
 struct Hero { float v[4]; };
@@ -116,10 +106,23 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 // a / b, exactly — with the one case that is both frequent and trivially known kept away from the IEEE division's slow
 // path: a zero numerator over a positive (finite or infinite) denominator is that same zero.  (Channels of a hero sample
 // that fall outside a measured spectrum — the Cornell box's albedos end at 700 nm — are exactly 0; ncu: the slow-path
-// subroutine was entered from these quotients ~0.5 M times per launch.)  Lanes taking the shortcut divide 1 by 1.
+// subroutine was entered from these quotients ~0.77 M times per launch, at 5-24 lanes.)  Lanes taking the shortcut divide
+// 1 by 1.  The operands pass through an empty asm so that the optimiser cannot fold the selects back into "a / b, then
+// select" (it did: r5a capture, FCHK on the raw numerator).
 __device__ __forceinline__ float div_or_zero(float a, float b) {
 	const bool zero = (a == 0.0f) && (b > 0.0f);
-	const float q = (zero ? 1.0f : a) / (zero ? 1.0f : b);
+	float an = zero ? 1.0f : a, bn = zero ? 1.0f : b;
+	asm("" : "+f"(an), "+f"(bn));
+	const float q = an / bn;
+	return zero ? a : q;
+}
+// the same for a divisor known at compile time (only the numerator needs hiding: the division keeps its constant reciprocal)
+template <typename F>
+__device__ __forceinline__ float div_const_or_zero(float a, F divide) {
+	const bool zero = a == 0.0f;
+	float an = zero ? 1.0f : a;
+	asm("" : "+f"(an));
+	const float q = divide(an);
 	return zero ? a : q;
 }
 
@@ -508,7 +511,15 @@ __device__ __noinline__ void sample_spherical_triangle(int light_quad, int light
 			else { alpha = cos_alpha = nan; }
 		}
 	}
-	pdf = 1.0f / surface_area;  // geometry.cpp:115 (inf when the area is 0)
+	// geometry.cpp:115: pdf = 1 / area, +inf when the area is +0 (every point coplanar with the light: the whole ceiling of
+	// the Cornell box) — written out so that those lanes stay off the reciprocal's slow path
+	{
+		const bool flat = surface_area == 0.0f;
+		float sa = flat ? 1.0f : surface_area;
+		asm("" : "+f"(sa));
+		const float r = 1.0f / sa;
+		pdf = flat ? __int_as_float(0x7f800000) : r;
+	}
 
 	// Arvo sampling (random.cpp:101-154)
 	float sin_alpha = sinf_x(alpha);
@@ -913,7 +924,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 				f_s = material_albedo<UPS>(P, S, m, st_x, st_y, lambda_0);
 				if (mat_kind == SSB_MATERIAL_LAMBERT) {
 #pragma unroll
-					for (int c = 0; c < 4; ++c) f_s.v[c] = div_or_zero(f_s.v[c], SSB_PI_F);
+					for (int c = 0; c < 4; ++c) f_s.v[c] = div_const_or_zero(f_s.v[c], [](float x) { return x / SSB_PI_F; });
 				}
 			}
 		}
@@ -930,7 +941,13 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			float r1 = rand_1f(rng);
 			sample_spherical_triangle(light_quad, lt, hx, hy, hz, r0, r1, sx, sy, sz, pdf);
 			pdf *= 0.5f;
-			pdf /= (float)S.hdr()->nlights;
+			{  // pdf /= nlights (scene.cpp:428-430); inf / n = inf without the division's slow path
+				const bool pinf = pdf == __int_as_float(0x7f800000);
+				float pn = pinf ? 1.0f : pdf;
+				asm("" : "+f"(pn));
+				pn /= (float)S.hdr()->nlights;
+				pdf = pinf ? pdf : pn;
+			}
 			l_ndl = dot3(sx, sy, sz, nx, ny, nz);
 		}
 		SSB_PHASE_BARRIER_AT(1);
@@ -1044,241 +1061,6 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 	}
 }
 
-#if SSB_FUSED_TRACE
-// ---- EXPERIMENT: stage 2 of a bounce AND stage 1 of the next one.  Same arithmetic as ssb_shade_kernel, re-ordered so that
-// the BSDF sample is drawn before the shadow query (the shadow query draws no random numbers, so the order of the draws
-// is the reference's: light sample, then BSDF sample), and the shadow ray and the next path ray — same origin, same
-// ignored quad — are traced by ONE call (scene_intersect2: the filter's record loads and origin-only terms are shared).
-// A next ray that misses ends the path right here (leaf 0, the records written so far), exactly what the intersect stage
-// of the next depth would have recorded; a hit is compacted into the next depth's queue as a closest-hit record
-// (recH ping-pong, hit_q, per-quad histogram for the counting sort), so depths >= 1 need no intersect launch and no
-// ray records (only the direction is kept, for MaterialMirror).
-template <bool FIRST, int UPS>
-__global__ void __launch_bounds__(SSB_SHADE_THREADS, SSB_SHADE_MIN_BLOCKS)
-ssb_shade_trace_kernel(const __grid_constant__ KParams P) {
-	__shared__ __align__(8) unsigned long long blob_bar;
-	stage_scene(P, &blob_bar);
-	const SceneView S;
-
-	const unsigned full = 0xffffffffu;
-	const int lane = threadIdx.x & 31;
-	const float eps = P.eps;
-	const bool els = P.els != 0;
-	const int depth = (int)P.depth;
-	const uint32_t n_in = P.nhits[depth];
-	const int pin = depth & 1, pout = pin ^ 1;
-	const float4* __restrict__ recH_in = pin ? P.recH2 : P.recH;
-	float4* __restrict__ recH_out = pin ? P.recH : P.recH2;
-	const uint32_t nthreads = gridDim.x * blockDim.x;
-	const uint32_t n_round = (n_in + blockDim.x - 1u) / blockDim.x * blockDim.x;
-	const bool more_depth = (uint32_t)depth + 1u < P.max_depth;
-	const bool light_phase = more_depth && els && (!P.indirect_only || !FIRST);
-	const bool next_depth_traced = !(els && (uint32_t)depth + 2u >= P.max_depth);  // (dead-work skip of the last depth)
-	uint32_t* bins = P.bin_count + (size_t)(depth + 1) * SSB_MAX_QUADS;  // hits of the NEXT depth per quad
-	__shared__ uint32_t s_bins[SSB_MAX_QUADS];
-	for (uint32_t q = threadIdx.x; q < SSB_MAX_QUADS; q += blockDim.x) s_bins[q] = 0;
-	__syncthreads();
-
-	__shared__ float4 s_pipe[2][4][SSB_SHADE_THREADS];
-	auto prefetch = [&](uint32_t it, bool ok, int stage) {
-		if (ok) {
-			cp_async16(&s_pipe[stage][0][threadIdx.x], &recH_in[2 * (size_t)it]);
-			cp_async16(&s_pipe[stage][1][threadIdx.x], &recH_in[2 * (size_t)it + 1]);
-			cp_async16(&s_pipe[stage][2][threadIdx.x], &P.recR[pin][2 * (size_t)it]);
-			cp_async16(&s_pipe[stage][3][threadIdx.x], &P.recR[pin][2 * (size_t)it + 1]);
-		}
-		cp_async_commit();
-	};
-	int stage = 0;
-	uint32_t item_cur, item_nxt;
-	{
-		const uint32_t s0 = blockIdx.x * blockDim.x + threadIdx.x;
-		item_cur = s0 < n_in ? P.order[s0] : 0u;
-		item_nxt = (s0 < n_in && nthreads < n_in - s0) ? P.order[s0 + nthreads] : 0u;
-		prefetch(item_cur, s0 < n_in, 0);
-	}
-	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += nthreads) {
-		const bool valid = slot < n_in;
-		const int cur = stage;
-		uint32_t item_nn = 0u;
-		{
-			const uint32_t left = valid ? n_in - slot : 0u;
-			prefetch(item_nxt, nthreads < left, stage ^ 1);
-			if (nthreads < left && nthreads < left - nthreads) item_nn = P.order[slot + 2u * nthreads];
-			cp_async_wait<1>();
-			stage ^= 1;
-		}
-		bool cont = false;  // the next path ray exists AND hits something
-		float lambda_0 = 0;
-		uint32_t id = 0, item = 0;
-		Rng rng; rng.state = 0; rng.inc = 1;
-		float hx = 0, hy = 0, hz = 0, nx = 0, ny = 0, nz = 1;
-		int cur_quad = 0;
-		uint32_t mat_kind = SSB_MATERIAL_LAMBERT;
-		Hero local, f_s;
-		local.v[0] = local.v[1] = local.v[2] = local.v[3] = 0.0f;
-		f_s = local;
-
-		// ---- phase 0: gather the path, emission, albedo (as ssb_shade_kernel)
-		if (valid) {
-			item = item_cur;
-			const float4 h0 = s_pipe[cur][0][threadIdx.x], h1 = s_pipe[cur][1][threadIdx.x];
-			const float4 r0 = s_pipe[cur][2][threadIdx.x], r1 = s_pipe[cur][3][threadIdx.x];
-			hx = h0.x; hy = h0.y; hz = h0.z;
-			const uint32_t hq = __float_as_uint(h0.w);
-			id = __float_as_uint(r1.x);
-			lambda_0 = r1.y;
-			rng.state = ((unsigned long long)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
-			rng.inc = ((unsigned long long)__float_as_uint(r0.w) << 32) | __float_as_uint(r0.z);
-			cur_quad = (int)(hq & 0x7fffffffu);
-			const ssb_quad& quad = S.quads()[cur_quad];
-			const ssb_tri& tri = quad.tri[hq >> 31];
-			const DevMaterial& m = S.materials()[quad.material];
-			mat_kind = m.kind;
-			nx = tri.normal[0]; ny = tri.normal[1]; nz = tri.normal[2];
-			const float st_x = (h1.x * tri.v[0].st[0] + h1.y * tri.v[1].st[0]) + h1.z * tri.v[2].st[0];
-			const float st_y = (h1.x * tri.v[0].st[1] + h1.y * tri.v[1].st[1]) + h1.z * tri.v[2].st[1];
-			if (!els || (FIRST && !P.indirect_only)) {
-				Hero e = material_emission<UPS>(P, S, m, lambda_0);
-#pragma unroll
-				for (int c = 0; c < 4; ++c) local.v[c] = local.v[c] + e.v[c];
-			}
-			if (more_depth) {
-				f_s = material_albedo<UPS>(P, S, m, st_x, st_y, lambda_0);
-				if (mat_kind == SSB_MATERIAL_LAMBERT) {
-#pragma unroll
-					for (int c = 0; c < 4; ++c) f_s.v[c] = div_or_zero(f_s.v[c], SSB_PI_F);
-				}
-			}
-		}
-		SSB_PHASE_BARRIER_AT(0);
-
-		// ---- phase 1: light sample (as ssb_shade_kernel)
-		float sx = 0, sy = 0, sz = 1, pdf = 1.0f, l_ndl = 0.0f;
-		int light_quad = -1;
-		if (valid && light_phase) {
-			uint32_t li = rand_choice(rng, S.hdr()->nlights);
-			light_quad = (int)S.lights()[li];
-			const int lt = (rand_1f(rng) <= 0.5f) ? 0 : 1;
-			float r0 = rand_1f(rng);
-			float r1 = rand_1f(rng);
-			sample_spherical_triangle(light_quad, lt, hx, hy, hz, r0, r1, sx, sy, sz, pdf);
-			pdf *= 0.5f;
-			pdf /= (float)S.hdr()->nlights;
-			l_ndl = dot3(sx, sy, sz, nx, ny, nz);
-		}
-		SSB_PHASE_BARRIER_AT(1);
-
-		// ---- phase 2: interact_bsdf + recursion decision (renderer.cpp:222-245), BEFORE the shadow query: the reference
-		// draws these random numbers after the light sample's and the shadow query draws none
-		float wix = 0, wiy = 0, wiz = 1, pdf_w_i = 1.0f, n_dot_l = 0.0f;
-		bool recurse = false;
-		if (valid && more_depth) {
-			if (mat_kind == SSB_MATERIAL_LAMBERT) {
-				float cx, cy, cz;
-				do {
-					float angle = rand_1f(rng) * (2.0f * SSB_PI_F);
-					const float2 sc_angle = sincosf_x(angle);
-					const float si = sc_angle.x, co = sc_angle.y;
-					float radius_sq = rand_1f(rng);
-					float radius = sqrtf(radius_sq);
-					cx = radius * co; cy = sqrtf(1.0f - radius_sq); cz = radius * si;
-					pdf_w_i = cy;
-				} while (pdf_w_i <= eps);
-				pdf_w_i *= 1.0f / SSB_PI_F;
-				float sign = copysignf(1.0f, nz);
-				float a = -1.0f / (sign + nz);
-				float b = nx * ny * a;
-				float bxx = 1.0f + sign * nx * nx * a, bxy = sign * b, bxz = -sign * nx;
-				float bzx = b, bzy = sign + ny * ny * a, bzz = -ny;
-				wix = (cx * bxx + cy * nx) + cz * bzx;
-				wiy = (cx * bxy + cy * ny) + cz * bzy;
-				wiz = (cx * bxz + cy * nz) + cz * bzz;
-			} else {
-				const float4 din = P.recA[pin][2 * (size_t)item + 1];  // incoming direction (depth 0: written by the camera-ray stage)
-				float vx = -din.x, vy = -din.y, vz = -din.z;
-				float d2 = 2.0f * dot3(vx, vy, vz, nx, ny, nz);
-				wix = -vx + d2 * nx; wiy = -vy + d2 * ny; wiz = -vz + d2 * nz;
-				pdf_w_i = __int_as_float(0x7f800000);
-			}
-			float ff = (f_s.v[0] * f_s.v[0] + f_s.v[1] * f_s.v[1]) + (f_s.v[2] * f_s.v[2] + f_s.v[3] * f_s.v[3]);
-			if (ff > 0.0f) {
-				if (isfinite(pdf_w_i)) n_dot_l = dot3(wix, wiy, wiz, nx, ny, nz);
-				else { n_dot_l = 1.0f; pdf_w_i = 1.0f; }
-				recurse = n_dot_l > 0.0f;
-			}
-		}
-
-		// ---- phase 3: the shadow query and the next closest-hit query, one call
-		const bool shadow = valid && light_phase && l_ndl > 0.0f;
-		const bool trace_next = recurse && next_depth_traced;
-		Hit hs, hn;
-		hs.quad = -1; hn.quad = -1; hn.tri = 0; hn.dist = 0.0f; hn.bx = hn.by = hn.bz = 0.0f;
-		if (shadow || trace_next) scene_intersect2(S, eps, cur_quad, hs, hn, shadow, trace_next, hx, hy, hz, sx, sy, sz, wix, wiy, wiz);
-		if (shadow && hs.quad == light_quad) {
-			const DevMaterial& lm = S.materials()[S.quads()[light_quad].material];
-			Hero emitted = material_emission<UPS>(P, S, lm, lambda_0);
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				float fe = (mat_kind == SSB_MATERIAL_LAMBERT) ? f_s.v[c] : 0.0f;
-				local.v[c] = local.v[c] + div_or_zero((emitted.v[c] * l_ndl) * fe, pdf);
-			}
-		}
-
-		// ---- phase 4: fold record, end of path or the next depth's closest-hit record
-		uint32_t hq_next = 0xffffffffu;
-		if (valid) {
-			Hero rad;
-			rad.v[0] = rad.v[1] = rad.v[2] = rad.v[3] = 0.0f;
-			int nrec = depth;
-			if (recurse) {
-				const size_t rec = (size_t)depth * P.total_work + id;
-				P.stk_local[rec] = make_float4(local.v[0], local.v[1], local.v[2], local.v[3]);
-				P.stk_f[rec] = make_float4(f_s.v[0], f_s.v[1], f_s.v[2], f_s.v[3]);
-				P.stk_np[rec] = make_float2(n_dot_l, pdf_w_i);
-				nrec = depth + 1;
-				// the child L() returns 0 when it is not entered (last depth under explicit light sampling) or when its ray
-				// misses (renderer.cpp:161-163): rad stays 0 in both cases
-				if (trace_next && hn.quad >= 0) { cont = true; hq_next = (uint32_t)hn.quad | ((uint32_t)hn.tri << 31); }
-			} else {
-				rad = local;
-			}
-			if (!cont) {
-				P.leaf[id] = make_float4(rad.v[0], rad.v[1], rad.v[2], rad.v[3]);
-				P.meta[id] = make_float2(lambda_0, __int_as_float(nrec | (1 << 16)));
-			}
-		}
-
-		// ---- compaction: paths whose next ray hit something become closest-hit records of the next depth
-		const unsigned mask = __ballot_sync(full, cont);
-		if (mask) {
-			unsigned base = 0;
-			const int leader = __ffs(mask) - 1;
-			if (lane == leader) base = atomicAdd(&P.counts[depth + 1], (uint32_t)__popc(mask));
-			base = __shfl_sync(full, base, leader);
-			if (cont) {
-				const uint32_t o = base + __popc(mask & ((1u << lane) - 1u));
-				const float d_ = hn.dist;  // Ray::at (stdafx.hpp:219) of the new ray, origin = this hit point
-				recH_out[2 * (size_t)o] = make_float4(hx + d_ * wix, hy + d_ * wiy, hz + d_ * wiz, __uint_as_float(hq_next));
-				recH_out[2 * (size_t)o + 1] = make_float4(hn.bx, hn.by, hn.bz, 0.f);
-				P.recA[pout][2 * (size_t)o + 1] = make_float4(wix, wiy, wiz, lambda_0);  // direction only (MaterialMirror reads it)
-				P.recR[pout][2 * (size_t)o] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
-				                                          __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32)));
-				P.recR[pout][2 * (size_t)o + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
-				P.hit_q[o] = hq_next;
-				const uint32_t q = hq_next & 0x7fffffffu;
-				const unsigned peers = __match_any_sync(mask, q);
-				if (lane == __ffs(peers) - 1) atomicAdd(&s_bins[q], (uint32_t)__popc(peers));
-			}
-		}
-		item_cur = item_nxt; item_nxt = item_nn;
-		SSB_PHASE_BARRIER_AT(3);
-	}
-	__syncthreads();
-	for (uint32_t q = threadIdx.x; q < SSB_MAX_QUADS; q += blockDim.x)
-		if (s_bins[q]) atomicAdd(&bins[q], s_bins[q]);
-}
-#endif  // SSB_FUSED_TRACE
 
 // Unwind the recursion of one sample and convert it to the value the reference's _render_sample returns:
 //   radiance = local + ((child * n.l) * f_s) / pdf        (renderer.cpp:216,248)

@@ -1,7 +1,7 @@
 """CPU: the device's scene_intersect (simple-spectral_b200/csrc/ssb_isect.cuh — packed conservative filter over the
 filter entries of ssb_blob.hpp, nearest-candidate-first exact tests) compiled for the HOST by tools/isect_check.cpp and
 compared, hit record by hit record and bit for bit, with the reference's plain list scan (Scene::intersect,
-scene.cpp:433-445) on ~6 M rays (and as many ray PAIRS through the two-ray form scene_intersect2): random, surface-to-surface, edge / corner / diagonal targeted, grazing, axis-aligned,
+scene.cpp:433-445) on ~6 M rays: random, surface-to-surface, edge / corner / diagonal targeted, grazing, axis-aligned,
 tied (duplicated / coplanar quads), on the reference's own scenes (quads from the golden table dumps) and on synthetic
 ones (non-planar, degenerate, more than 32 filter entries, tiny / huge / far-from-origin coordinates).
 

@@ -126,24 +126,6 @@ void check_ray(const char* scene, Stats& st, V3 o, V3 d, int ignore, float eps, 
 		}
 		st.mismatches++;
 	}
-	// the two-rays-from-one-origin form (scene_intersect2): this ray + an unrelated second direction, each against its own
-	// list scan; an absent ray must come back as "no hit"
-	{
-		const V3 d2 = rand_dir();
-		Hit p0, p1, l1;
-		const int mode = (int)(st.rays % 4);  // both, both, only the first, only the second
-		const bool act0 = mode != 3, act1 = mode != 2;
-		scene_intersect2(S, eps, ignore, p0, p1, act0, act1, o.x, o.y, o.z, d.x, d.y, d.z, d2.x, d2.y, d2.z);
-		scene_intersect_listscan(S, eps, ignore, l1, o.x, o.y, o.z, d2.x, d2.y, d2.z);
-		Hit none; none.quad = -1;
-		const bool ok0 = same(p0, act0 ? b : none), ok1 = same(p1, act1 ? l1 : none);
-		if (!ok0 || !ok1) {
-			if (st.mismatches < 10)
-				fprintf(stderr, "MISMATCH (two-ray form, ray %d) %s: o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) d2=(%.9g %.9g %.9g) ignore=%d: quad %d/%d vs list scan %d/%d\n",
-				        ok0 ? 1 : 0, scene, o.x, o.y, o.z, d.x, d.y, d.z, d2.x, d2.y, d2.z, ignore, p0.quad, p1.quad, b.quad, l1.quad);
-			st.mismatches++;
-		}
-	}
 	if (out) *out = b;
 }
 
