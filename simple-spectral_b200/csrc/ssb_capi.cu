@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <initializer_list>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -139,9 +141,26 @@ struct ssb_ctx {
 	size_t resolve_capacity = 0;  // pixels
 
 	ssb_stats stats{};
+	// cached launch configuration (see ssb_render)
+	const void* occ_key_kernel = nullptr;
+	size_t occ_key_smem = 0;
+	int occ[4] = { 0, 0, 0, 0 };
 };
 
 namespace {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (device, kernel) shared by every context of the process:
+// it is only ever RAISED here, so that a context with small tables cannot lower it under one with large tables.
+cudaError_t raise_dynamic_smem_limit(int device, const void* kernel, size_t bytes) {
+	static std::mutex mu;
+	static std::map<std::pair<int, const void*>, size_t> limit;
+	std::lock_guard<std::mutex> lock(mu);
+	size_t& cur = limit[std::make_pair(device, kernel)];
+	if (bytes <= cur) return cudaSuccess;
+	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+	if (e == cudaSuccess) cur = bytes;
+	return e;
+}
 
 cudaError_t copy_to_device(ssb_ctx* c, void* dst, const void* src, size_t bytes) {
 	cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
@@ -274,7 +293,7 @@ int validate_options(const ssb_options* o, uint32_t& x1, uint32_t& y1, uint32_t&
 	return SSB_OK;
 }
 
-const size_t kWaveBudgetBytes = (size_t)12 << 30;  // device memory for the path state + fold records of one pass
+const size_t kWaveBudgetBytes = (size_t)24 << 30;  // device memory for the path state + fold records of one pass (of 180 GB)
 // counters, cleared once per pass: queue lengths [D+2] | hits per depth [D] | per-depth per-quad counts and cursors
 const size_t kCountsOff = 0, kNhitsOff = SSB_MAX_DEPTH + 2, kBinCountOff = kNhitsOff + SSB_MAX_DEPTH,
              kBinCursorOff = kBinCountOff + (size_t)SSB_MAX_DEPTH * SSB_MAX_QUADS,
@@ -552,7 +571,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 
 	// ---- size one pass: N = npix_rect * chunk samples share the wavefront buffers
 	const uint32_t nrec_depths = o->max_depth > 1 ? o->max_depth - 1 : 1;
-	const size_t bytes_per_sample = 2 * (32 + 32) + 32 + (size_t)nrec_depths * (16 + 16 + 8) + 16 + 8 + 4 + (4 + 4);
+	const size_t bytes_per_sample = 2 * (32 + 32) + 32 + (size_t)nrec_depths * 64 + 32 + 4 + (4 + 4);
 	size_t budget = kWaveBudgetBytes;
 	if (const char* e = getenv("SSB_WAVE_BUDGET_MB")) {  // tests force multi-pass rendering with a tiny budget
 		long mb = atol(e);
@@ -567,11 +586,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	const size_t o_a0 = off; off += up(N * 32); const size_t o_a1 = off; off += up(N * 32);
 	const size_t o_r0 = off; off += up(N * 32); const size_t o_r1 = off; off += up(N * 32);
 	const size_t o_h = off; off += up(N * 32);
-	const size_t o_sl = off; off += up(N * nrec_depths * 16);
-	const size_t o_sf = off; off += up(N * nrec_depths * 16);
-	const size_t o_sn = off; off += up(N * nrec_depths * 8);
-	const size_t o_leaf = off; off += up(N * 16);
-	const size_t o_meta = off; off += up(N * 8);
+	const size_t o_stk = off; off += up(N * nrec_depths * 64);
+	const size_t o_leaf = off; off += up(N * 32);
 	const size_t o_ff = off; off += up(N * 4);
 	const size_t o_hq = off; off += up(N * 4);
 	const size_t o_ord = off; off += up(N * 4);
@@ -590,9 +606,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.recA[0] = reinterpret_cast<float4*>(wv + o_a0); P.recA[1] = reinterpret_cast<float4*>(wv + o_a1);
 	P.recR[0] = reinterpret_cast<float4*>(wv + o_r0); P.recR[1] = reinterpret_cast<float4*>(wv + o_r1);
 	P.recH = reinterpret_cast<float4*>(wv + o_h);
-	P.stk_local = reinterpret_cast<float4*>(wv + o_sl); P.stk_f = reinterpret_cast<float4*>(wv + o_sf);
-	P.stk_np = reinterpret_cast<float2*>(wv + o_sn);
-	P.leaf = reinterpret_cast<float4*>(wv + o_leaf); P.meta = reinterpret_cast<float2*>(wv + o_meta);
+	P.stk = reinterpret_cast<float4*>(wv + o_stk);
+	P.leaf = reinterpret_cast<float4*>(wv + o_leaf);
 	P.ff = reinterpret_cast<float*>(wv + o_ff);
 	P.counts = c->d_counts + kCountsOff;
 	P.nhits = c->d_counts + kNhitsOff;
@@ -630,13 +645,19 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 		default: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_MENG>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_MENG>; break;
 	}
 	kfn k_isect_first = ssb_intersect_kernel<true>, k_isect_next = ssb_intersect_kernel<false>;
+	// dynamic shared memory opt-in + resident CTAs per SM: queried once per (kernel set, table size) and kept in the context
+	// (four attribute calls and four occupancy queries per ssb_render were a measurable part of a 2 ms strong-scaling slice)
 	int occ_sf = 0, occ_sn = 0, occ_if = 0, occ_in = 0;
-	for (kfn k : { k_shade_first, k_shade_next, k_isect_first, k_isect_next })
-		SSB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sf, k_shade_first, SSB_SHADE_THREADS, smem));
-	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, k_shade_next, SSB_SHADE_THREADS, smem));
-	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_if, k_isect_first, SSB_INTERSECT_THREADS, smem));
-	SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_in, k_isect_next, SSB_INTERSECT_THREADS, smem));
+	if (c->occ_key_kernel != (const void*)k_shade_next || c->occ_key_smem != smem) {
+		for (kfn k : { k_shade_first, k_shade_next, k_isect_first, k_isect_next })
+			SSB_CUDA(raise_dynamic_smem_limit(c->device, (const void*)k, smem));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[0], k_shade_first, SSB_SHADE_THREADS, smem));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[1], k_shade_next, SSB_SHADE_THREADS, smem));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[2], k_isect_first, SSB_INTERSECT_THREADS, smem));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[3], k_isect_next, SSB_INTERSECT_THREADS, smem));
+		c->occ_key_kernel = (const void*)k_shade_next; c->occ_key_smem = smem;
+	}
+	occ_sf = c->occ[0]; occ_sn = c->occ[1]; occ_if = c->occ[2]; occ_in = c->occ[3];
 	if (occ_sf < 1 || occ_sn < 1 || occ_if < 1 || occ_in < 1) return fail(SSB_ERR_UNSUPPORTED, "kernels do not fit on an SM with %zu bytes of tables", smem);
 	const uint32_t nquads = (uint32_t)c->quads.size();
 
@@ -666,14 +687,12 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 				SSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tex_ready, 0));
 				c->tex_pending = false;
 			}
-			ssb_bin_scan_kernel<<<1, 32, 0, c->stream>>>(P, nquads);
-			SSB_CUDA(cudaGetLastError());
 			const unsigned grid_b = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * 8, (P.total_work + 1023) / 1024);
-			ssb_bin_scatter_kernel<<<grid_b, 256, 0, c->stream>>>(P, d == 0 ? 1u : 0u, nquads);
+			ssb_bin_scatter_kernel<<<grid_b, SSB_MAX_QUADS, 0, c->stream>>>(P, d == 0 ? 1u : 0u, nquads);
 			SSB_CUDA(cudaGetLastError());
 			(d == 0 ? k_shade_first : k_shade_next)<<<grid_s, SSB_SHADE_THREADS, smem, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
-			launches += 4;
+			launches += 3;
 		}
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes + 1], c->stream));
 		ssb_fold_kernel<<<(unsigned)((P.total_work + 255) / 256), 256, 0, c->stream>>>(P);

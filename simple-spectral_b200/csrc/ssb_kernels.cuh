@@ -53,13 +53,15 @@ struct KParams {
 	float4* recA[2];
 	float4* recR[2];
 	float4* recH;
-	// per-depth records for the backward fold, indexed [depth][sample id]
-	float4* stk_local;
-	float4* stk_f;
-	float2* stk_np;     // n.l, pdf
-	// per-sample end of path
-	float4* leaf;       // value returned by the deepest L() call
-	float2* meta;       // lambda_0, (#records | hit<<16) as int bits
+	// per-depth records for the backward fold, indexed [depth][sample id]: ONE 64-byte record (two whole sectors)
+	//   {local radiance} {f_s} {n.l, pdf, -, -} {-}
+	// per vertex.  The sample ids of a warp are scattered (paths are sorted by hit quad), so anything smaller than a sector
+	// is a partial write that the L2 has to complete with a DRAM read before it can be written back: the three separate
+	// 16/16/8-byte arrays of round 1 cost ~96 B written + ~96 B read per vertex for 40 B of payload (ncu: the shade launches
+	// read 211 B per path for 68 B of records).  Whole records also mean the fold stage fetches no neighbour's bytes.
+	float4* stk;
+	// per-sample end of path, one 32-byte record: {value returned by the deepest L() call} {lambda_0, #records | hit<<16, -, -}
+	float4* leaf;
 	float* ff;          // dot(camera ray, camera dir), only when FLAT_FIELD_CORRECTION is off (renderer.cpp:265)
 	uint32_t* counts;   // queue length per depth; counts[0] = samples in the pass
 	// closest-hit records of the current depth (indexed like the input queue) and the sort-by-quad machinery
@@ -644,13 +646,13 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 	for (uint32_t q = threadIdx.x; q < SSB_MAX_QUADS; q += blockDim.x) s_bins[q] = 0;
 	__syncthreads();
 #if SSB_PIPELINE_ISECT
-	// [stage][record: recA.0, recA.1, recR.1][thread]
-	__shared__ float4 s_pipe[FIRST ? 1 : 2][FIRST ? 1 : 3][FIRST ? 1 : SSB_INTERSECT_THREADS];
+	// [stage][record: recA.0, recA.1][thread]  (the sample id, needed only by the few paths that miss, is fetched on demand:
+	// prefetching recR for every path moved 32 B per query for nothing)
+	__shared__ float4 s_pipe[FIRST ? 1 : 2][FIRST ? 1 : 2][FIRST ? 1 : SSB_INTERSECT_THREADS];
 	auto prefetch = [&](uint32_t it, int stage) {
 		if (!FIRST && it < n_in) {
 			cp_async16(&s_pipe[stage][0][threadIdx.x], &P.recA[pin][2 * (size_t)it]);
 			cp_async16(&s_pipe[stage][1][threadIdx.x], &P.recA[pin][2 * (size_t)it + 1]);
-			cp_async16(&s_pipe[stage][2][threadIdx.x], &P.recR[pin][2 * (size_t)it + 1]);
 		}
 		cp_async_commit();
 	};
@@ -724,14 +726,10 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				P.recH[2 * (size_t)item + 1] = make_float4(hit.bx, hit.by, hit.bz, 0.f);
 			} else {
 				// miss: L() returns 0 (renderer.cpp:161-163 with no hit); hit_anything only if an earlier depth hit
-#if SSB_PIPELINE_ISECT
-				const float4 r1 = FIRST ? P.recR[pin][2 * (size_t)item + 1] : s_pipe[cur][2][threadIdx.x];
-#else
 				const float4 r1 = P.recR[pin][2 * (size_t)item + 1];
-#endif
 				const uint32_t id = __float_as_uint(r1.x);
-				P.leaf[id] = make_float4(0.f, 0.f, 0.f, 0.f);
-				P.meta[id] = make_float2(r1.y, __int_as_float(depth | (FIRST ? 0 : (1 << 16))));
+				P.leaf[2 * (size_t)id] = make_float4(0.f, 0.f, 0.f, 0.f);
+				P.leaf[2 * (size_t)id + 1] = make_float4(r1.y, __int_as_float(depth | (FIRST ? 0 : (1 << 16))), 0.f, 0.f);
 			}
 			P.hit_q[item] = hq;
 		}
@@ -749,26 +747,39 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 		if (s_bins[q]) atomicAdd(&bins[q], s_bins[q]);
 }
 
-// ---- exclusive prefix sum of the per-quad hit counts of depth P.depth -> scatter cursors; one small CTA
-__global__ void ssb_bin_scan_kernel(const __grid_constant__ KParams P, uint32_t nquads) {
-	if (threadIdx.x != 0) return;
-	const uint32_t* cnt = P.bin_count + (size_t)P.depth * SSB_MAX_QUADS;
-	uint32_t* cur = P.bin_cursor + (size_t)P.depth * SSB_MAX_QUADS;
-	uint32_t acc = 0;
-	for (uint32_t q = 0; q < nquads; ++q) { cur[q] = acc; acc += cnt[q]; }
-	P.nhits[P.depth] = acc;
-}
-
-// ---- counting-sort scatter: order[] = queue positions of the hit paths, grouped by hit quad.  Each CTA takes tiles of
-// 4 x blockDim queue entries: it counts the tile's hits per quad in shared memory, reserves one contiguous range per
-// quad with a single global atomic, and places the entries through shared-memory cursors.
+// ---- counting-sort scatter: order[] = queue positions of the hit paths, grouped by hit quad.  Every CTA first turns the
+// per-quad hit counts of the depth (complete: the intersect launch has finished) into bin offsets with a block-wide
+// exclusive scan (<= SSB_MAX_QUADS = blockDim counters: cheaper than a separate one-thread launch per depth, which cost
+// a launch gap + ~5 us nine times per frame), then takes tiles of 4 x blockDim queue entries: it counts the tile's hits
+// per quad in shared memory, reserves one contiguous range per quad with a single global atomic on the quad's cursor
+// (zeroed with the other counters at the start of the pass), and places the entries through shared-memory cursors.
 #define SSB_SCATTER_PER_THREAD 4
-__global__ void __launch_bounds__(256) ssb_bin_scatter_kernel(const __grid_constant__ KParams P, uint32_t first_depth, uint32_t nquads) {
+__global__ void __launch_bounds__(SSB_MAX_QUADS) ssb_bin_scatter_kernel(const __grid_constant__ KParams P, uint32_t first_depth, uint32_t nquads) {
 	__shared__ uint32_t s_cnt[SSB_MAX_QUADS];
 	__shared__ uint32_t s_base[SSB_MAX_QUADS];
+	__shared__ uint32_t s_off[SSB_MAX_QUADS];
+	__shared__ uint32_t s_warp[SSB_MAX_QUADS / 32];
 	const int depth = (int)P.depth;
 	const uint32_t n_in = first_depth ? (uint32_t)P.total_work : P.counts[depth];
 	uint32_t* cur = P.bin_cursor + (size_t)depth * SSB_MAX_QUADS;
+	{
+		const uint32_t* cnt = P.bin_count + (size_t)depth * SSB_MAX_QUADS;
+		const uint32_t q = threadIdx.x, lane = q & 31u;
+		const uint32_t v = q < nquads ? cnt[q] : 0u;
+		uint32_t incl = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= (uint32_t)d) incl += t;
+		}
+		if (lane == 31u) s_warp[q >> 5] = incl;
+		__syncthreads();
+		uint32_t before = 0;
+		for (uint32_t w = 0; w < (q >> 5); ++w) before += s_warp[w];
+		s_off[q] = before + incl - v;
+		if (blockIdx.x == 0 && q == blockDim.x - 1) P.nhits[depth] = before + incl;  // total hits = length of `order`
+		__syncthreads();
+	}
 	const uint32_t tile = blockDim.x * SSB_SCATTER_PER_THREAD;
 	for (uint32_t t0 = blockIdx.x * tile; t0 < n_in; t0 += gridDim.x * tile) {
 		for (uint32_t q = threadIdx.x; q < nquads; q += blockDim.x) s_cnt[q] = 0;
@@ -783,7 +794,7 @@ __global__ void __launch_bounds__(256) ssb_bin_scatter_kernel(const __grid_const
 		__syncthreads();
 		for (uint32_t q = threadIdx.x; q < nquads; q += blockDim.x) {
 			const uint32_t c = s_cnt[q];
-			s_base[q] = c ? atomicAdd(&cur[q], c) : 0u;
+			s_base[q] = c ? s_off[q] + atomicAdd(&cur[q], c) : 0u;
 			s_cnt[q] = 0;
 		}
 		__syncthreads();
@@ -1013,10 +1024,11 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 					recurse = n_dot_l > 0.0f;
 				}
 				if (recurse) {
-					const size_t rec = (size_t)depth * P.total_work + id;
-					P.stk_local[rec] = make_float4(local.v[0], local.v[1], local.v[2], local.v[3]);
-					P.stk_f[rec] = make_float4(f_s.v[0], f_s.v[1], f_s.v[2], f_s.v[3]);
-					P.stk_np[rec] = make_float2(n_dot_l, pdf_w_i);
+					float4* rec = P.stk + 4 * ((size_t)depth * P.total_work + id);
+					rec[0] = make_float4(local.v[0], local.v[1], local.v[2], local.v[3]);
+					rec[1] = make_float4(f_s.v[0], f_s.v[1], f_s.v[2], f_s.v[3]);
+					rec[2] = make_float4(n_dot_l, pdf_w_i, 0.f, 0.f);
+					rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);  // (completes the second sector: no read-modify-write in the L2)
 					nrec = depth + 1;
 					// Dead-work skip (result-identical): with explicit light sampling the L() call at the last depth
 					// can add neither emission (last_was_delta == false) nor children: it returns 0, hit_anything is
@@ -1033,8 +1045,8 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			}
 			// ---- the path ends here: the deepest L() call returns `rad`, `nrec` records wait to be folded
 			if (!cont) {
-				P.leaf[id] = make_float4(rad.v[0], rad.v[1], rad.v[2], rad.v[3]);
-				P.meta[id] = make_float2(lambda_0, __int_as_float(nrec | (1 << 16)));
+				P.leaf[2 * (size_t)id] = make_float4(rad.v[0], rad.v[1], rad.v[2], rad.v[3]);
+				P.leaf[2 * (size_t)id + 1] = make_float4(lambda_0, __int_as_float(nrec | (1 << 16)), 0.f, 0.f);
 			}
 		}
 
@@ -1074,16 +1086,14 @@ __global__ void __launch_bounds__(256) ssb_fold_kernel(const __grid_constant__ K
 	const DevHeader* hdr = reinterpret_cast<const DevHeader*>(P.blob);
 	const float* pool = reinterpret_cast<const float*>(P.blob + hdr->off_pool);
 	const DevSpectrum sx = hdr->xbar, sy = hdr->ybar, sz = hdr->zbar;
-	const float4 lf = P.leaf[id];
-	const float2 mt = P.meta[id];
+	const float4 lf = P.leaf[2 * id], mt = P.leaf[2 * id + 1];
 	const float lambda_0 = mt.x;
 	const int info = __float_as_int(mt.y);
 	const int nrec = info & 0xffff;
 	float r0 = lf.x, r1 = lf.y, r2 = lf.z, r3 = lf.w;
 	for (int d = nrec - 1; d >= 0; --d) {
-		const size_t rec = (size_t)d * P.total_work + id;
-		const float4 lo = P.stk_local[rec], f = P.stk_f[rec];
-		const float2 np = P.stk_np[rec];
+		const float4* rec = P.stk + 4 * ((size_t)d * P.total_work + id);
+		const float4 lo = rec[0], f = rec[1], np = rec[2];
 		// Exact shortcut: the child radiance is +0 in all four channels (miss / skipped last depth — the common
 		// case at the deepest record) and n.l, pdf are positive finite, f_s non-negative finite: then
 		// ((+0*n.l)*f_s)/pdf is +0 and local + (+0) == local bit for bit (local is never -0: it is a sum that
