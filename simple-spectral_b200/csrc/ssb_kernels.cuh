@@ -604,6 +604,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- whole-sector accesses (sm_100: 256-bit LDG/STG).  A path record is one 32-byte sector; written as two 16-byte
+// stores it reaches the L2 as two PARTIAL sector writes, and the L2 completes a partially written sector with a DRAM read
+// (ncu, r5c: the intersect stage read 50 B per ray for 32 B of ray record, the shade stage 212 B per vertex for ~90 B).
+// One 32-byte store per record carries the full byte mask: no fill.
+__device__ __forceinline__ void st_sector(float4* p, const float4 a, const float4 b) {
+	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+__device__ __forceinline__ void ld_sector(const float4* p, float4& a, float4& b) {
+	asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p) : "memory");
+}
+
 #ifndef SSB_INTERSECT_THREADS
 #define SSB_INTERSECT_THREADS 256
 #endif
@@ -702,11 +713,11 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				// hero wavelength (renderer.cpp:134-143): drawn in spectral mode only
 				const float lambda_0 = (P.render_mode == SSB_RENDER_RGB) ? 0.0f : P.lambda_min + rand_1f(rng) * P.lambda_step;
 				if (!P.flat_field) P.ff[id] = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
-				P.recA[0][2 * (size_t)item] = make_float4(ox, oy, oz, __int_as_float(-1));
-				P.recA[0][2 * (size_t)item + 1] = make_float4(dx, dy, dz, lambda_0);
-				P.recR[0][2 * (size_t)item] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
-				                                          __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32)));
-				P.recR[0][2 * (size_t)item + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
+				st_sector(&P.recA[0][2 * (size_t)item], make_float4(ox, oy, oz, __int_as_float(-1)), make_float4(dx, dy, dz, lambda_0));
+				st_sector(&P.recR[0][2 * (size_t)item],
+				          make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
+				                      __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32))),
+				          make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f));
 			} else {
 #if SSB_PIPELINE_ISECT
 				const float4 a = s_pipe[cur][0][threadIdx.x], b = s_pipe[cur][1][threadIdx.x];
@@ -722,14 +733,13 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				hq = (uint32_t)hit.quad | ((uint32_t)hit.tri << 31);
 				// hit position (Ray::at, stdafx.hpp:219): origin of the shadow ray and of the next path ray
 				const float d_ = hit.dist;
-				P.recH[2 * (size_t)item] = make_float4(ox + d_ * dx, oy + d_ * dy, oz + d_ * dz, __uint_as_float(hq));
-				P.recH[2 * (size_t)item + 1] = make_float4(hit.bx, hit.by, hit.bz, 0.f);
+				st_sector(&P.recH[2 * (size_t)item], make_float4(ox + d_ * dx, oy + d_ * dy, oz + d_ * dz, __uint_as_float(hq)),
+				          make_float4(hit.bx, hit.by, hit.bz, 0.f));
 			} else {
 				// miss: L() returns 0 (renderer.cpp:161-163 with no hit); hit_anything only if an earlier depth hit
 				const float4 r1 = P.recR[pin][2 * (size_t)item + 1];
 				const uint32_t id = __float_as_uint(r1.x);
-				P.leaf[2 * (size_t)id] = make_float4(0.f, 0.f, 0.f, 0.f);
-				P.leaf[2 * (size_t)id + 1] = make_float4(r1.y, __int_as_float(depth | (FIRST ? 0 : (1 << 16))), 0.f, 0.f);
+				st_sector(&P.leaf[2 * (size_t)id], make_float4(0.f, 0.f, 0.f, 0.f), make_float4(r1.y, __int_as_float(depth | (FIRST ? 0 : (1 << 16))), 0.f, 0.f));
 			}
 			P.hit_q[item] = hq;
 		}
@@ -1025,10 +1035,8 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 				}
 				if (recurse) {
 					float4* rec = P.stk + 4 * ((size_t)depth * P.total_work + id);
-					rec[0] = make_float4(local.v[0], local.v[1], local.v[2], local.v[3]);
-					rec[1] = make_float4(f_s.v[0], f_s.v[1], f_s.v[2], f_s.v[3]);
-					rec[2] = make_float4(n_dot_l, pdf_w_i, 0.f, 0.f);
-					rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);  // (completes the second sector: no read-modify-write in the L2)
+					st_sector(rec, make_float4(local.v[0], local.v[1], local.v[2], local.v[3]), make_float4(f_s.v[0], f_s.v[1], f_s.v[2], f_s.v[3]));
+					st_sector(rec + 2, make_float4(n_dot_l, pdf_w_i, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
 					nrec = depth + 1;
 					// Dead-work skip (result-identical): with explicit light sampling the L() call at the last depth
 					// can add neither emission (last_was_delta == false) nor children: it returns 0, hit_anything is
@@ -1045,8 +1053,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			}
 			// ---- the path ends here: the deepest L() call returns `rad`, `nrec` records wait to be folded
 			if (!cont) {
-				P.leaf[2 * (size_t)id] = make_float4(rad.v[0], rad.v[1], rad.v[2], rad.v[3]);
-				P.leaf[2 * (size_t)id + 1] = make_float4(lambda_0, __int_as_float(nrec | (1 << 16)), 0.f, 0.f);
+				st_sector(&P.leaf[2 * (size_t)id], make_float4(rad.v[0], rad.v[1], rad.v[2], rad.v[3]), make_float4(lambda_0, __int_as_float(nrec | (1 << 16)), 0.f, 0.f));
 			}
 		}
 
@@ -1059,11 +1066,11 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			base = __shfl_sync(full, base, leader);
 			if (cont) {
 				const uint32_t o = base + __popc(mask & ((1u << lane) - 1u));
-				P.recA[pout][2 * (size_t)o] = make_float4(ox, oy, oz, __int_as_float(ignore));
-				P.recA[pout][2 * (size_t)o + 1] = make_float4(dx, dy, dz, lambda_0);
-				P.recR[pout][2 * (size_t)o] = make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
-				                                          __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32)));
-				P.recR[pout][2 * (size_t)o + 1] = make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f);
+				st_sector(&P.recA[pout][2 * (size_t)o], make_float4(ox, oy, oz, __int_as_float(ignore)), make_float4(dx, dy, dz, lambda_0));
+				st_sector(&P.recR[pout][2 * (size_t)o],
+				          make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
+				                      __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32))),
+				          make_float4(__uint_as_float(id), lambda_0, 0.f, 0.f));
 			}
 		}
 #if SSB_PIPELINE_SHADE
@@ -1086,14 +1093,17 @@ __global__ void __launch_bounds__(256) ssb_fold_kernel(const __grid_constant__ K
 	const DevHeader* hdr = reinterpret_cast<const DevHeader*>(P.blob);
 	const float* pool = reinterpret_cast<const float*>(P.blob + hdr->off_pool);
 	const DevSpectrum sx = hdr->xbar, sy = hdr->ybar, sz = hdr->zbar;
-	const float4 lf = P.leaf[2 * id], mt = P.leaf[2 * id + 1];
+	float4 lf, mt;
+	ld_sector(&P.leaf[2 * id], lf, mt);
 	const float lambda_0 = mt.x;
 	const int info = __float_as_int(mt.y);
 	const int nrec = info & 0xffff;
 	float r0 = lf.x, r1 = lf.y, r2 = lf.z, r3 = lf.w;
 	for (int d = nrec - 1; d >= 0; --d) {
 		const float4* rec = P.stk + 4 * ((size_t)d * P.total_work + id);
-		const float4 lo = rec[0], f = rec[1], np = rec[2];
+		float4 lo, f;
+		ld_sector(rec, lo, f);
+		const float4 np = rec[2];
 		// Exact shortcut: the child radiance is +0 in all four channels (miss / skipped last depth — the common
 		// case at the deepest record) and n.l, pdf are positive finite, f_s non-negative finite: then
 		// ((+0*n.l)*f_s)/pdf is +0 and local + (+0) == local bit for bit (local is never -0: it is a sum that
