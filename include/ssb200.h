@@ -27,8 +27,10 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 3u /* 2: RGB render mode (ssb_material.*_rgb, ssb_options.render_mode), n_wavelengths;
-                           * 3: ssb_options.prebaked_textures (was `reserved`) */
+#define SSB_ABI_VERSION 4u /* 2: RGB render mode (ssb_material.*_rgb, ssb_options.render_mode), n_wavelengths;
+                           * 3: ssb_options.prebaked_textures (was `reserved`);
+                           * 4: ssb_options.band_* / scan_mode (appended), ssb_device_count, ssb_accum_merge,
+                           *    ssb_debug_intersect */
 
 #define SSB_OK 0
 #define SSB_ERR_DATA (-1)
@@ -171,7 +173,17 @@ typedef struct ssb_options {
 	                                   * the polynomial — the pre-process Jakob & Hanika intend, which the reference describes but
 	                                   * does not implement (color.cpp:204-216,222-223).  The coefficients are the same floats the
 	                                   * per-lookup form computes, so results do not change by a bit; costs 16 B/texel of HBM. */
+	/* Multi-GPU row bands (the reference's Framebuffer::Tile decomposition, framebuffer.hpp:14-21, renderer.cpp:399-406,
+	 * dealt out statically): with band_count > 1 this call renders only the image rows j with
+	 * (j / band_height) % band_count == band_index — interleaved bands of band_height rows, so that every GPU gets a
+	 * share of the expensive and of the cheap rows.  Requires y0 == 0 and y1 == 0 or height.  Per-sample seeding makes
+	 * every pixel's samples the ones a single-GPU render draws: the merged frame is bit-identical.  0/0/0 = off. */
+	uint32_t band_height, band_count, band_index;
+	uint32_t scan_mode;               /* SSB_SCAN_*: how Scene::intersect's linear scan is executed (same hit record either way) */
 } ssb_options;
+#define SSB_SCAN_FILTERED 0u /* conservative packed filter + exact tests on the candidates (the default) */
+#define SSB_SCAN_LIST 1u     /* the reference's own loop: every quad, tri0 then tri1, exact test only (scene.cpp:433-445) —
+                              * the yardstick the filtered scan is fuzzed against on the device */
 
 typedef struct ssb_stats {
 	uint64_t samples;      /* path samples traced by the last ssb_render */
@@ -187,6 +199,7 @@ const char* ssb_last_error(void);
 /* fills *opt with the reference's defaults (stdafx.hpp:44-90) for a WxH image */
 void ssb_default_options(ssb_options* opt, uint32_t width, uint32_t height, uint32_t spp);
 
+int ssb_device_count(int* count); /* CUDA devices visible to this process (0 and SSB_ERR_DATA without a GPU) */
 int ssb_create(int device, ssb_ctx** out);
 void ssb_destroy(ssb_ctx* ctx);
 
@@ -217,6 +230,17 @@ int ssb_read_accum(ssb_ctx* ctx, double* dst_host);
 int ssb_write_accum(ssb_ctx* ctx, const double* src_host);
 int ssb_accum_device(ssb_ctx* ctx, double** dptr, size_t* count);
 
+/* Multi-GPU inside one process (the reference's Renderer uses every execution unit of the box by itself,
+ * renderer.cpp:396-430): fold the accumulator of `src` into the accumulator of `dst` (same resolution; the contexts may
+ * live on different GPUs).  `src_opt` = the options `src` rendered its share with:
+ *   - a pixel subset (band_count > 1, or a pixel rectangle smaller than the image): those pixels are COPIED from src
+ *     (disjoint tiles: a gather, bit-exact);
+ *   - otherwise (a sample range of the whole frame): dst += src, element-wise in f64.
+ * Ordered after everything already enqueued on either context's stream, asynchronous with respect to the host; src's
+ * stream in turn waits until dst has consumed the data.  Uses direct peer access (NVLink) when the devices allow it,
+ * else a peer copy into a staging buffer on dst's device. */
+int ssb_accum_merge(ssb_ctx* dst, ssb_ctx* src, const ssb_options* src_opt);
+
 /* Finish a frame: avg = accum * (1000/spp) (renderer.cpp:296), then
  * sRGBA = (ciexyz_to_srgb(float3(avg)), float(avg.a)) (renderer.cpp:298, color.cpp:237-257).
  * RGB mode: avg = accum / spp, sRGBA = (lrgb_to_srgb(float3(avg)), float(avg.a)) (renderer.cpp:304-306).
@@ -243,6 +267,12 @@ int ssb_synchronize(ssb_ctx* ctx);
  * evaluates fn over n inputs ON THE GPU.  fn: 0 sinf, 1 cosf, 2 acosf, 3 powf(x, y=arg),
  * 4 / 5: the sin / cos result of the paired sincos the kernels use. */
 int ssb_debug_eval_math(ssb_ctx* ctx, uint32_t fn, const float* x_host, float arg, float* out_host, size_t n);
+/* Closest-hit queries of n caller-supplied rays against the uploaded scene, on the GPU, through the same
+ * scene_intersect the render kernels call (scan_mode: SSB_SCAN_*).  rays: n x {origin[3], dir[3]}; ignore: n quad
+ * indices or -1 (may be NULL = none); out: n x {quad (int bits, -1 = miss), tri (int bits), dist, bx, by, bz}.
+ * Test hook of the conservative filter: tests/test_gpu_isect_fuzz.py compares SSB_SCAN_FILTERED with the oracle's scan. */
+int ssb_debug_intersect(ssb_ctx* ctx, const float* rays6_host, const int32_t* ignore_host, uint32_t scan_mode, float eps,
+                        float* out6_host, size_t n);
 /* Per-sample outputs of one pixel (float4 per sample), for matched-seed debugging. */
 int ssb_debug_trace_samples(ssb_ctx* ctx, const ssb_options* opt, uint32_t px, uint32_t py, float* out_host);
 

@@ -58,7 +58,17 @@ typedef struct ssbh_renderer_options {
 	uint32_t prebaked_textures; /* ssb_options.prebaked_textures (JH coefficient textures, color.cpp:204-216) */
 	uint32_t progressive; /* 1: render in sample slices 1,1,2,4,... and refresh the framebuffer after each (the live
 	                       * preview of the reference's window, main.cpp:316-323); the final image is unchanged */
+	/* Multi-GPU (appended in ABI 4; the reference's Renderer uses every execution unit of the box by itself,
+	 * renderer.cpp:396-430): ndevices > 0 renders on devices[0..ndevices) (one context + host thread each; `device` is
+	 * then ignored), merged and resolved on devices[0].  shard: 0 = interleaved bands of band_height rows (0 = 8, the
+	 * reference's tile edge; bit-identical to one GPU), 1 = sample ranges (differs by f64 summation order only). */
+	const int* devices;
+	uint32_t ndevices;
+	uint32_t shard;
+	uint32_t band_height;
 } ssbh_renderer_options;
+#define SSBH_SHARD_TILES 0u
+#define SSBH_SHARD_SAMPLES 1u
 int ssbh_renderer_new(const ssbh_renderer_options* options, ssbh_renderer** out);
 int ssbh_renderer_render(ssbh_renderer* r); /* render_start() + render_wait() */
 /* The reference's asynchronous life cycle (renderer.hpp:71-81; main.cpp:313-327): start returns at once, a caller polls

@@ -11,7 +11,7 @@
  *
  * Pinning: this file is checked bit-for-bit against the real reference compiled here
  * (oracle/_ref/simple_spectral_*_hooked, see oracle/build_ref.py) at matched per-sample seeds:
- * tests/test_oracle_vs_ref.py (live, when oracle/_ref exists) and the committed fixtures under
+ * tests/test_oracle_golden.py (live, when oracle/_ref exists) and the committed fixtures under
  * tests/golden/ (made by tests/golden/make_golden.py).
  *
  * Third-party arithmetic the reference inherits and that is NOT under /root/reference:
@@ -318,6 +318,8 @@ typedef struct {
 	v3 normal;
 	v2 st;
 	float dist;
+	int tri;           /* which triangle of the quad, and its barycentrics: not in the reference's HitRecord (it keeps only */
+	float bx, by, bz;  /* normal and st); recorded for ssb_oracle_intersect, the yardstick of the device's hit records */
 } hitrec_t;
 typedef struct { v3 orig, dir; } ray_t;
 
@@ -372,6 +374,7 @@ static int tri_intersect(const octx* c, const ssb_tri* tri, const ray_t* ray, hi
 		hitrec->st.x = bx * tri->v[0].st[0] + by * tri->v[1].st[0] + bz * tri->v[2].st[0];
 		hitrec->st.y = bx * tri->v[0].st[1] + by * tri->v[1].st[1] + bz * tri->v[2].st[1];
 		hitrec->dist = dist;
+		hitrec->bx = bx; hitrec->by = by; hitrec->bz = bz;
 		return 1;
 	}
 	return 0;
@@ -386,9 +389,9 @@ static int scene_intersect(const octx* c, const ray_t* ray, hitrec_t* hitrec, in
 		if ((int)q == ignore) continue;
 		const ssb_quad* quad = &c->scene->quads[q];
 		if (c->counters) c->counters->tri_tests++;
-		int h = tri_intersect(c, &quad->tri[0], ray, hitrec);
-		if (!h) { if (c->counters) c->counters->tri_tests++; h = tri_intersect(c, &quad->tri[1], ray, hitrec); }
-		if (h) { hitrec->quad = (int)q; hit = 1; }
+		int h = tri_intersect(c, &quad->tri[0], ray, hitrec), t = 0;
+		if (!h) { if (c->counters) c->counters->tri_tests++; h = tri_intersect(c, &quad->tri[1], ray, hitrec); t = 1; }
+		if (h) { hitrec->quad = (int)q; hitrec->tri = t; hit = 1; }
 	}
 	return hit;
 }
@@ -661,6 +664,33 @@ static int prepare(octx* c, const ssb_scene* scene, const ssb_color* color, cons
 	return SSB_OK;
 }
 
+/* Scene::intersect (scene.cpp:433-445) for n caller-supplied rays: rays6 = n x {origin, direction}, ignore = n quad
+ * indices or -1 (or NULL), out6 = n x {quad (int bits, -1: miss), tri (int bits), dist, barycentrics U,V,W * det_recip}.
+ * The yardstick of tests/test_gpu_isect_fuzz.py for the device's filtered scan. */
+int ssb_oracle_intersect(const ssb_scene* scene, const float* rays6, const int32_t* ignore, float eps, float* out6, size_t n) {
+	if (!scene || !rays6 || !out6) return SSB_ERR_ARG;
+	ssb_options opt;
+	memset(&opt, 0, sizeof(opt));
+	opt.eps = eps;
+	octx c;
+	memset(&c, 0, sizeof(c));
+	c.scene = scene; c.opt = &opt;
+	#pragma omp parallel for schedule(static)
+	for (long long r = 0; r < (long long)n; ++r) {
+		ray_t ray;
+		ray.orig = v3_make(rays6[6 * r], rays6[6 * r + 1], rays6[6 * r + 2]);
+		ray.dir = v3_make(rays6[6 * r + 3], rays6[6 * r + 4], rays6[6 * r + 5]);
+		hitrec_t h;
+		memset(&h, 0, sizeof(h));
+		scene_intersect(&c, &ray, &h, ignore ? ignore[r] : -1);
+		int32_t q = h.quad, t = h.quad >= 0 ? h.tri : 0;
+		memcpy(out6 + 6 * r, &q, 4); memcpy(out6 + 6 * r + 1, &t, 4);
+		out6[6 * r + 2] = h.dist;
+		out6[6 * r + 3] = h.quad >= 0 ? h.bx : 0.0f; out6[6 * r + 4] = h.quad >= 0 ? h.by : 0.0f; out6[6 * r + 5] = h.quad >= 0 ? h.bz : 0.0f;
+	}
+	return SSB_OK;
+}
+
 /* Renderer::_render_pixel's sample loop, renderer.cpp:292-295: accum += double4(sample * 0.001f) */
 int ssb_oracle_render(const ssb_scene* scene, const ssb_color* color, const ssb_options* opt,
                       double* accum, float* samples_out, ssb_oracle_counters* counters) {
@@ -681,6 +711,8 @@ int ssb_oracle_render(const ssb_scene* scene, const ssb_color* color, const ssb_
 		c.counters = counters ? &local : NULL;
 		#pragma omp for schedule(dynamic, 1)
 		for (uint32_t j = opt->y0; j < y1; ++j) {
+			/* ssb_options.band_*: only the rows of this share of the interleaved row bands (include/ssb200.h) */
+			if (opt->band_count > 1 && (opt->band_height == 0 || (j / opt->band_height) % opt->band_count != opt->band_index)) continue;
 			for (uint32_t i = opt->x0; i < x1; ++i) {
 				size_t pixel = (size_t)j * opt->width + i;
 				double* avg = accum ? accum + 4 * pixel : NULL;

@@ -15,6 +15,7 @@ typedef struct ssb_oracle_counters { /* path statistics, all uin
 int ssb_oracle_render(const ssb_scene* scene, const ssb_color* color, const ssb_options* opt,
                       double* accum, float* samples_out, ssb_oracle_counters* counters);
 int ssb_oracle_resolve(const ssb_color* color, const ssb_options* opt, const double* accum, double* xyza, float* srgba);
+int ssb_oracle_intersect(const ssb_scene* scene, const float* rays6, const int32_t* ignore, float eps, float* out6, size_t n);
 void ssb_oracle_eval_math(uint32_t fn, const float* x, float arg, float* out, size_t n);
 #ifdef __cplusplus
 }

@@ -55,9 +55,13 @@ def lib():
     L.ssb_synchronize.argtypes = [C.c_void_p]
     L.ssb_debug_eval_math.argtypes = [C.c_void_p, C.c_uint32, P(C.c_float), C.c_float, P(C.c_float), C.c_size_t]
     L.ssb_debug_trace_samples.argtypes = [C.c_void_p, P(_abi.ssb_options), C.c_uint32, C.c_uint32, P(C.c_float)]
+    L.ssb_device_count.argtypes = [P(C.c_int)]
+    L.ssb_accum_merge.argtypes = [C.c_void_p, C.c_void_p, P(_abi.ssb_options)]
+    L.ssb_debug_intersect.argtypes = [C.c_void_p, P(C.c_float), P(C.c_int32), C.c_uint32, C.c_float, P(C.c_float), C.c_size_t]
     for name in ("ssb_create", "ssb_upload_scene", "ssb_upload_scene_async", "ssb_upload_color", "ssb_render", "ssb_clear", "ssb_read_accum",
                  "ssb_write_accum", "ssb_accum_device", "ssb_resolve", "ssb_resolve_device", "ssb_set_stream",
-                 "ssb_render_frame", "ssb_get_stats", "ssb_synchronize", "ssb_debug_eval_math", "ssb_debug_trace_samples"):
+                 "ssb_render_frame", "ssb_get_stats", "ssb_synchronize", "ssb_debug_eval_math", "ssb_debug_trace_samples",
+                 "ssb_device_count", "ssb_accum_merge", "ssb_debug_intersect"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -67,13 +71,19 @@ EXPORTED_SYMBOLS = (
     "ssb_abi_version", "ssb_last_error", "ssb_default_options", "ssb_create", "ssb_destroy", "ssb_upload_scene",
     "ssb_upload_scene_async", "ssb_upload_color", "ssb_render", "ssb_clear", "ssb_read_accum", "ssb_write_accum", "ssb_accum_device",
     "ssb_resolve", "ssb_resolve_device", "ssb_set_stream", "ssb_render_frame", "ssb_get_stats", "ssb_synchronize", "ssb_debug_eval_math",
-    "ssb_debug_trace_samples",
+    "ssb_debug_trace_samples", "ssb_device_count", "ssb_accum_merge", "ssb_debug_intersect",
 )
 
 
 def check(code):
     if code != 0:
         raise SsbError(code, lib().ssb_last_error().decode(errors="replace"))
+
+
+def device_count():
+    n = C.c_int()
+    check(lib().ssb_device_count(C.byref(n)))
+    return n.value
 
 
 class Context:
@@ -170,6 +180,23 @@ class Context:
 
     def synchronize(self):
         check(lib().ssb_synchronize(self._h))
+
+    def merge_from(self, src, src_opt):
+        """ssb_accum_merge: fold the accumulator of `src` (another Context, possibly on another GPU) into this one;
+        `src_opt` = the options src rendered its share with (pixel subset: copied; sample range: added)."""
+        check(lib().ssb_accum_merge(self._h, src._h, C.byref(src_opt)))
+
+    def intersect(self, rays, ignore=None, scan_mode=0, eps=1e-3):
+        """ssb_debug_intersect: closest hits of n rays (n x 6: origin, direction) -> (quad, tri, dist, bary[n,3])."""
+        import numpy as np
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        n = rays.shape[0]
+        out = np.empty((n, 6), np.float32)
+        ign = None if ignore is None else np.ascontiguousarray(ignore, np.int32)
+        check(lib().ssb_debug_intersect(self._h, rays.ctypes.data_as(C.POINTER(C.c_float)),
+                                        ign.ctypes.data_as(C.POINTER(C.c_int32)) if ign is not None else None,
+                                        int(scan_mode), float(eps), out.ctypes.data_as(C.POINTER(C.c_float)), n))
+        return out[:, 0].view(np.int32).copy(), out[:, 1].view(np.int32).copy(), out[:, 2].copy(), out[:, 3:6].copy()
 
     def eval_math(self, fn, x, arg=0.0):
         import numpy as np

@@ -7,6 +7,7 @@ SSB_MATERIAL_LAMBERT, SSB_MATERIAL_MIRROR = 0, 1
 SSB_ALBEDO_CONSTANT, SSB_ALBEDO_TEXTURE = 0, 1
 SSB_UPSAMPLE_OURS, SSB_UPSAMPLE_MENG, SSB_UPSAMPLE_JH = 1, 2, 3
 SSB_RENDER_SPECTRAL, SSB_RENDER_RGB = 0, 1
+SSB_SCAN_FILTERED, SSB_SCAN_LIST = 0, 1
 
 
 class ssb_vertex(C.Structure):
@@ -69,7 +70,9 @@ class ssb_options(C.Structure):
                 ("max_depth", C.c_uint32), ("explicit_light_sampling", C.c_uint32),
                 ("flat_field_correction", C.c_uint32), ("eps", C.c_float), ("seed", C.c_uint64),
                 ("render_mode", C.c_uint32), ("n_wavelengths", C.c_uint32),
-                ("keep_accumulator", C.c_uint32), ("prebaked_textures", C.c_uint32)]
+                ("keep_accumulator", C.c_uint32), ("prebaked_textures", C.c_uint32),
+                ("band_height", C.c_uint32), ("band_count", C.c_uint32), ("band_index", C.c_uint32),
+                ("scan_mode", C.c_uint32)]
 
 
 class ssb_stats(C.Structure):

@@ -30,6 +30,8 @@ void print_usage() {
 		"    --variant=ours1931|ours2006|meng|jh|rgb   (the reference's compile-time modes)\n"
 		"    --wavelengths=2|3|4                       (SAMPLE_WAVELENGTHS, default 4)\n"
 		"    --seed=<n>  --device=<n>  --data-root=<dir containing data/>\n"
+		"    --devices=<a-b | a,b,c | all> [--shard=tiles|samples]   (several GPUs: interleaved row bands, bit-identical\n"
+		"                                              to one GPU, or sample ranges)\n"
 		"    --prebake                                 (variant jh: texel -> coefficient textures, once)\n"
 		"    --progressive [--preview=<path>]          (refine in sample slices; rewrite <path> after each)\n");
 }
@@ -102,6 +104,33 @@ int main(int argc, char* argv[]) {
 		} catch (int code) { if (code != -2) throw; }
 		try { o.seed = std::strtoull(a.get("--seed", "--seed").c_str(), nullptr, 10); } catch (int code) { if (code != -2) throw; }
 		try { o.device = std::atoi(a.get("--device", "--device").c_str()); } catch (int code) { if (code != -2) throw; }
+		try {  // --devices=0-7 | --devices=0,2,5 | --devices=all: render on several GPUs of the box
+			std::string v = a.get("--devices", "--devices");
+			if (v == "all") {
+				int n = 0;
+				if (ssb_device_count(&n) != SSB_OK) { std::fprintf(stderr, "%s\n", ssb_last_error()); throw -1; }
+				for (int d = 0; d < n; ++d) o.devices.push_back(d);
+			} else {
+				size_t pos = 0;
+				while (pos <= v.size()) {
+					size_t comma = v.find(',', pos);
+					std::string item = v.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+					size_t dash = item.find('-');
+					try {
+						if (dash == std::string::npos) o.devices.push_back(std::stoi(item));
+						else { int lo = std::stoi(item.substr(0, dash)), hi = std::stoi(item.substr(dash + 1)); if (hi < lo || hi - lo > 63) throw -1; for (int d = lo; d <= hi; ++d) o.devices.push_back(d); }
+					} catch (...) { std::fprintf(stderr, "Invalid device list \"%s\"!\n", v.c_str()); throw -1; }
+					if (comma == std::string::npos) break;
+					pos = comma + 1;
+				}
+			}
+		} catch (int code) { if (code != -2) throw; }
+		try {
+			std::string v = a.get("--shard", "--shard");
+			if (v == "tiles") o.shard = ssbh::RendererOptions::SHARD_TILES;
+			else if (v == "samples") o.shard = ssbh::RendererOptions::SHARD_SAMPLES;
+			else { std::fprintf(stderr, "Unknown shard mode \"%s\" (tiles | samples)\n", v.c_str()); throw -1; }
+		} catch (int code) { if (code != -2) throw; }
 		try { o.data_root = a.get("--data-root", "--data-root"); } catch (int code) { if (code != -2) throw; }
 		try { a.get("--prebake", "--prebake"); o.prebaked_textures = true; } catch (int code) { if (code != -2) throw; }
 		try { a.get("--progressive", "--progressive"); o.progressive = true; } catch (int code) { if (code != -2) throw; }
@@ -128,12 +157,22 @@ int main(int argc, char* argv[]) {
 			}
 		}
 		renderer.render_wait();
-		std::printf("%.3f Mpath-samples/s on the device (%llu samples, %.3f ms)\n",
-		            renderer.last_stats.samples / renderer.last_stats.device_ms / 1e3,
-		            (unsigned long long)renderer.last_stats.samples, renderer.last_stats.device_ms);
+		if (!preview_path.empty()) {  // the last slices may have finished between two polls: the preview ends on the final image
+			ssbh::Framebuffer shot;
+			shot.res[0] = o.res[0]; shot.res[1] = o.res[1];
+			renderer.snapshot(shot.pixels);
+			shot.save(preview_path);
+		}
+		if (renderer.last_stats.device_ms > 0)
+			std::printf("%.3f Mpath-samples/s on the device%s (%llu samples, %.3f ms)\n",
+			            renderer.last_stats.samples / renderer.last_stats.device_ms / 1e3, renderer.device_count() > 1 ? "s" : "",
+			            (unsigned long long)renderer.last_stats.samples, renderer.last_stats.device_ms);
 	} catch (ssbh::Error const& e) {
 		std::fprintf(stderr, "%s\n", e.message.c_str());
 		return e.code;
+	} catch (std::exception const& e) {  // bad_alloc, length_error, ...: the reference would abort; report and fail
+		std::fprintf(stderr, "%s\n", e.what());
+		return -1;
 	}
 	return 0;
 }

@@ -122,6 +122,13 @@ int ssbh_renderer_new(const ssbh_renderer_options* o, ssbh_renderer** out) {
 		r.data_root = o->data_root ? o->data_root : ".";
 		r.prebaked_textures = o->prebaked_textures != 0;
 		r.progressive = o->progressive != 0;
+		if (o->ndevices) {
+			if (!o->devices) throw Error{ SSB_ERR_ARG, "ssbh_renderer_new: devices is NULL" };
+			r.devices.assign(o->devices, o->devices + o->ndevices);
+		}
+		if (o->shard > SSBH_SHARD_SAMPLES) throw Error{ SSB_ERR_UNSUPPORTED, "ssbh_renderer_new: unknown shard mode" };
+		r.shard = o->shard;
+		if (o->band_height) r.band_height = o->band_height;
 		*out = new ssbh_renderer{ new Renderer(r) };
 	});
 }

@@ -18,20 +18,43 @@ Renderer::Renderer(RendererOptions const& opts) : options(opts) {
 		std::fprintf(stderr, "Warning: Plane converges much faster without explicit light sampling!\n");
 	if (options.scene_name != "plane-srgb" && !options.explicit_light_sampling)  // renderer.cpp:18-26
 		std::fprintf(stderr, "Warning: Cornell converges much faster with explicit light sampling!\n");
-	int rc = ssb_create(options.device, &ctx_);
-	if (rc != SSB_OK) throw Error{ rc, ssb_last_error() };
+	devices_ = options.devices.empty() ? std::vector<int>{ options.device } : options.devices;
+	ctxs_.assign(devices_.size(), nullptr);
+	// one thread per device: context creation and the texture upload (48 MiB) of the GPUs overlap
+	std::vector<Error> errs(devices_.size(), Error{ 0, "" });
 	ssb_color fc = color.flat();
-	if ((rc = ssb_upload_color(ctx_, &fc)) != SSB_OK || (rc = ssb_upload_scene(ctx_, &scene.flat)) != SSB_OK) {
-		std::string msg = ssb_last_error();
-		ssb_destroy(ctx_);
-		ctx_ = nullptr;
-		throw Error{ rc, msg };
+	auto setup = [&](size_t d) {
+		int rc = ssb_create(devices_[d], &ctxs_[d]);
+		if (rc == SSB_OK) rc = ssb_upload_color(ctxs_[d], &fc);
+		if (rc == SSB_OK) rc = ssb_upload_scene(ctxs_[d], &scene.flat);
+		if (rc != SSB_OK) errs[d] = Error{ rc, ssb_last_error() };
+	};
+	if (devices_.size() == 1) setup(0);
+	else {
+		std::vector<std::thread> th;
+		for (size_t d = 0; d < devices_.size(); ++d) th.emplace_back(setup, d);
+		for (auto& t : th) t.join();
 	}
+	Error bad{ 0, "" };
+	for (auto const& e : errs) if (e.code != 0 && bad.code == 0) bad = e;
+	if (bad.code == 0 && devices_.size() > 1) {
+		int rc = ssb_create(devices_[0], &sum_ctx_);
+		if (rc == SSB_OK) rc = ssb_upload_color(sum_ctx_, &fc);  // resolve needs the XYZ -> l-RGB matrix
+		if (rc != SSB_OK) bad = Error{ rc, ssb_last_error() };
+	}
+	if (bad.code != 0) {
+		for (ssb_ctx* c : ctxs_) if (c) ssb_destroy(c);
+		if (sum_ctx_) ssb_destroy(sum_ctx_);
+		ctxs_.clear(); sum_ctx_ = nullptr;
+		throw bad;
+	}
+	ctx_ = sum_ctx_ ? sum_ctx_ : ctxs_[0];
 }
 Renderer::~Renderer() {
 	continue_ = false;
 	if (worker_.joinable()) worker_.join();
-	if (ctx_) ssb_destroy(ctx_);
+	for (ssb_ctx* c : ctxs_) if (c) ssb_destroy(c);
+	if (sum_ctx_) ssb_destroy(sum_ctx_);
 }
 
 ssb_options Renderer::make_options() const {
@@ -62,6 +85,61 @@ void Renderer::render_start() {
 // framebuffer refreshed after each slice with the average so far (`ssb_resolve` with spp = samples done).  Sample
 // ranges accumulate in sample order into the context's f64 accumulator (ssb_render does not clear it for
 // sample_begin > 0), so the finished frame is bit-identical to the single-call one.
+// One slice of the sample range on every device.  Single GPU: one ssb_render.  Several: each device renders its share
+// (its interleaved row bands of the slice's samples, or its part of the slice's sample range) from its own host thread —
+// the ~30 kernel launches of a pass are enqueued concurrently, not device after device — into its own accumulator.
+void Renderer::render_slice(ssb_options const& slice, ssb_stats& sum) {
+	const size_t nd = ctxs_.size();
+	if (nd == 1) {
+		int rc = ssb_render(ctxs_[0], &slice);
+		if (rc != SSB_OK) throw Error{ rc, ssb_last_error() };
+		ssb_stats st{};
+		ssb_get_stats(ctxs_[0], &st);
+		sum.samples += st.samples; sum.device_ms += st.device_ms; sum.trace_ms += st.trace_ms; sum.launches += st.launches;
+		return;
+	}
+	std::vector<ssb_options> part(nd, slice);
+	std::vector<char> active(nd, 1);
+	const uint32_t s0 = slice.sample_begin, s1 = slice.sample_end ? slice.sample_end : slice.spp;
+	for (size_t d = 0; d < nd; ++d) {
+		part[d].keep_accumulator = 1;  // the accumulators are cleared once per frame (work()): later slices add to them
+		if (options.shard == RendererOptions::SHARD_SAMPLES) {
+			const uint32_t b = s0 + (uint32_t)((uint64_t)(s1 - s0) * d / nd), e = s0 + (uint32_t)((uint64_t)(s1 - s0) * (d + 1) / nd);
+			part[d].sample_begin = b; part[d].sample_end = e;
+			active[d] = e > b;
+			if (e == 0) active[d] = 0;  // (sample_end == 0 would mean "all")
+		} else {
+			part[d].band_height = options.band_height; part[d].band_count = (uint32_t)nd; part[d].band_index = (uint32_t)d;
+			active[d] = (uint64_t)d * options.band_height < slice.height;
+		}
+	}
+	std::vector<Error> errs(nd, Error{ 0, "" });
+	std::vector<std::thread> th;
+	for (size_t d = 0; d < nd; ++d) {
+		if (!active[d]) continue;
+		th.emplace_back([&, d] {
+			int rc = ssb_render(ctxs_[d], &part[d]);
+			if (rc != SSB_OK) errs[d] = Error{ rc, ssb_last_error() };
+		});
+	}
+	for (auto& t : th) t.join();
+	for (auto const& e : errs) if (e.code != 0) throw e;
+	double ms = 0, trace = 0;
+	for (size_t d = 0; d < nd; ++d) {
+		if (!active[d]) continue;
+		ssb_stats st{};
+		ssb_get_stats(ctxs_[d], &st);  // (waits for that device: the GPUs run concurrently, the slice takes the longest of them)
+		sum.samples += st.samples; sum.launches += st.launches;
+		ms = std::max(ms, st.device_ms); trace = std::max(trace, st.trace_ms);
+	}
+	sum.device_ms += ms; sum.trace_ms += trace;
+}
+
+// The worker: the whole frame in one device call, or — progressive — in sample slices of doubling size, the
+// framebuffer refreshed after each slice with the average so far (`ssb_resolve` with spp = samples done).  Sample
+// ranges accumulate in sample order into the context's f64 accumulator (ssb_render does not clear it for
+// sample_begin > 0), so the finished frame is bit-identical to the single-call one.  With several GPUs the per-device
+// accumulators are merged into a separate accumulator on the first device before each resolve (ssb_accum_merge).
 void Renderer::work() {
 	auto t0 = std::chrono::steady_clock::now();
 	std::printf("\rRender started                               ");
@@ -70,21 +148,39 @@ void Renderer::work() {
 	try {
 		ssb_options o = make_options();
 		std::vector<float> preview(framebuffer.pixels.size());
+		const size_t nd = ctxs_.size();
+		if (nd > 1) {  // every device needs a cleared accumulator of the frame's size before the first (partial) render
+			for (ssb_ctx* c : ctxs_) {
+				ssb_options empty = o;  // an empty pixel rectangle: allocates and clears the accumulator, traces nothing
+				empty.x0 = o.width; empty.x1 = o.width;
+				int rc = ssb_render(c, &empty);
+				if (rc != SSB_OK) throw Error{ rc, ssb_last_error() };
+			}
+		}
 		uint32_t done = 0;
-		while (done < o.spp && continue_) {
+		bool go = continue_;
+		while (done < o.spp && go) {
 			ssb_options slice = o;
 			slice.sample_begin = done;
 			slice.sample_end = options.progressive ? std::min(o.spp, done == 0 ? 1u : 2u * done) : o.spp;
-			int rc = ssb_render(ctx_, &slice);
-			if (rc != SSB_OK) throw Error{ rc, ssb_last_error() };
+			render_slice(slice, sum);
 			done = slice.sample_end;
+			go = continue_;  // read ONCE per slice: `last` and the loop exit below must agree (a render_stop() landing in
+			                 // between would otherwise end the loop after a non-last resolve that skipped the XYZA copy)
+			const bool last = done == o.spp || !go;
 			ssb_options avg = o;
 			avg.spp = done;  // avg = accum * 1000/done (renderer.cpp:296 with the samples so far)
-			const bool last = done == o.spp || !continue_;
+			int rc;
+			if (nd > 1) {
+				if ((rc = ssb_clear(sum_ctx_)) != SSB_OK) throw Error{ rc, ssb_last_error() };
+				for (size_t d = 0; d < nd; ++d) {
+					ssb_options how = o;  // what device d holds: its bands of the frame, or partial sums of all pixels
+					if (options.shard != RendererOptions::SHARD_SAMPLES) { how.band_height = options.band_height; how.band_count = (uint32_t)nd; how.band_index = (uint32_t)d; }
+					if ((rc = ssb_accum_merge(sum_ctx_, ctxs_[d], &how)) != SSB_OK) throw Error{ rc, ssb_last_error() };
+				}
+				sum.launches += (uint32_t)nd;
+			}
 			if ((rc = ssb_resolve(ctx_, &avg, last ? xyza.data() : nullptr, preview.data())) != SSB_OK) throw Error{ rc, ssb_last_error() };
-			ssb_stats st{};
-			ssb_get_stats(ctx_, &st);
-			sum.samples += st.samples; sum.device_ms += st.device_ms; sum.trace_ms += st.trace_ms; sum.launches += st.launches;
 			{
 				std::lock_guard<std::mutex> lock(fb_mutex_);
 				framebuffer.pixels.swap(preview);
@@ -99,6 +195,8 @@ void Renderer::work() {
 		rendered_ = done > 0;
 	} catch (Error const& e) {
 		error_ = e; failed_ = true;
+	} catch (std::exception const& e) {  // bad_alloc & co. must reach render_wait(), not std::terminate
+		error_ = Error{ SSB_ERR_DATA, e.what() }; failed_ = true;
 	}
 	last_stats = sum;
 	double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

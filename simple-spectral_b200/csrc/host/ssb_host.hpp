@@ -154,6 +154,18 @@ struct RendererOptions {
 	uint32_t n_wavelengths = 4;                  // SAMPLE_WAVELENGTHS (stdafx.hpp:90): 2, 3 or 4
 	uint64_t seed = 1;
 	int device = 0;
+	// Multi-GPU (the reference's Renderer spreads its tiles over every core of the box, renderer.cpp:396-430): render on all
+	// of `devices` (empty: just `device`; a device may be listed more than once), one host thread and one context per
+	// entry, the frame split as `shard` says, the f64 accumulators merged on the first device (ssb_accum_merge: peer
+	// loads over NVLink) and resolved there.
+	std::vector<int> devices;
+	enum Shard : uint32_t {
+		SHARD_TILES = 0,    // interleaved bands of band_height rows (ssb_options.band_*): disjoint pixels, bit-identical to one GPU
+		SHARD_SAMPLES = 1,  // every GPU renders all pixels for a slice of the sample range: partial sums added in device order
+		                    // (differs from one GPU only by the order of the f64 additions, ~1e-16 relative)
+	};
+	uint32_t shard = SHARD_TILES;
+	uint32_t band_height = 8;  // rows per band: the reference's tile edge (framebuffer.hpp:14-21 tiles are 8 x 8)
 	std::string data_root = ".";
 	// JH only: texel -> coefficient pre-process once per texture (ssb_options.prebaked_textures; color.cpp:204-216)
 	bool prebaked_textures = false;
@@ -189,9 +201,15 @@ public:
 	ssb_options make_options() const;
 	ssb_stats last_stats{};  // of the whole frame (summed over slices)
 
+	size_t device_count() const { return ctxs_.size(); }
+
 private:
 	void work();
-	ssb_ctx* ctx_ = nullptr;
+	void render_slice(ssb_options const& slice, ssb_stats& sum);
+	std::vector<ssb_ctx*> ctxs_;   // one per entry of options.devices
+	std::vector<int> devices_;
+	ssb_ctx* sum_ctx_ = nullptr;   // multi-GPU only: merge target + resolve, on the first device
+	ssb_ctx* ctx_ = nullptr;       // the context that resolves (ctxs_[0], or sum_ctx_)
 	std::thread worker_;
 	mutable std::mutex fb_mutex_;
 	std::atomic<bool> continue_{ true }, rendering_{ false };

@@ -290,7 +290,20 @@ int validate_options(const ssb_options* o, uint32_t& x1, uint32_t& y1, uint32_t&
 	if (!rgb && !(o->lambda_max > o->lambda_min)) return fail(SSB_ERR_ARG, "lambda_max must exceed lambda_min");
 	if (o->n_wavelengths != 0 && (o->n_wavelengths < 2 || o->n_wavelengths > 4))  // glm::vec<N,float> of the reference: N = 2, 3, 4
 		return fail(SSB_ERR_UNSUPPORTED, "n_wavelengths must be 0 (= 4), 2, 3 or 4");
+	if (o->band_count > 1) {
+		if (o->band_height == 0 || o->band_index >= o->band_count) return fail(SSB_ERR_ARG, "row bands: band_height must be positive and band_index < band_count");
+		if (o->y0 != 0 || y1 != o->height) return fail(SSB_ERR_ARG, "row bands cover the whole image height: y0/y1 must be 0");
+	}
+	if (o->scan_mode > SSB_SCAN_LIST) return fail(SSB_ERR_UNSUPPORTED, "unknown scan mode %u", o->scan_mode);
 	return SSB_OK;
+}
+
+// rows j < height with (j / band_h) % band_n == band_i
+uint32_t band_rows(uint32_t height, uint32_t band_h, uint32_t band_n, uint32_t band_i) {
+	uint32_t rows = 0;
+	for (uint32_t b = band_i; (unsigned long long)b * band_h < height; b += band_n)
+		rows += std::min<unsigned long long>(band_h, height - (unsigned long long)b * band_h);
+	return rows;
 }
 
 const size_t kWaveBudgetBytes = (size_t)24 << 30;  // device memory for the path state + fold records of one pass (of 180 GB)
@@ -317,6 +330,16 @@ void ssb_default_options(ssb_options* opt, uint32_t width, uint32_t height, uint
 	opt->flat_field_correction = 1;            // FLAT_FIELD_CORRECTION (stdafx.hpp:55)
 	opt->eps = 0.001f;                         // EPS (stdafx.hpp:58)
 	opt->seed = 1;
+}
+
+int ssb_device_count(int* count) {
+	if (!count) return fail(SSB_ERR_ARG, "ssb_device_count: NULL argument");
+	*count = 0;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) return fail(SSB_ERR_DATA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+	*count = n;
+	return SSB_OK;
 }
 
 int ssb_create(int device, ssb_ctx** out) {
@@ -563,7 +586,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	if ((rc = ensure_accum(c, o->width, o->height)) != SSB_OK) return rc;
 	if (o->sample_begin == 0 && !o->keep_accumulator) SSB_CUDA(cudaMemsetAsync(c->d_accum, 0, (size_t)o->width * o->height * 4 * sizeof(double), c->stream));
 
-	const uint32_t rect_w = x1 - o->x0, rect_h = y1 - o->y0;
+	const bool banded = o->band_count > 1;
+	const uint32_t rect_w = x1 - o->x0, rect_h = banded ? band_rows(o->height, o->band_height, o->band_count, o->band_index) : y1 - o->y0;
 	const size_t npix_rect = (size_t)rect_w * rect_h;
 	const uint32_t nsamp_total = s1 - o->sample_begin;
 	c->stats = ssb_stats{}; c->stats_pending = false; c->passes = 0;
@@ -621,6 +645,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.indirect_only = o->indirect_only; P.upsampling = o->upsampling; P.max_depth = o->max_depth;
 	P.els = o->explicit_light_sampling; P.flat_field = o->flat_field_correction;
 	P.render_mode = o->render_mode;
+	P.band_h = banded ? o->band_height : 1u; P.band_n = banded ? o->band_count : 1u; P.band_i = banded ? o->band_index : 0u;
+	P.scan_list = o->scan_mode == SSB_SCAN_LIST ? 1u : 0u;
 	P.eps = o->eps; P.lambda_min = o->lambda_min;
 	P.n_wavelengths = o->n_wavelengths ? o->n_wavelengths : 4u;  // SAMPLE_WAVELENGTHS (stdafx.hpp:90)
 	P.lambda_step = (o->lambda_max - o->lambda_min) / (float)P.n_wavelengths;  // LAMBDA_STEP (stdafx.hpp:289)
@@ -738,6 +764,56 @@ int ssb_accum_device(ssb_ctx* c, double** dptr, size_t* count) {
 	return SSB_OK;
 }
 
+int ssb_accum_merge(ssb_ctx* dst, ssb_ctx* src, const ssb_options* so) {
+	if (!dst || !src || !so) return fail(SSB_ERR_ARG, "ssb_accum_merge: NULL argument");
+	if (dst == src) return fail(SSB_ERR_ARG, "ssb_accum_merge: dst and src are the same context");
+	if (!src->d_accum) return fail(SSB_ERR_ARG, "ssb_accum_merge: src has rendered nothing");
+	uint32_t x1, y1, s1;
+	int rc = validate_options(so, x1, y1, s1);
+	if (rc != SSB_OK) return rc;
+	if (src->accum_w != so->width || src->accum_h != so->height) return fail(SSB_ERR_ARG, "ssb_accum_merge: src_opt is not what src rendered (resolution)");
+	SSB_CUDA(cudaSetDevice(dst->device));
+	if ((rc = ensure_accum(dst, so->width, so->height)) != SSB_OK) return rc;
+	const size_t count = (size_t)so->width * so->height * 4;
+	// src's accumulator is complete once everything enqueued on its stream so far has run
+	SSB_CUDA(cudaSetDevice(src->device));
+	SSB_CUDA(cudaEventRecord(src->ev_accum_ready, src->stream));
+	SSB_CUDA(cudaSetDevice(dst->device));
+	SSB_CUDA(cudaStreamWaitEvent(dst->stream, src->ev_accum_ready, 0));
+	const double* sp = src->d_accum;
+	if (src->device != dst->device) {
+		int can = 0;
+		SSB_CUDA(cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+		if (can) {  // direct loads from the peer's HBM over NVLink
+			cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+			if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+			if (e != cudaSuccess) can = 0;
+		}
+		if (!can) {  // no peer mapping (PCIe topology, MIG, ...): copy into a staging buffer on dst's device
+			if (dst->peer_staging_count < count) {
+				SSB_CUDA(cudaStreamSynchronize(dst->stream));
+				cudaFree(dst->d_peer_staging); dst->d_peer_staging = nullptr; dst->peer_staging_count = 0;
+				SSB_CUDA(cudaMalloc(&dst->d_peer_staging, count * sizeof(double)));
+				dst->peer_staging_count = count;
+			}
+			SSB_CUDA(cudaMemcpyPeerAsync(dst->d_peer_staging, dst->device, src->d_accum, src->device, count * sizeof(double), dst->stream));
+			sp = dst->d_peer_staging;
+		}
+	}
+	const bool banded = so->band_count > 1;
+	const bool subset = banded || so->x0 != 0 || x1 != so->width || so->y0 != 0 || y1 != so->height;
+	const uint32_t mode = banded ? 2u : (subset ? 1u : 0u);
+	const size_t npix = (size_t)so->width * so->height;
+	ssb_accum_merge_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, dst->stream>>>(dst->d_accum, sp, so->width, so->height, mode, so->x0, so->y0, x1, y1,
+	                                                                            banded ? so->band_height : 1u, banded ? so->band_count : 1u, banded ? so->band_index : 0u);
+	SSB_CUDA(cudaGetLastError());
+	// src must not overwrite its accumulator before dst has read it
+	SSB_CUDA(cudaEventRecord(dst->ev_accum_ready, dst->stream));
+	SSB_CUDA(cudaSetDevice(src->device));
+	SSB_CUDA(cudaStreamWaitEvent(src->stream, dst->ev_accum_ready, 0));
+	return SSB_OK;
+}
+
 static int resolve_impl(ssb_ctx* c, const ssb_options* o, double* xyza_host, float* srgba_host, bool device_only);
 
 int ssb_resolve(ssb_ctx* c, const ssb_options* o, double* xyza_host, float* srgba_host) {
@@ -849,6 +925,37 @@ int ssb_debug_eval_math(ssb_ctx* c, uint32_t fn, const float* x_host, float arg,
 	if (e == cudaSuccess) e = cudaMemcpy(out_host, dout, n * sizeof(float), cudaMemcpyDeviceToHost);
 	cudaFree(dx); cudaFree(dout);
 	if (e != cudaSuccess) return fail(SSB_ERR_DATA, "ssb_debug_eval_math: %s", cudaGetErrorString(e));
+	return SSB_OK;
+}
+
+int ssb_debug_intersect(ssb_ctx* c, const float* rays, const int32_t* ignore, uint32_t scan_mode, float eps, float* out, size_t n) {
+	if (!c || !rays || !out) return fail(SSB_ERR_ARG, "ssb_debug_intersect: NULL argument");
+	if (scan_mode > SSB_SCAN_LIST) return fail(SSB_ERR_UNSUPPORTED, "unknown scan mode %u", scan_mode);
+	if (n == 0) return SSB_OK;
+	SSB_CUDA(cudaSetDevice(c->device));
+	int rc;
+	if (c->blob_dirty && (rc = build_blob(c)) != SSB_OK) return rc;
+	float *d_rays = nullptr, *d_out = nullptr;
+	int32_t* d_ign = nullptr;
+	cudaError_t e = cudaMalloc(&d_rays, n * 6 * sizeof(float));
+	if (e == cudaSuccess) e = cudaMalloc(&d_out, n * 6 * sizeof(float));
+	if (e == cudaSuccess && ignore) e = cudaMalloc(&d_ign, n * sizeof(int32_t));
+	if (e == cudaSuccess) e = copy_to_device(c, d_rays, rays, n * 6 * sizeof(float));
+	if (e == cudaSuccess && ignore) e = copy_to_device(c, d_ign, ignore, n * sizeof(int32_t));
+	if (e == cudaSuccess) {
+		KParams P{};
+		P.blob = c->d_blob; P.eps = eps; P.scan_list = scan_mode == SSB_SCAN_LIST ? 1u : 0u;
+		e = raise_dynamic_smem_limit(c->device, (const void*)ssb_debug_intersect_kernel, c->blob_bytes);
+		if (e == cudaSuccess) {
+			const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 4);
+			ssb_debug_intersect_kernel<<<grid, 256, c->blob_bytes, c->stream>>>(P, d_rays, d_ign, d_out, n);
+			e = cudaGetLastError();
+		}
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_rays); cudaFree(d_out); cudaFree(d_ign);
+	if (e != cudaSuccess) return fail(SSB_ERR_DATA, "ssb_debug_intersect: %s", cudaGetErrorString(e));
 	return SSB_OK;
 }
 

@@ -391,4 +391,11 @@ SSB_ISECT_FN void scene_intersect_listscan(const SceneView& S, float eps, int ig
 	}
 }
 
+#if defined(__CUDACC__)
+SSB_ISECT_NOINLINE void scene_intersect_listscan_noinline(const SceneView& S, float eps, int ignore, Hit& hit,
+                                                          float ox, float oy, float oz, float dx, float dy, float dz) {
+	scene_intersect_listscan(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+}
+#endif
+
 }  // namespace ssbk

@@ -78,6 +78,8 @@ struct KParams {
 	uint32_t render_mode;  // SSB_RENDER_SPECTRAL / SSB_RENDER_RGB
 	uint32_t n_wavelengths;  // SAMPLE_WAVELENGTHS (2..4): channels >= n of every Hero are exactly 0
 	uint32_t depth;     // depth processed by this launch
+	uint32_t band_h, band_n, band_i;  // ssb_options.band_*: rows j with (j / band_h) % band_n == band_i (band_n <= 1: all rows of the rectangle)
+	uint32_t scan_list;  // SSB_SCAN_LIST: the reference's plain list scan instead of the filtered one
 	float eps, lambda_min, lambda_step;
 	unsigned long long seed;
 	double pv_inv[16];
@@ -615,11 +617,13 @@ __device__ __forceinline__ void ld_sector(const float4* p, float4& a, float4& b)
 	asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p) : "memory");
 }
 
+// launch bounds, measured (profiles/r5e_ab.txt, r5f_ab.txt): intersect 512 x 2 beats 256 x 4 by 1 % (the same 32 warps per SM
+// in half as many CTAs: half the blob stagings and histogram flushes); shade 256 x 3 beats 192 x 4 and 128 x 6 by 4 %
 #ifndef SSB_INTERSECT_THREADS
-#define SSB_INTERSECT_THREADS 256
+#define SSB_INTERSECT_THREADS 512
 #endif
 #ifndef SSB_INTERSECT_MIN_BLOCKS
-#define SSB_INTERSECT_MIN_BLOCKS 4
+#define SSB_INTERSECT_MIN_BLOCKS 2
 #endif
 #ifndef SSB_SHADE_THREADS
 #define SSB_SHADE_THREADS 256
@@ -627,6 +631,18 @@ __device__ __forceinline__ void ld_sector(const float4* p, float4& a, float4& b)
 #ifndef SSB_SHADE_MIN_BLOCKS
 #define SSB_SHADE_MIN_BLOCKS 3
 #endif
+
+// image row of local row `lr` of the pass rectangle: consecutive rows, or the lr-th row of this GPU's interleaved bands
+__device__ __forceinline__ uint32_t image_row(const KParams& P, uint32_t lr) {
+	if (P.band_n <= 1u) return P.y0 + lr;
+	return ((lr / P.band_h) * P.band_n + P.band_i) * P.band_h + lr % P.band_h;
+}
+// Scene::intersect as the kernels run it: the filtered scan, or (ssb_options.scan_mode, uniform) the reference's own loop
+__device__ __forceinline__ void scene_query(const KParams& P, const SceneView& S, float eps, int ignore, Hit& hit,
+                                            float ox, float oy, float oz, float dx, float dy, float dz) {
+	if (P.scan_list) scene_intersect_listscan_noinline(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+	else scene_intersect(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+}
 
 __device__ __forceinline__ void stage_scene(const KParams& P, unsigned long long* bar) {
 	const DevHeader* gh = reinterpret_cast<const DevHeader*>(P.blob);
@@ -689,7 +705,7 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				const uint32_t id = item;
 				uint32_t kk = id / npix_rect;
 				uint32_t pr = id - kk * npix_rect;
-				uint32_t pi = P.x0 + pr % P.rect_w, pj = P.y0 + pr / P.rect_w;
+				uint32_t pi = P.x0 + pr % P.rect_w, pj = image_row(P, pr / P.rect_w);
 				uint32_t k = P.sample_begin + kk;
 				unsigned long long sample_index = (unsigned long long)k * ((unsigned long long)P.width * P.height) +
 				                                  ((unsigned long long)pj * P.width + pi);
@@ -728,7 +744,7 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				dx = b.x; dy = b.y; dz = b.z;
 			}
 			Hit hit;
-			scene_intersect(S, P.eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+			scene_query(P, S, P.eps, ignore, hit, ox, oy, oz, dx, dy, dz);
 			if (hit.quad >= 0) {
 				hq = (uint32_t)hit.quad | ((uint32_t)hit.tri << 31);
 				// hit position (Ray::at, stdafx.hpp:219): origin of the shadow ray and of the next path ray
@@ -839,8 +855,10 @@ __global__ void __launch_bounds__(SSB_MAX_QUADS) ssb_bin_scatter_kernel(const __
 // one at the end of the iteration (mask 9) 910.7; without the barrier after the shadow query (mask 11) 907; only the
 // end-of-iteration one (8) 905; only the one after light sampling (2) 869; none 841.  The barrier after the shadow query
 // was where warps waited longest (ncu: 10 % of all warp time) — that phase's length varies with the exact tests a warp runs.
+// Round 2, after the record traffic was cut (whole-sector records): the end-of-iteration barrier alone (8) is now the best,
+// 990 vs 986 with mask 9 and 913 with none (profiles/r5d_ab.txt).
 #ifndef SSB_SHADE_SYNC_MASK
-#define SSB_SHADE_SYNC_MASK 9
+#define SSB_SHADE_SYNC_MASK 8
 #endif
 #define SSB_PHASE_BARRIER_AT(k) do { if ((SSB_SHADE_SYNC_MASK >> (k)) & 1) SSB_PHASE_BARRIER(); } while (0)
 template <bool FIRST, int UPS>
@@ -976,7 +994,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 		// ---- phase 2: shadow query + direct contribution (renderer.cpp:192-218)
 		if (valid && light_phase && l_ndl > 0.0f) {
 			Hit hs;
-			scene_intersect(S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
+			scene_query(P, S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
 			if (hs.quad == light_quad) {
 				const DevMaterial& lm = S.materials()[S.quads()[light_quad].material];
 				Hero emitted = material_emission<UPS>(P, S, lm, lambda_0);
@@ -1156,7 +1174,7 @@ __global__ void __launch_bounds__(128) ssb_accumulate_kernel(const __grid_consta
 	const uint32_t npix_rect = P.rect_w * P.rect_h;
 	const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
 	if (pr >= npix_rect) return;
-	const uint32_t pi = P.x0 + pr % P.rect_w, pj = P.y0 + pr / P.rect_w;
+	const uint32_t pi = P.x0 + pr % P.rect_w, pj = image_row(P, pr / P.rect_w);
 	double* a = P.accum + 4 * ((size_t)pj * P.width + pi);
 	double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
 	const bool rgb = P.render_mode == SSB_RENDER_RGB;
@@ -1167,6 +1185,43 @@ __global__ void __launch_bounds__(128) ssb_accumulate_kernel(const __grid_consta
 		else { a0 += (double)(s.x * 0.001f); a1 += (double)(s.y * 0.001f); a2 += (double)(s.z * 0.001f); a3 += (double)(s.w * 0.001f); }
 	}
 	a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
+}
+
+// ssb_accum_merge: dst (+)= src over the pixels src rendered.  mode 0: dst += src (sample shards of the whole frame);
+// mode 1: the pixel rectangle [x0,x1) x [y0,y1) is copied; mode 2: the rows of src's interleaved bands are copied.
+// `src` may be a peer GPU's memory (direct NVLink loads) or a staging copy on this device.  One thread per pixel, the four
+// doubles of a pixel as two 16-byte accesses.
+__global__ void __launch_bounds__(256) ssb_accum_merge_kernel(double* __restrict__ dst, const double* __restrict__ src, uint32_t width, uint32_t height,
+                                                              uint32_t mode, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                                                              uint32_t band_h, uint32_t band_n, uint32_t band_i) {
+	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= (size_t)width * height) return;
+	const uint32_t i = (uint32_t)(p % width), j = (uint32_t)(p / width);
+	const double2* s2 = reinterpret_cast<const double2*>(src) + 2 * p;
+	double2* d2 = reinterpret_cast<double2*>(dst) + 2 * p;
+	if (mode == 0u) {
+		const double2 a = s2[0], b = s2[1];
+		double2 c = d2[0], d = d2[1];
+		c.x += a.x; c.y += a.y; d.x += b.x; d.y += b.y;
+		d2[0] = c; d2[1] = d;
+		return;
+	}
+	const bool mine = mode == 1u ? (i >= x0 && i < x1 && j >= y0 && j < y1) : (i >= x0 && i < x1 && (j / band_h) % band_n == band_i);
+	if (mine) { d2[0] = s2[0]; d2[1] = s2[1]; }
+}
+
+// ssb_debug_intersect: closest-hit queries of caller-supplied rays through the render kernels' scene_intersect
+__global__ void __launch_bounds__(256) ssb_debug_intersect_kernel(const __grid_constant__ KParams P, const float* __restrict__ rays, const int32_t* __restrict__ ignore,
+                                                                  float* __restrict__ out, size_t n) {
+	__shared__ __align__(8) unsigned long long blob_bar;
+	stage_scene(P, &blob_bar);
+	const SceneView S;
+	for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (size_t)gridDim.x * blockDim.x) {
+		Hit hit;
+		scene_query(P, S, P.eps, ignore ? ignore[r] : -1, hit, rays[6 * r], rays[6 * r + 1], rays[6 * r + 2], rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]);
+		out[6 * r] = __int_as_float(hit.quad); out[6 * r + 1] = __int_as_float(hit.tri); out[6 * r + 2] = hit.dist;
+		out[6 * r + 3] = hit.bx; out[6 * r + 4] = hit.by; out[6 * r + 5] = hit.bz;
+	}
 }
 
 // avg *= 1000/spp; framebuffer = (ciexyz_to_srgb(float3(avg)), float(avg.a)) (renderer.cpp:296-298, color.cpp:237-257)

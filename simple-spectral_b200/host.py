@@ -15,7 +15,11 @@ class ssbh_renderer_options(C.Structure):
                 ("upsampling", C.c_uint32), ("explicit_light_sampling", C.c_uint32), ("max_depth", C.c_uint32),
                 ("flat_field_correction", C.c_uint32), ("seed", C.c_uint64), ("device", C.c_int),
                 ("data_root", C.c_char_p), ("render_mode", C.c_uint32), ("n_wavelengths", C.c_uint32),
-                ("prebaked_textures", C.c_uint32), ("progressive", C.c_uint32)]
+                ("prebaked_textures", C.c_uint32), ("progressive", C.c_uint32),
+                ("devices", C.POINTER(C.c_int)), ("ndevices", C.c_uint32), ("shard", C.c_uint32), ("band_height", C.c_uint32)]
+
+
+SSBH_SHARD_TILES, SSBH_SHARD_SAMPLES = 0, 1
 
 
 HOST_SYMBOLS = (
@@ -213,13 +217,20 @@ class Renderer:
 
     def __init__(self, scene_name, width, height, spp, output_path=None, indirect_only=False, variant="ours1931",
                  explicit_light_sampling=True, max_depth=10, flat_field_correction=True, seed=1, device=0, data_root=None,
-                 n_wavelengths=4, prebaked_textures=False, progressive=False):
+                 n_wavelengths=4, prebaked_textures=False, progressive=False, devices=None, shard="tiles", band_height=0):
+        """devices: list of GPU indices to render on together (None: just `device`); shard: "tiles" (interleaved row
+        bands, bit-identical to one GPU) or "samples" (sample ranges, f64 summation order differs)."""
         obs, ups = VARIANTS[variant]
         self._keep = (scene_name.encode(), output_path.encode() if output_path else None, (data_root or find_data_root()).encode())
         o = ssbh_renderer_options(self._keep[0], width, height, spp, int(indirect_only), self._keep[1], obs, ups,
                                   int(explicit_light_sampling), max_depth, int(flat_field_correction), seed, device, self._keep[2],
                                   _abi.SSB_RENDER_RGB if variant == "rgb" else _abi.SSB_RENDER_SPECTRAL, n_wavelengths,
                                   int(prebaked_textures), int(progressive))
+        if devices:
+            self._devices = (C.c_int * len(devices))(*devices)
+            o.devices, o.ndevices = self._devices, len(devices)
+        o.shard = {"tiles": SSBH_SHARD_TILES, "samples": SSBH_SHARD_SAMPLES}[shard]
+        o.band_height = band_height
         self._h = C.c_void_p()
         self.width, self.height = width, height
         _check(hostlib().ssbh_renderer_new(C.byref(o), C.byref(self._h)))

@@ -46,6 +46,8 @@ def oracle():
     L.ssb_oracle_render.restype = C.c_int
     L.ssb_oracle_resolve.argtypes = [P(abi.ssb_color), P(abi.ssb_options), P(C.c_double), P(C.c_double), P(C.c_float)]
     L.ssb_oracle_resolve.restype = C.c_int
+    L.ssb_oracle_intersect.argtypes = [P(abi.ssb_scene), P(C.c_float), P(C.c_int32), C.c_float, P(C.c_float), C.c_size_t]
+    L.ssb_oracle_intersect.restype = C.c_int
     L.ssb_oracle_eval_math.argtypes = [C.c_uint32, P(C.c_float), C.c_float, P(C.c_float), C.c_size_t]
     L.ssb_oracle_eval_math.restype = None
     return L
@@ -153,6 +155,19 @@ def oracle_resolve(flat, opt, acc):
                                      xyza.ctypes.data_as(C.POINTER(C.c_double)), srgba.ctypes.data_as(C.POINTER(C.c_float)))
     assert rc == 0
     return xyza, srgba
+
+
+def oracle_intersect(scene, rays, ignore=None, eps=1e-3):
+    """Scene::intersect of the checker for n rays -> (quad, tri, dist, bary[n,3]) like Context.intersect."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+    n = rays.shape[0]
+    out = np.empty((n, 6), np.float32)
+    ign = None if ignore is None else np.ascontiguousarray(ignore, np.int32)
+    rc = oracle().ssb_oracle_intersect(C.byref(scene), rays.ctypes.data_as(C.POINTER(C.c_float)),
+                                       ign.ctypes.data_as(C.POINTER(C.c_int32)) if ign is not None else None, float(eps),
+                                       out.ctypes.data_as(C.POINTER(C.c_float)), n)
+    assert rc == 0
+    return out[:, 0].view(np.int32).copy(), out[:, 1].view(np.int32).copy(), out[:, 2].copy(), out[:, 3:6].copy()
 
 
 def gpu_context(flat, device=0):

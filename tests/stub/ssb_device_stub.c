@@ -35,8 +35,10 @@ void ssb_default_options(ssb_options* o, uint32_t width, uint32_t height, uint32
 	o->eps = 0.001f; o->seed = 1;
 }
 
+#define STUB_DEVICES 4 /* the stub pretends to be a four-GPU box */
+int ssb_device_count(int* count) { *count = STUB_DEVICES; return SSB_OK; }
 int ssb_create(int device, ssb_ctx** out) {
-	if (device != 0) { g_err = "stub: device out of range"; return SSB_ERR_ARG; }
+	if (device < 0 || device >= STUB_DEVICES) { g_err = "stub: device out of range"; return SSB_ERR_ARG; }
 	*out = (ssb_ctx*)calloc(1, sizeof(ssb_ctx));
 	return SSB_OK;
 }
@@ -56,7 +58,13 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	if (rc != SSB_OK) { g_err = "stub: oracle render failed"; return rc; }
 	uint32_t s1 = o->sample_end ? o->sample_end : o->spp;
 	memset(&c->stats, 0, sizeof(c->stats));
-	c->stats.samples = (uint64_t)o->width * o->height * (s1 - o->sample_begin);
+	{ /* pixels of the requested subset (rectangle, or this share of the interleaved row bands) */
+		uint32_t x1 = o->x1 ? o->x1 : o->width, y1 = o->y1 ? o->y1 : o->height;
+		uint64_t rows = 0;
+		for (uint32_t j = o->y0; j < y1; ++j)
+			if (o->band_count <= 1 || (j / o->band_height) % o->band_count == o->band_index) ++rows;
+		c->stats.samples = rows * (x1 - o->x0) * (s1 - o->sample_begin);
+	}
 	c->stats.device_ms = 1.0; c->stats.trace_ms = 1.0; c->stats.launches = 1;
 	c->stats.reserved = ++c->renders;
 	return SSB_OK;
@@ -68,3 +76,29 @@ int ssb_resolve(ssb_ctx* c, const ssb_options* o, double* xyza, float* srgba) {
 }
 
 int ssb_get_stats(ssb_ctx* c, ssb_stats* out) { *out = c->stats; return SSB_OK; }
+
+int ssb_clear(ssb_ctx* c) {
+	if (c->accum) memset(c->accum, 0, (size_t)c->w * c->h * 4 * sizeof(double));
+	return SSB_OK;
+}
+
+/* same rule as the library: a pixel subset is copied, a whole-frame share (sample range) is added */
+int ssb_accum_merge(ssb_ctx* dst, ssb_ctx* src, const ssb_options* o) {
+	if (!src->accum || src->w != o->width || src->h != o->height) { g_err = "stub: merge source mismatch"; return SSB_ERR_ARG; }
+	if (!dst->accum || dst->w != o->width || dst->h != o->height) {
+		free(dst->accum);
+		dst->accum = (double*)calloc((size_t)o->width * o->height * 4, sizeof(double));
+		dst->w = o->width; dst->h = o->height;
+	}
+	uint32_t x1 = o->x1 ? o->x1 : o->width, y1 = o->y1 ? o->y1 : o->height;
+	int banded = o->band_count > 1;
+	int subset = banded || o->x0 != 0 || x1 != o->width || o->y0 != 0 || y1 != o->height;
+	for (uint32_t j = 0; j < o->height; ++j)
+		for (uint32_t i = 0; i < o->width; ++i) {
+			size_t p = 4 * ((size_t)j * o->width + i);
+			if (!subset) { for (int k = 0; k < 4; ++k) dst->accum[p + k] += src->accum[p + k]; continue; }
+			int mine = banded ? (i >= o->x0 && i < x1 && (j / o->band_height) % o->band_count == o->band_index) : (i >= o->x0 && i < x1 && j >= o->y0 && j < y1);
+			if (mine) memcpy(dst->accum + p, src->accum + p, 4 * sizeof(double));
+		}
+	return SSB_OK;
+}

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_defaults():
     L = ssb.lib()
-    assert L.ssb_abi_version() == 3  # 3: ssb_options.prebaked_textures
+    assert L.ssb_abi_version() == 4  # 4: row bands, scan mode, ssb_accum_merge, ssb_device_count, ssb_debug_intersect
     o = ssb.ssb_options()
     L.ssb_default_options(C.byref(o), 512, 512, 64)
     d = ssb.default_options(512, 512, 64)
@@ -64,3 +64,12 @@ def test_struct_sizes_match_c():
     names = ("ssb_vertex", "ssb_tri", "ssb_quad", "ssb_spectrum", "ssb_material", "ssb_texture", "ssb_camera", "ssb_scene", "ssb_color", "ssb_options")
     for n, s in zip(names, out):
         assert C.sizeof(getattr(ssb, n)) == int(s), n
+
+
+def test_host_struct_size_matches_c():
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "s.c"), "w").write('#include <stdio.h>\n#include "ssb200_host.h"\nint main(void){ printf("%zu\\n", sizeof(ssbh_renderer_options)); return 0; }\n')
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(tmp, "s.c"), "-o", os.path.join(tmp, "s")], check=True)
+        out = subprocess.run([os.path.join(tmp, "s")], capture_output=True, text=True, check=True).stdout.split()
+    assert C.sizeof(host.ssbh_renderer_options) == int(out[0])

@@ -61,10 +61,13 @@ def stub(tmp_path_factory):
 W, H = 16, 12
 
 
-def _new(L, spp, progressive, output=None, scene=b"cornell"):
-    keep = (scene, output.encode() if output else None, pu.data_root().encode())
+def _new(L, spp, progressive, output=None, scene=b"cornell", devices=None, shard=0, band_height=0):
+    keep = (scene, output.encode() if output else None, pu.data_root().encode(), (C.c_int * len(devices))(*devices) if devices else None)
     o = host.ssbh_renderer_options(keep[0], W, H, spp, 0, keep[1], 1931, pu.abi.SSB_UPSAMPLE_OURS, 1, 10, 1, 7, 0, keep[2],
                                    pu.abi.SSB_RENDER_SPECTRAL, 4, 0, int(progressive))
+    if devices:
+        o.devices, o.ndevices = keep[3], len(devices)
+    o.shard, o.band_height = shard, band_height
     h = C.c_void_p()
     rc = L.ssbh_renderer_new(C.byref(o), C.byref(h))
     assert rc == 0, L.ssbh_last_error()
@@ -160,6 +163,42 @@ def test_stop_ends_the_render_after_the_slice_in_flight_and_saves(stub, tmp_path
     # the renderer can be started again
     L.ssbh_renderer_stop(h)
     L.ssbh_renderer_free(h)
+
+
+def test_multi_device_tiles_are_bit_identical_and_samples_differ_only_by_summation_order(stub):
+    """The Renderer's multi-GPU path (RendererOptions::devices; reference renderer.cpp:396-430 spreads its tiles over all
+    cores): one context + host thread per device, interleaved row bands or sample ranges, merged on the first device.
+    Row bands (disjoint pixels, per-sample seeding) must give the single-device frame bit for bit — also progressively,
+    with more devices than bands, and with a device listed twice; sample ranges add partial f64 sums in device order."""
+    L = stub
+    spp = 6
+    one = _new(L, spp, False)
+    assert L.ssbh_renderer_render(one) == 0, L.ssbh_last_error()
+    x1, f1, s1 = _results(L, one)
+    L.ssbh_renderer_free(one)
+    for devices, band_h, progressive in (([0, 1, 2], 0, False), ([0, 1, 2, 3], 5, True), ([1, 1], 1, False), ([0, 1, 2, 3], 4, False)):
+        h = _new(L, spp, progressive, devices=devices, shard=host.SSBH_SHARD_TILES, band_height=band_h)
+        assert L.ssbh_renderer_render(h) == 0, L.ssbh_last_error()
+        x, f, st = _results(L, h)
+        L.ssbh_renderer_free(h)
+        assert st.samples == W * H * spp, (devices, st.samples)
+        assert pu.bits_equal(x, x1) and pu.bits_equal(f, f1), (devices, band_h, progressive)
+    for devices, progressive in (([0, 1, 2], False), ([0, 1, 2, 3], True)):
+        h = _new(L, spp, progressive, devices=devices, shard=host.SSBH_SHARD_SAMPLES)
+        assert L.ssbh_renderer_render(h) == 0, L.ssbh_last_error()
+        x, f, st = _results(L, h)
+        L.ssbh_renderer_free(h)
+        assert st.samples == W * H * spp
+        assert pu.rel_err(x, x1).max() <= 1e-14
+    bad = _new(L, spp, False, devices=[0, 1], shard=host.SSBH_SHARD_TILES)
+    L.ssbh_renderer_free(bad)
+    # a device the box does not have: the constructor fails and nothing leaks
+    keep = (b"cornell", None, pu.data_root().encode(), (C.c_int * 2)(0, 9))
+    o = host.ssbh_renderer_options(keep[0], W, H, spp, 0, keep[1], 1931, pu.abi.SSB_UPSAMPLE_OURS, 1, 10, 1, 7, 0, keep[2],
+                                   pu.abi.SSB_RENDER_SPECTRAL, 4, 0, 0)
+    o.devices, o.ndevices = keep[3], 2
+    h = C.c_void_p()
+    assert L.ssbh_renderer_new(C.byref(o), C.byref(h)) == pu.abi.SSB_ERR_ARG and not h
 
 
 def test_worker_errors_surface_in_wait(stub):
