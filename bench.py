@@ -31,10 +31,24 @@ sys.path.insert(0, ROOT)
 METRIC = "Mpath-samples/s"
 JSON_OUT = None  # where the one JSON line goes (stdout unless main_ours redirected fd 1, see there)
 SCENE, VARIANT = "cornell-srgb", "ours1931"
+HEADLINE_SHA = "3ceea29f9217d925"  # f64 accumulators of the headline frame (seed 1) on one GPU: tools/ab.py prints it for every build
 # SURVEY.md §8(d) algorithmic HBM bytes per path sample (wavefront model the north star names):
 # 5.30 closest-hit stages x 192 B ray state read+write + 47 B texture sectors + 32 B f64 XYZA output
 ALGO_BYTES_PER_SAMPLE = {"cornell-srgb": 5.30 * 192 + 47 + 32, "cornell": 5.30 * 192 + 32, "plane-srgb": 2.0 * 192 + 64 + 32}
 JH_EXTRA_BYTES_PER_SAMPLE = {"cornell-srgb": 375.0, "cornell": 0.0, "plane-srgb": 512.0}  # 8 coefficient sectors per textured lookup
+
+
+def source_sha():
+    """sha256 over the device-code sources: ties an ncu-derived figure (profiles/trace_kernel_traffic.json) to the build
+    it was captured on — bench.py refuses to quote DRAM traffic / instruction counts of another build."""
+    import hashlib
+    h = hashlib.sha256()
+    src = os.path.join(ROOT, "simple-spectral_b200", "csrc")
+    for f in sorted(os.listdir(src)):
+        if f.endswith((".cu", ".cuh", ".hpp")):
+            h.update(open(os.path.join(src, f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "ssb200.h"), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def measured_peaks():
@@ -48,7 +62,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region: NVML polled every 20 ms from a thread (the same
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled every 5 ms from a thread (the same
     counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; nvidia-smi itself needs ~100 ms to
     start, longer than a short timed region), nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -90,7 +104,7 @@ class ClockSampler:
                 self.bits |= int(get(self.handle))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -232,16 +246,12 @@ def main_ours(args, rank, local_rank, world):
     rmode = ssb.SSB_RENDER_RGB if VARIANT == "rgb" else ssb.SSB_RENDER_SPECTRAL
     tiles = args.shard == "tiles" and world > 1
     if tiles:
-        # option A of SURVEY 8(e): the SAME frame (spp unchanged) split into row bands, strong scaling; the reduce then
-        # sums disjoint pixels (Cornell rows differ in cost, so the bands are not perfectly balanced)
-        sharding = importlib.import_module("simple-spectral_b200.sharding")
+        # option A of SURVEY 8(e): the SAME frame (spp unchanged) split into interleaved bands of 8 rows (ssb_options.band_*,
+        # the reference's tile edge) — strong scaling; every rank gets a share of the expensive and of the cheap rows in ONE
+        # launch sequence, and the reduce sums disjoint pixels (+0 elsewhere): bit-identical to one GPU
         total_spp = SPP
-        # one contiguous row band per rank (measured at N=2: four interleaved bands per rank balance the load better but
-        # their extra launches cost more: 11.11 vs 10.87 ms/frame); band b belongs to rank b % world
-        nb = 1 * world
-        bands = [sharding.tile_shard(b, nb, H) for b in range(rank, nb, world)]
-        band_opts = [host.options_for(color, W, H, total_spp, seed=1, y0=y0, y1=y1, render_mode=rmode, keep_accumulator=1,
-                                      prebaked_textures=int(args.prebake)) for (y0, y1) in bands if y1 > y0]
+        band_opts = [host.options_for(color, W, H, total_spp, seed=1, render_mode=rmode, keep_accumulator=1, prebaked_textures=int(args.prebake),
+                                      band_height=8, band_count=world, band_index=rank)]
         opt = band_opts[0]
     else:
         total_spp = SPP * world  # weak scaling: the job is the same frame at spp 64*N
@@ -367,6 +377,63 @@ def main_ours(args, rank, local_rank, world):
     e2e_ms = t.item()
     e2e_value = samples_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e6
 
+    # ---------------- frame checksum of the job just measured (every line): sha256 of the f64 XYZA accumulators on rank 0
+    import hashlib
+
+    def accum_sha():
+        return hashlib.sha256(np.ascontiguousarray(ctx.read_accum(W, H)).tobytes()).hexdigest()[:16]
+
+    step_device()
+    torch.cuda.synchronize()
+    frame_sha = accum_sha() if rank == 0 else None
+
+    # ---------------- strong scaling of the FIXED headline job (N > 1): the same spp-SPP frame split over the ranks, both ways
+    strong = None
+    if world > 1 and not tiles:
+        strong = {}
+        for mode in ("tiles", "samples"):
+            if mode == "tiles":
+                so = host.options_for(color, W, H, SPP, seed=1, render_mode=rmode, keep_accumulator=1, prebaked_textures=int(args.prebake),
+                                      band_height=8, band_count=world, band_index=rank)
+            else:
+                so = host.options_for(color, W, H, SPP, seed=1, render_mode=rmode, keep_accumulator=1, prebaked_textures=int(args.prebake),
+                                      sample_begin=SPP * rank // world, sample_end=SPP * (rank + 1) // world)
+            empty = so.sample_end != 0 and so.sample_end <= so.sample_begin  # more ranks than samples
+            full = host.options_for(color, W, H, SPP, seed=1, render_mode=rmode)
+
+            def step_strong(reduce=True):
+                ctx.clear()
+                if not empty:
+                    ctx.render(so)
+                if reduce:
+                    dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
+                    if rank == 0:
+                        ctx.resolve_device(full)
+
+            for _ in range(3):
+                step_strong()
+            torch.cuda.synchronize(); dist.barrier()
+            times = {}
+            for key, red in (("frame", True), ("render_only", False)):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(args.steps):
+                    step_strong(red)
+                b.record(stream)
+                torch.cuda.synchronize()
+                tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=f"cuda:{local_rank}")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.barrier()
+                times[key] = tt.item() / args.steps
+            step_strong()
+            torch.cuda.synchronize()
+            sha = accum_sha() if rank == 0 else None
+            strong[mode] = {"value": npix * SPP / (times["frame"] * 1e-3) / 1e6, "unit": METRIC, "ms_per_frame": times["frame"],
+                            "render_only_ms": times["render_only"], "reduce_and_resolve_ms": times["frame"] - times["render_only"],
+                            "frame_sha": sha, "scaling": "strong",
+                            "shard": "interleaved bands of 8 rows (ssb_options.band_*)" if mode == "tiles" else "sample ranges"}
+        dist.barrier()
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         algo_per_sample = ALGO_BYTES_PER_SAMPLE[SCENE] + (JH_EXTRA_BYTES_PER_SAMPLE[SCENE] if VARIANT == "jh" else 0.0)
@@ -375,9 +442,14 @@ def main_ours(args, rank, local_rank, world):
         traffic, issue = None, None
         tp = os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")
         headline = (SCENE, VARIANT, W, H, SPP) == ("cornell-srgb", "ours1931", 512, 512, 64)  # what the ncu capture ran
+        traffic_note = None
         if os.path.exists(tp) and headline:
             try:
                 prof = json.load(open(tp))
+                if prof.get("source_sha") != source_sha():
+                    traffic_note = (f"profiles/trace_kernel_traffic.json was captured on another build (source_sha {prof.get('source_sha')} != "
+                                    f"{source_sha()}): traffic / issue not quoted")
+                    raise ValueError(traffic_note)
                 traffic = prof.get("dram_bytes_per_launch")
                 wi, ti = prof.get("warp_instructions_per_frame"), prof.get("thread_instructions_per_frame")
                 if wi and clocks.get("sm_mhz"):
@@ -403,14 +475,24 @@ def main_ours(args, rank, local_rank, world):
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "calls": "ssb_upload_color + ssb_upload_scene_async (pinned RGB8 texture) + ssb_render_frame -> pinned XYZA f64 + sRGBA f32"},
             "gpu_launches": int(launches),
+            "frame_sha": frame_sha,
+            "frame_sha_note": "sha256[:16] of the f64 XYZA accumulators of the measured job on rank 0" +
+                              (f"; the 1-GPU spp{SPP} frame of the headline config is {HEADLINE_SHA}" if (SCENE, VARIANT, W, H, SPP) == ("cornell-srgb", "ours1931", 512, 512, 64) else ""),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "kernel": "bounce stage = ssb_intersect_kernel + counting sort + ssb_shade_kernel over all path depths of one frame "
                                    "(CUDA events around the launch sequence)", "kernel_ms": trace_ms,
-                         "algorithmic_bytes_per_sample": algo_per_sample, "issue": issue,
+                         "algorithmic_bytes_per_sample": algo_per_sample, "issue": issue, "traffic_note": traffic_note,
                          "note": "achieved = SURVEY.md 8(d) algorithmic bytes (wavefront ray-state model) / bounce-stage time; traffic = ncu dram bytes of the "
                                  "same launches (profiles/). The stage is instruction-issue bound (un-fused fp32 + f64 exact libm), DRAM ~20-30 % busy: see DESIGN.md (d)"},
         }
+        if strong is not None:
+            # the fixed spp-SPP frame at N GPUs; the tiles frame must be the 1-GPU frame bit for bit (per-sample seeding, disjoint pixels)
+            line["strong"] = strong
+            line["strong"]["job"] = f"{SCENE} {W}x{H} spp{SPP} (fixed), split over {world} GPUs + one NCCL reduce of f64 XYZA + resolve on rank 0"
+            line["strong"]["limiter"] = ("per-GPU slice of %.2f ms against a floor of ~30 dependent kernel launches per pass (each depth's queue length is "
+                                         "read on the device, so the launches cannot be merged) + the 8 MB ncclReduce and resolve: see reduce_and_resolve_ms"
+                                         % strong["tiles"]["render_only_ms"])
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(W, H, args.cpu_spp)
@@ -428,7 +510,7 @@ def main():
     global SCENE, VARIANT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)  # 100 frames x ~17 ms: a timed region of > 1.5 s by default
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=512)

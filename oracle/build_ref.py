@@ -60,6 +60,12 @@ VARIANTS = {
 # sRGB -> spectrum -> sRGB error after every red level — the source of tests/golden/roundtrip_running_max.json and of the
 # one number the reference documents, 1.851469e-5 (main.cpp:242-245).
 TOOLS = {"roundtrip": dict(alg=1, observer=1931)}
+# Not a CPU variant either: THE COMPILED BOUNDARY.  The real reference with integration/renderer_ssb200.cpp (the stub of
+# INTEGRATION.md) added and Renderer::render_start / render_wait of renderer.cpp compiled out, linked against
+# simple-spectral_b200/libssb200.so: main.cpp, Color::init, Scene::get_new_*, Framebuffer::save are the reference's own
+# code, the per-pixel loop is the library.  Needs a GPU to RUN (tests/test_gpu_boundary.py); built here like the others.
+BOUNDARY = {"ssb200": dict(alg=1, observer=1931), "ssb200_jh": dict(alg=3, observer=1931)}
+ROOT = os.path.dirname(HERE)
 CXX_SOURCES = [
     "main.cpp", "renderer.cpp", "scene.cpp", "geometry.cpp", "material.cpp", "spectrum.cpp",
     "framebuffer.cpp", "util/color.cpp", "util/random.cpp", "util/spherical-tri.cpp",
@@ -155,7 +161,21 @@ def patch_roundtrip(src_dir):
     open(p, "w", encoding="utf-8").write(t)
 
 
-def build_one(tmp, name, alg, observer, hooked, lodepng_obj, roundtrip=False, **variant_kw):
+def patch_boundary(src_dir):
+    """renderer.cpp: compile out the two functions the stub replaces; the stub reads a few private members."""
+    shutil.copy(os.path.join(ROOT, "integration", "renderer_ssb200.cpp"), os.path.join(src_dir, "renderer_ssb200.cpp"))
+    for name in ("spectrum.hpp", "material.hpp"):
+        p = os.path.join(src_dir, name)
+        t = open(p, encoding="utf-8-sig").read().replace("private:", "public:")
+        open(p, "w", encoding="utf-8").write(t)
+    p = os.path.join(src_dir, "renderer.cpp")
+    t = open(p, encoding="utf-8-sig").read()
+    t = sub_once(t, r"^void Renderer::render_start\(\) \{$", "#ifndef SSB200_BOUNDARY\nvoid Renderer::render_start() {", "render_start")
+    t = sub_once(t, r"(^void Renderer::render_wait \(\) \{\n(?:.*\n)*?^\}\n)", r"\1#endif\n", "render_wait")
+    open(p, "w", encoding="utf-8").write(t)
+
+
+def build_one(tmp, name, alg, observer, hooked, lodepng_obj, roundtrip=False, boundary=False, **variant_kw):
     tag = name + ("_hooked" if hooked else "")
     src_dir = os.path.join(tmp, tag, "src")
     shutil.copytree(os.path.join(REF, "src"), src_dir, ignore=shutil.ignore_patterns("lodepng*"))
@@ -168,10 +188,14 @@ def build_one(tmp, name, alg, observer, hooked, lodepng_obj, roundtrip=False, **
         patch_hooks(src_dir)
     if roundtrip:
         patch_roundtrip(src_dir)
-    flags = FLAGS_HOOKED if (hooked or roundtrip) else FLAGS_PRISTINE
+    if boundary:
+        patch_boundary(src_dir)
+    flags = FLAGS_HOOKED if (hooked or roundtrip or boundary) else FLAGS_PRISTINE
+    if boundary:
+        flags = [*flags, "-DSSB200_BOUNDARY", "-I", os.path.join(ROOT, "include")]
     inc = ["-I", SHIM, "-I", os.path.join(REF, "src")]  # lodepng.h is found through the original tree
     objs = []
-    for s in CXX_SOURCES:
+    for s in CXX_SOURCES + (["renderer_ssb200.cpp"] if boundary else []):
         o = os.path.join(tmp, tag, s.replace("/", "_") + ".o")
         # util/*.cpp include "lodepng/lodepng.h" relative to util/, which is not copied: add that dir
         run(["g++", "-std=c++17", "-w", *flags, *inc, "-I", os.path.join(REF, "src", "util"),
@@ -182,7 +206,13 @@ def build_one(tmp, name, alg, observer, hooked, lodepng_obj, roundtrip=False, **
         run(["gcc", "-w", *flags, "-c", os.path.join(src_dir, s), "-o", o])
         objs.append(o)
     out = os.path.join(OUT, "simple_spectral_" + tag)
-    run(["g++", *objs, lodepng_obj, "-o", out, "-pthread", "-lm"])
+    link = []
+    if boundary:  # oracle/_ref/<binary> finds the library two directories up, wherever the repo lies
+        lib_dir = os.path.join(ROOT, "simple-spectral_b200")
+        if not os.path.exists(os.path.join(lib_dir, "libssb200.so")):
+            raise SystemExit("oracle/build_ref.py: build simple-spectral_b200/libssb200.so first (__graft_entry__.build())")
+        link = ["-L", lib_dir, "-lssb200", "-Wl,-rpath,$ORIGIN/../../simple-spectral_b200"]
+    run(["g++", *objs, lodepng_obj, "-o", out, "-pthread", "-lm", *link])
     return out
 
 
@@ -202,6 +232,9 @@ def main():
             for name in which:
                 if name in TOOLS:
                     jobs.append(ex.submit(build_one, tmp, name, TOOLS[name]["alg"], TOOLS[name]["observer"], False, lodepng_obj, roundtrip=True))
+                    continue
+                if name in BOUNDARY:
+                    jobs.append(ex.submit(build_one, tmp, name, BOUNDARY[name]["alg"], BOUNDARY[name]["observer"], False, lodepng_obj, boundary=True))
                     continue
                 v = VARIANTS[name]
                 for hooked in (False, True):

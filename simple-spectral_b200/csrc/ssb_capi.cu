@@ -646,7 +646,6 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.els = o->explicit_light_sampling; P.flat_field = o->flat_field_correction;
 	P.render_mode = o->render_mode;
 	P.band_h = banded ? o->band_height : 1u; P.band_n = banded ? o->band_count : 1u; P.band_i = banded ? o->band_index : 0u;
-	P.scan_list = o->scan_mode == SSB_SCAN_LIST ? 1u : 0u;
 	P.eps = o->eps; P.lambda_min = o->lambda_min;
 	P.n_wavelengths = o->n_wavelengths ? o->n_wavelengths : 4u;  // SAMPLE_WAVELENGTHS (stdafx.hpp:90)
 	P.lambda_step = (o->lambda_max - o->lambda_min) / (float)P.n_wavelengths;  // LAMBDA_STEP (stdafx.hpp:289)
@@ -663,14 +662,21 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 
 	const size_t smem = c->blob_bytes;
 	typedef void (*kfn)(const KParams);
-	kfn k_shade_first = nullptr, k_shade_next = nullptr;
-	switch (rgb ? (uint32_t)SSB_UPS_RGB : o->upsampling) {  // one instantiation per upsampling mode keeps the instruction footprint small
-		case SSB_UPS_RGB: k_shade_first = ssb_shade_kernel<true, SSB_UPS_RGB>; k_shade_next = ssb_shade_kernel<false, SSB_UPS_RGB>; break;
-		case SSB_UPSAMPLE_OURS: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_OURS>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_OURS>; break;
-		case SSB_UPSAMPLE_JH: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_JH>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_JH>; break;
-		default: k_shade_first = ssb_shade_kernel<true, SSB_UPSAMPLE_MENG>; k_shade_next = ssb_shade_kernel<false, SSB_UPSAMPLE_MENG>; break;
+	kfn k_shade_first = nullptr, k_shade_next = nullptr, k_isect_first = nullptr, k_isect_next = nullptr;
+	// one instantiation per upsampling mode keeps the instruction footprint small; LIST = ssb_options.scan_mode
+#define SSB_PICK(UPS, LIST)                                                                                         \
+	do {                                                                                                            \
+		k_shade_first = ssb_shade_kernel<true, UPS, LIST>; k_shade_next = ssb_shade_kernel<false, UPS, LIST>;       \
+		k_isect_first = ssb_intersect_kernel<true, LIST>; k_isect_next = ssb_intersect_kernel<false, LIST>;          \
+	} while (0)
+	const bool list = o->scan_mode == SSB_SCAN_LIST;
+	switch (rgb ? (uint32_t)SSB_UPS_RGB : o->upsampling) {
+		case SSB_UPS_RGB: if (list) SSB_PICK(SSB_UPS_RGB, true); else SSB_PICK(SSB_UPS_RGB, false); break;
+		case SSB_UPSAMPLE_OURS: if (list) SSB_PICK(SSB_UPSAMPLE_OURS, true); else SSB_PICK(SSB_UPSAMPLE_OURS, false); break;
+		case SSB_UPSAMPLE_JH: if (list) SSB_PICK(SSB_UPSAMPLE_JH, true); else SSB_PICK(SSB_UPSAMPLE_JH, false); break;
+		default: if (list) SSB_PICK(SSB_UPSAMPLE_MENG, true); else SSB_PICK(SSB_UPSAMPLE_MENG, false); break;
 	}
-	kfn k_isect_first = ssb_intersect_kernel<true>, k_isect_next = ssb_intersect_kernel<false>;
+#undef SSB_PICK
 	// dynamic shared memory opt-in + resident CTAs per SM: queried once per (kernel set, table size) and kept in the context
 	// (four attribute calls and four occupancy queries per ssb_render were a measurable part of a 2 ms strong-scaling slice)
 	int occ_sf = 0, occ_sn = 0, occ_if = 0, occ_in = 0;

@@ -256,27 +256,6 @@ SSB_ISECT_FN float entry_plane_key(const float4 pl, float ox, float oy, float oz
 	return (fabsf(nd) >= SSB_GRAZE) ? tp : -__int_as_float(0x7f800000);
 }
 
-// Conservative in-plane test of one filter entry (pair record `rec`, lane `odd`): true when the half-line
-// {(u_o, v_o) + t (u_d, v_d), t >= 0} — the ray projected onto the entry's plane, in the entry's scaled rectangle
-// coordinates — misses the square [-1,1]^2 (the bounding rectangle enlarged by the margin).  Separating axes of a line
-// and a box in 2-D: u, v, and the normal of the line.  The rectangle's enlargement (>= 1e-4 of the scene extent) is
-// orders of magnitude more than the rounding of these few fused multiply-adds.  An all-zero (degenerate) entry gives
-// 0 > 0 everywhere: never rejected.
-SSB_ISECT_FN bool entry_missed_in_plane(const float4* rec, int odd, float ox, float oy, float oz, float dx, float dy, float dz) {
-	const float4 a2 = rec[2], a3 = rec[3], a4 = rec[4], a5 = rec[5];
-	const float uax = odd ? a2.y : a2.x, uay = odd ? a2.w : a2.z, uaz = odd ? a3.y : a3.x, uaw = odd ? a3.w : a3.z;
-	const float vbx = odd ? a4.y : a4.x, vby = odd ? a4.w : a4.z, vbz = odd ? a5.y : a5.x, vbw = odd ? a5.w : a5.z;
-	const float uo = __fmaf_rn(uax, ox, __fmaf_rn(uay, oy, __fmaf_rn(uaz, oz, uaw)));
-	const float vo = __fmaf_rn(vbx, ox, __fmaf_rn(vby, oy, __fmaf_rn(vbz, oz, vbw)));
-	const float ud = __fmaf_rn(uax, dx, __fmaf_rn(uay, dy, uaz * dz));
-	const float vd = __fmaf_rn(vbx, dx, __fmaf_rn(vby, dy, vbz * dz));
-	const bool sep_u = (uo > 1.0f && ud >= 0.0f) || (uo < -1.0f && ud <= 0.0f);
-	const bool sep_v = (vo > 1.0f && vd >= 0.0f) || (vo < -1.0f && vd <= 0.0f);
-	const float cr = __fmaf_rn(ud, vo, -(vd * uo));  // cross((u_d, v_d), (0,0) - (u_o, v_o)), up to sign
-	const bool sep_n = fabsf(cr) > (fabsf(ud) + fabsf(vd)) * 1.0001f;
-	return sep_u || sep_v || sep_n;
-}
-
 SSB_ISECT_NOINLINE void scene_intersect(const SceneView& S, float eps, int ignore, Hit& hit,
                                         float ox, float oy, float oz, float dx, float dy, float dz) {
 	hit.quad = -1; hit.tri = 0; hit.dist = __int_as_float(0x7f800000);
@@ -348,16 +327,12 @@ SSB_ISECT_NOINLINE void scene_intersect(const SceneView& S, float eps, int ignor
 		}
 #endif
 		// ---- phase 3: the reference's own order (one exact test per iteration keeps lanes with different candidates together)
-		// Entries that kept BOTH triangles are mostly planes the ray runs (nearly) parallel to, with the origin close to the
-		// plane — every shadow ray from the Cornell box's ceiling towards the coplanar light keeps the four other ceiling
-		// pieces and the light this way, ten exact tests at one or two lanes.  For those the filter could not place the
-		// ray/plane point, but the PROJECTION of the ray onto the plane is well conditioned whatever the angle: a hit point
-		// o + t d (t >= eps > 0) has the in-plane coordinates (u_o + t u_d, v_o + t v_d), so an entry whose enlarged
-		// rectangle the projected half-line misses cannot be hit.
-		for (unsigned m = candA & candB; m != 0u; m &= m - 1u) {
-			const int e = __ffs(m) - 1;
-			if (entry_missed_in_plane(S.fpairs() + 8 * ((base + e) >> 1), (base + e) & 1, ox, oy, oz, dx, dy, dz)) { candA &= ~(1u << e); candB &= ~(1u << e); }
-		}
+		// (Entries that keep BOTH triangles are mostly planes the ray runs (nearly) parallel to with the origin close to the
+		// plane: every shadow ray from the Cornell box's ceiling towards the coplanar light keeps the four other ceiling
+		// pieces and the light this way.  They cannot be thinned out by where the ray's projection runs in the plane: for a ray
+		// IN a triangle's plane the watertight test's U, V, W are all rounding noise around zero, and the reference accepts
+		// such a "hit" wherever the noise happens to agree in sign — also far beside the triangle.  An in-plane pre-reject
+		// tried in round 2 was caught by the device fuzz test on exactly such a ray; tests/test_gpu_isect_fuzz.py.)
 		SSB_STAT(queries, base == 0 ? 1 : 0); SSB_STAT(inorder, base == 0 ? 1 : 0); SSB_STAT(candidates, __builtin_popcount(candA) + __builtin_popcount(candB));
 		while (candA | candB) {
 			const unsigned any = candA | candB;

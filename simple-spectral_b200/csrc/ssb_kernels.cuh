@@ -79,7 +79,7 @@ struct KParams {
 	uint32_t n_wavelengths;  // SAMPLE_WAVELENGTHS (2..4): channels >= n of every Hero are exactly 0
 	uint32_t depth;     // depth processed by this launch
 	uint32_t band_h, band_n, band_i;  // ssb_options.band_*: rows j with (j / band_h) % band_n == band_i (band_n <= 1: all rows of the rectangle)
-	uint32_t scan_list;  // SSB_SCAN_LIST: the reference's plain list scan instead of the filtered one
+	uint32_t scan_list;  // ssb_debug_intersect only: SSB_SCAN_LIST (the render kernels take the scan mode as a template parameter)
 	float eps, lambda_min, lambda_step;
 	unsigned long long seed;
 	double pv_inv[16];
@@ -638,9 +638,13 @@ __device__ __forceinline__ uint32_t image_row(const KParams& P, uint32_t lr) {
 	return ((lr / P.band_h) * P.band_n + P.band_i) * P.band_h + lr % P.band_h;
 }
 // Scene::intersect as the kernels run it: the filtered scan, or (ssb_options.scan_mode, uniform) the reference's own loop
-__device__ __forceinline__ void scene_query(const KParams& P, const SceneView& S, float eps, int ignore, Hit& hit,
+// Scene::intersect as the kernels run it: the filtered scan, or — template parameter LIST, chosen by ssb_options.scan_mode —
+// the reference's own loop.  (A run-time branch on a kernel parameter cost 1 % of the frame even when never taken: the
+// second callee's registers and code; profiles/r5g_ab.txt.  Hence separate instantiations.)
+template <bool LIST>
+__device__ __forceinline__ void scene_query(const SceneView& S, float eps, int ignore, Hit& hit,
                                             float ox, float oy, float oz, float dx, float dy, float dz) {
-	if (P.scan_list) scene_intersect_listscan_noinline(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+	if (LIST) scene_intersect_listscan_noinline(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
 	else scene_intersect(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
 }
 
@@ -653,7 +657,7 @@ __device__ __forceinline__ void stage_scene(const KParams& P, unsigned long long
 // FIRST: depth 0 — the path is created here (Renderer::_render_sample prologue, renderer.cpp:103-138) and its state
 // written.  A miss ends the path (L() returns 0).  Hits are recorded and counted per hit quad, so that the shading
 // stage can run with all lanes of a warp on the same quad / material.
-template <bool FIRST>
+template <bool FIRST, bool LIST>
 __global__ void __launch_bounds__(SSB_INTERSECT_THREADS, SSB_INTERSECT_MIN_BLOCKS)
 ssb_intersect_kernel(const __grid_constant__ KParams P) {
 	__shared__ __align__(8) unsigned long long blob_bar;
@@ -744,7 +748,7 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				dx = b.x; dy = b.y; dz = b.z;
 			}
 			Hit hit;
-			scene_query(P, S, P.eps, ignore, hit, ox, oy, oz, dx, dy, dz);
+			scene_query<LIST>(S, P.eps, ignore, hit, ox, oy, oz, dx, dy, dz);
 			if (hit.quad >= 0) {
 				hq = (uint32_t)hit.quad | ((uint32_t)hit.tri << 31);
 				// hit position (Ray::at, stdafx.hpp:219): origin of the shadow ray and of the next path ray
@@ -861,7 +865,7 @@ __global__ void __launch_bounds__(SSB_MAX_QUADS) ssb_bin_scatter_kernel(const __
 #define SSB_SHADE_SYNC_MASK 8
 #endif
 #define SSB_PHASE_BARRIER_AT(k) do { if ((SSB_SHADE_SYNC_MASK >> (k)) & 1) SSB_PHASE_BARRIER(); } while (0)
-template <bool FIRST, int UPS>
+template <bool FIRST, int UPS, bool LIST>
 __global__ void __launch_bounds__(SSB_SHADE_THREADS, SSB_SHADE_MIN_BLOCKS)
 ssb_shade_kernel(const __grid_constant__ KParams P) {
 	__shared__ __align__(8) unsigned long long blob_bar;
@@ -994,7 +998,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 		// ---- phase 2: shadow query + direct contribution (renderer.cpp:192-218)
 		if (valid && light_phase && l_ndl > 0.0f) {
 			Hit hs;
-			scene_query(P, S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
+			scene_query<LIST>(S, eps, cur_quad, hs, hx, hy, hz, sx, sy, sz);
 			if (hs.quad == light_quad) {
 				const DevMaterial& lm = S.materials()[S.quads()[light_quad].material];
 				Hero emitted = material_emission<UPS>(P, S, lm, lambda_0);
@@ -1218,7 +1222,8 @@ __global__ void __launch_bounds__(256) ssb_debug_intersect_kernel(const __grid_c
 	const SceneView S;
 	for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (size_t)gridDim.x * blockDim.x) {
 		Hit hit;
-		scene_query(P, S, P.eps, ignore ? ignore[r] : -1, hit, rays[6 * r], rays[6 * r + 1], rays[6 * r + 2], rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]);
+		if (P.scan_list) scene_query<true>(S, P.eps, ignore ? ignore[r] : -1, hit, rays[6 * r], rays[6 * r + 1], rays[6 * r + 2], rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]);
+		else scene_query<false>(S, P.eps, ignore ? ignore[r] : -1, hit, rays[6 * r], rays[6 * r + 1], rays[6 * r + 2], rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]);
 		out[6 * r] = __int_as_float(hit.quad); out[6 * r + 1] = __int_as_float(hit.tri); out[6 * r + 2] = hit.dist;
 		out[6 * r + 3] = hit.bx; out[6 * r + 4] = hit.by; out[6 * r + 5] = hit.bz;
 	}

@@ -21,11 +21,13 @@ def tile_shard(rank, world, height):
     return y0, y0 + base + (1 if rank < rem else 0)
 
 
-def shard_options(opt_factory, rank, world, spp_total, mode="samples", height=None):
+def shard_options(opt_factory, rank, world, spp_total, mode="samples", height=None, band_height=8):
     """opt_factory(**fields) -> ssb_options for this rank's part of the job."""
     if mode == "samples":
         b, e = sample_shard(rank, world, spp_total)
         return opt_factory(spp=spp_total, sample_begin=b, sample_end=e)
+    if mode == "bands":  # interleaved bands of band_height rows (ssb_options.band_*): what the library and bench.py use
+        return opt_factory(spp=spp_total, band_height=band_height, band_count=world, band_index=rank)
     y0, y1 = tile_shard(rank, world, height)
     return opt_factory(spp=spp_total, y0=y0, y1=y1)
 

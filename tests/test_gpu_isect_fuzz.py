@@ -75,13 +75,25 @@ def _rand_quads(rng, n, scale, offset, kind):
     return (q * scale + offset).astype(np.float32)
 
 
-def _rays(rng, quads_v, n):
-    """A mix of ray families; returns rays (n,6) float32 and ignore (n,) int32."""
+def fuzz_quads(rng, nq, scale, offset, kind):
+    qv = _rand_quads(rng, nq, scale, offset, kind)
+    if kind != "degenerate" and nq >= 8:
+        # ties: a duplicated quad, a coplanar overlapping one, a coplanar neighbour sharing an edge (the ceiling pieces of the Cornell box)
+        qv[nq - 1] = qv[0]
+        qv[nq - 2] = qv[1] + (qv[1][1] - qv[1][0]) * np.float32(0.5)
+        qv[nq - 3] = qv[2] + (qv[2][1] - qv[2][0])
+    return qv
+
+
+def _rays(rng, quads_v, n, in_plane=False):
+    """A mix of ray families (in_plane: mostly family 4); returns rays (n,6) float32 and ignore (n,) int32."""
     lo, hi = quads_v.reshape(-1, 3).min(0).astype(np.float64), quads_v.reshape(-1, 3).max(0).astype(np.float64)
     ext = np.maximum(hi - lo, 1e-30)
     nq = quads_v.shape[0]
     o = np.empty((n, 3)); d = np.empty((n, 3)); ign = np.full(n, -1, np.int32)
     fam = rng.integers(0, 6, n)
+    if in_plane:
+        fam = np.where(rng.uniform(size=n) < 0.85, 4, fam)
     qi = rng.integers(0, nq, n)
     s, t = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
     special = np.array([0.0, 1.0, 0.5, 1e-7, 1 - 1e-7, 1e-4, 1 - 1e-4, 0.25])
@@ -109,9 +121,9 @@ def _rays(rng, quads_v, n):
     e1 = Q[:, 1] - Q[:, 0]; e2 = Q[:, 3] - Q[:, 0]
     inpl = e1 * rng.uniform(-1, 1, n)[:, None] + e2 * rng.uniform(-1, 1, n)[:, None]
     nrm = np.cross(e1, e2); nn = np.linalg.norm(nrm, axis=1); nrm = nrm / np.where(nn > 0, nn, 1)[:, None]
-    tilt = 10.0 ** rng.uniform(-9, -1, n) * rng.choice([-1, 0, 1], n)
+    tilt = 10.0 ** rng.uniform(-9, -1, n) * rng.choice([-1, 0, 1], n, p=[0.15, 0.7, 0.15] if in_plane else None)
     d[m] = (inpl + nrm * (tilt * np.linalg.norm(inpl, axis=1))[:, None])[m]
-    o[m] = (target - inpl * rng.uniform(0, 2, n)[:, None])[m]
+    o[m] = (target - inpl * rng.uniform(0.7 if in_plane else 0.0, 3.0 if in_plane else 2.0, n)[:, None])[m]
     m4 = m & (rng.uniform(size=n) < 0.5); ign[m4] = qi[m4]
     # 5: from a quad's surface into a random direction, ignoring it
     m = fam == 5; o[m] = target[m]; ign[m] = qi[m]
@@ -133,20 +145,20 @@ CASES = [  # name, quads, kind, scale, offset, rays
     ("14 degenerate", 14, "degenerate", 1.0, 0.0, 300_000),
     ("10 slivers x1000", 10, "sliver", 1000.0, 0.0, 300_000),
     ("18 trapezoids", 18, "trapezoid", 300.0, 100.0, 500_000),
+    # rays IN the planes of the quads, large coordinates: the watertight test's U, V, W are rounding noise there and the
+    # reference accepts "hits" beside the triangles (caught an in-plane pre-reject in round 2)
+    ("in-plane rays, 18 trapezoids x300", 18, "trapezoid", 300.0, 100.0, 1_000_000),
+    ("in-plane rays, 19 axis boxes x550", 19, "axis", 550.0, 275.0, 1_000_000),
+    ("in-plane rays, 16 mixed x1e4", 16, "mixed", 1e4, 0.0, 500_000),
 ]
 
 
 @pytest.mark.parametrize("name,nq,kind,scale,offset,nrays", CASES, ids=[c[0].replace(" ", "_") for c in CASES])
 def test_device_scan_equals_list_scan_on_random_scenes(name, nq, kind, scale, offset, nrays):
     rng = np.random.default_rng(zlib.crc32(name.encode()))
-    qv = _rand_quads(rng, nq, scale, offset, kind)
-    if kind != "degenerate" and nq >= 8:
-        # ties: a duplicated quad, a coplanar overlapping one, a coplanar neighbour sharing an edge (the ceiling pieces of the Cornell box)
-        qv[nq - 1] = qv[0]
-        qv[nq - 2] = qv[1] + (qv[1][1] - qv[1][0]) * np.float32(0.5)
-        qv[nq - 3] = qv[2] + (qv[2][1] - qv[2][0])
+    qv = fuzz_quads(rng, nq, scale, offset, kind)
     sc = _scene(qv)
-    rays, ign = _rays(rng, qv, nrays)
+    rays, ign = _rays(rng, qv, nrays, in_plane=name.startswith("in-plane"))
     eps = np.float32(1e-3 if scale >= 1 else 1e-6)
     want = pu.oracle_intersect(sc, rays, ign, eps)
     with pu.ssb.Context(0) as ctx:
@@ -158,7 +170,7 @@ def test_device_scan_equals_list_scan_on_random_scenes(name, nq, kind, scale, of
                                                 (got[3].view(np.uint32) != want[3].view(np.uint32)).any(axis=1)))
             assert not bad.any(), (name, mode, int(bad.sum()), int(np.flatnonzero(bad)[0]), rays[np.flatnonzero(bad)[0]], ign[np.flatnonzero(bad)[0]],
                                    [g[np.flatnonzero(bad)[0]] for g in got], [w[np.flatnonzero(bad)[0]] for w in want])
-    assert hit.mean() > 0.02, (name, hit.mean())  # the rays do hit things
+    assert hit.mean() > 0.02 or name.startswith("in-plane"), (name, hit.mean())  # the rays do hit things
 
 
 def test_render_with_the_list_scan_switch_is_bit_identical():

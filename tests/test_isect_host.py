@@ -56,3 +56,31 @@ def test_device_scene_intersect_equals_list_scan(tmp_path):
     # the nearest-first phase must actually be the one that runs on the reference's scenes
     for line in r.stdout.splitlines()[:2]:
         assert "nearest-first 0." in line and float(line.split("nearest-first ")[1].split()[0]) > 0.5, line
+
+
+def test_host_build_of_the_filter_on_the_device_fuzz_scenes(tmp_path):
+    """The random scenes and ray families of tests/test_gpu_isect_fuzz.py (in-plane rays, slivers, degenerate and
+    coplanar-overlapping quads, 1e-3 ... 1e6 coordinates) through the HOST build of the same scene_intersect
+    (tools/isect_host_lib.cpp), against the checker's list scan — fewer rays than the device run, same generators."""
+    import zlib
+    import numpy as np
+    import test_gpu_isect_fuzz as fz
+    so = str(tmp_path / "libisect_host.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, os.path.join(pu.ROOT, "tools", "isect_host_lib.cpp")], check=True)
+    L = C.CDLL(so)
+    L.isect_host.argtypes = [C.POINTER(_abi.ssb_quad), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_uint32, C.c_float, C.POINTER(C.c_float), C.c_size_t]
+    for name, nq, kind, scale, offset, nrays in fz.CASES:
+        rng = np.random.default_rng(zlib.crc32(name.encode()))
+        qv = fz.fuzz_quads(rng, nq, scale, offset, kind)
+        sc = fz._scene(qv)
+        rays, ign = fz._rays(rng, qv, min(nrays, 400_000), in_plane=name.startswith("in-plane"))
+        eps = np.float32(1e-3 if scale >= 1 else 1e-6)
+        want = pu.oracle_intersect(sc, rays, ign, eps)
+        out = np.empty((rays.shape[0], 6), np.float32)
+        L.isect_host(sc.quads, nq, rays.ctypes.data_as(C.POINTER(C.c_float)), ign.ctypes.data_as(C.POINTER(C.c_int32)), 0, float(eps),
+                     out.ctypes.data_as(C.POINTER(C.c_float)), rays.shape[0])
+        got = (out[:, 0].view(np.int32), out[:, 1].view(np.int32), out[:, 2], out[:, 3:6])
+        hit = want[0] >= 0
+        bad = (got[0] != want[0]) | (hit & ((got[1] != want[1]) | (got[2].view(np.uint32) != want[2].view(np.uint32)) |
+                                            (np.ascontiguousarray(got[3]).view(np.uint32) != want[3].view(np.uint32)).any(axis=1)))
+        assert not bad.any(), (name, int(bad.sum()), rays[np.flatnonzero(bad)[0]], ign[np.flatnonzero(bad)[0]])

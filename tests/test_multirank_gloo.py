@@ -44,7 +44,7 @@ def _worker(rank, world, port, mode, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     flat = pu.load_flat("cornell", "ours1931")
     W, H, SPP = 16, 12, 6
-    opt = sharding.shard_options(lambda **kw: pu.options("ours1931", W, H, seed=3, **kw), rank, world, SPP, mode=mode, height=H)
+    opt = sharding.shard_options(lambda **kw: pu.options("ours1931", W, H, seed=3, **kw), rank, world, SPP, mode=mode, height=H, band_height=5)
     acc, _, _ = pu.oracle_render(flat, opt)
     t = torch.from_numpy(acc.reshape(-1))
     sharding.reduce_accumulators(t, dist, dst=0)
@@ -54,7 +54,7 @@ def _worker(rank, world, port, mode, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["samples", "tiles"])
+@pytest.mark.parametrize("mode", ["samples", "tiles", "bands"])
 def test_two_ranks_reduce_to_the_single_rank_frame(tmp_path, mode):
     out = str(tmp_path / "acc.npy")
     mp.spawn(_worker, args=(2, _free_port(), mode, out), nprocs=2, join=True)
@@ -62,7 +62,7 @@ def test_two_ranks_reduce_to_the_single_rank_frame(tmp_path, mode):
     flat = pu.load_flat("cornell", "ours1931")
     full = pu.options("ours1931", 16, 12, 6, seed=3)
     want, _, _ = pu.oracle_render(flat, full)
-    if mode == "tiles":
+    if mode in ("tiles", "bands"):
         assert pu.bits_equal(got, want)            # disjoint pixels: bit-identical
     else:
         assert np.allclose(got, want, rtol=1e-14, atol=0)  # same samples, f64 summation order differs

@@ -44,6 +44,9 @@ if tot_wi:
             print(f"  {n:45s} {a[3]/1e9:8.3f} G warp-inst  {100*a[3]/tot_wi:5.1f}%   lanes {a[4]/a[3]:5.1f}")
 if len(sys.argv) > 2:
     bounce_b = sum(a[2] for n, a in agg.items() if "fold" not in n and "accumulate" not in n and "resolve" not in n)
-    json.dump({"dram_bytes_per_frame": tot_b, "dram_bytes_per_launch": bounce_b, "launches_per_frame": len(f),
+    import os, sys as _sys
+    _sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    json.dump({"source_sha": bench.source_sha(), "dram_bytes_per_frame": tot_b, "dram_bytes_per_launch": bounce_b, "launches_per_frame": len(f),
                "warp_instructions_per_frame": tot_wi, "thread_instructions_per_frame": tot_ti,
                "share": {n: a[1] / tot_ms for n, a in agg.items()}}, open(sys.argv[2], "w"), indent=1)
