@@ -439,28 +439,61 @@ static int upload_scene_impl(ssb_ctx* c, const ssb_scene* scene, bool async) {
 		SSB_CUDA(cudaStreamSynchronize(c->stream));
 		c->tex_pending = false;
 	}
-	std::vector<uchar4*> old_tex; old_tex.swap(c->d_textures);
-	std::vector<uint32_t> old_w; old_w.swap(c->tex_w);
-	std::vector<uint32_t> old_h; old_h.swap(c->tex_h);
+	// ---- textures, transactionally: (1) everything that can be refused is checked, and every buffer the new scene needs is
+	// allocated, BEFORE the context is touched — a NULL texel pointer or an out-of-memory leaves the previous scene intact;
+	// (2) only then are texels enqueued into (re-used or new) buffers; a CUDA error past that point invalidates the scene
+	// (have_scene = false, all texture buffers released) instead of leaving materials that index a half-built table.
 	for (uint32_t t = 0; t < scene->ntextures; ++t) {
 		const ssb_texture& tx = scene->textures[t];
 		if (!tx.rgb8 || tx.width == 0 || tx.height == 0) return fail(SSB_ERR_DATA, "texture %u: could not load texture", t);  // material.cpp:15-18
-		size_t n = (size_t)tx.width * tx.height;
-		uchar4* d = nullptr;
-		if (t < old_tex.size() && old_w[t] == tx.width && old_h[t] == tx.height) { d = old_tex[t]; old_tex[t] = nullptr; }
-		else SSB_CUDA(cudaMalloc(&d, n * sizeof(uchar4)));
-		c->d_textures.push_back(d); c->tex_w.push_back(tx.width); c->tex_h.push_back(tx.height);
-		if (3 * n > c->rgb_staging_capacity) {
-			cudaFree(c->d_rgb_staging); c->d_rgb_staging = nullptr; c->rgb_staging_capacity = 0;
-			SSB_CUDA(cudaMalloc(&c->d_rgb_staging, 3 * n));
-			c->rgb_staging_capacity = 3 * n;
-		}
-		// one H2D copy of the caller's RGB8 scanlines (fast when the caller's buffer is pinned), repack on the device
-		SSB_CUDA(cudaMemcpyAsync(c->d_rgb_staging, tx.rgb8, 3 * n, cudaMemcpyHostToDevice, up));
-		ssb_repack_rgb8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, up>>>(c->d_rgb_staging, d, n);
-		SSB_CUDA(cudaGetLastError());
 	}
-	for (uchar4* p : old_tex) if (p) cudaFree(p);
+	std::vector<uchar4*> new_tex(scene->ntextures, nullptr);
+	std::vector<char> reused(scene->ntextures, 0);
+	size_t staging_need = 0;
+	for (uint32_t t = 0; t < scene->ntextures; ++t) staging_need = std::max(staging_need, (size_t)3 * scene->textures[t].width * scene->textures[t].height);
+	unsigned char* new_staging = nullptr;
+	auto release_new = [&]() {
+		for (uint32_t t = 0; t < scene->ntextures; ++t) if (new_tex[t] && !reused[t]) cudaFree(new_tex[t]);
+		if (new_staging) cudaFree(new_staging);
+	};
+	for (uint32_t t = 0; t < scene->ntextures; ++t) {
+		const ssb_texture& tx = scene->textures[t];
+		if (t < c->d_textures.size() && c->tex_w[t] == tx.width && c->tex_h[t] == tx.height) { new_tex[t] = c->d_textures[t]; reused[t] = 1; continue; }
+		cudaError_t e = cudaMalloc(&new_tex[t], (size_t)tx.width * tx.height * sizeof(uchar4));
+		if (e != cudaSuccess) { new_tex[t] = nullptr; release_new(); return fail(SSB_ERR_DATA, "ssb_upload_scene: texture %u: %s", t, cudaGetErrorString(e)); }
+	}
+	if (staging_need > c->rgb_staging_capacity) {
+		cudaError_t e = cudaMalloc(&new_staging, staging_need);
+		if (e != cudaSuccess) { new_staging = nullptr; release_new(); return fail(SSB_ERR_DATA, "ssb_upload_scene: staging buffer: %s", cudaGetErrorString(e)); }
+	}
+	// ---- commit
+	if (new_staging) {
+		cudaStreamSynchronize(up);  // (a previous asynchronous upload may still read the old staging buffer)
+		cudaFree(c->d_rgb_staging);
+		c->d_rgb_staging = new_staging; c->rgb_staging_capacity = staging_need;
+	}
+	for (size_t t = 0; t < c->d_textures.size(); ++t)
+		if (!(t < scene->ntextures && reused[t])) cudaFree(c->d_textures[t]);  // (the synchronisation / event wait above covers their last reader)
+	c->d_textures.assign(new_tex.begin(), new_tex.end());
+	c->tex_w.resize(scene->ntextures); c->tex_h.resize(scene->ntextures);
+	cudaError_t copy_err = cudaSuccess;
+	for (uint32_t t = 0; t < scene->ntextures && copy_err == cudaSuccess; ++t) {
+		const ssb_texture& tx = scene->textures[t];
+		const size_t n = (size_t)tx.width * tx.height;
+		c->tex_w[t] = tx.width; c->tex_h[t] = tx.height;
+		// one H2D copy of the caller's RGB8 scanlines (fast when the caller's buffer is pinned), repack on the device
+		copy_err = cudaMemcpyAsync(c->d_rgb_staging, tx.rgb8, 3 * n, cudaMemcpyHostToDevice, up);
+		if (copy_err == cudaSuccess) {
+			ssb_repack_rgb8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, up>>>(c->d_rgb_staging, c->d_textures[t], n);
+			copy_err = cudaGetLastError();
+		}
+	}
+	if (copy_err != cudaSuccess) {
+		cudaStreamSynchronize(up);
+		free_textures(c);
+		c->have_scene = false; c->blob_dirty = true; c->tex_pending = false;
+		return fail(SSB_ERR_DATA, "ssb_upload_scene: texel upload failed (%s); the context holds no scene now", cudaGetErrorString(copy_err));
+	}
 	if (async) {
 		SSB_CUDA(cudaEventRecord(c->ev_tex_ready, up));
 		c->tex_pending = scene->ntextures != 0;
@@ -488,28 +521,42 @@ int ssb_upload_color(ssb_ctx* c, const ssb_color* color) {
 	if ((rc = copy_spectrum(color->basis_b, c->basis_b, "basis_b", false)) != SSB_OK) return rc;
 	memcpy(c->xyz_to_lrgb, color->xyz_to_lrgb, sizeof(c->xyz_to_lrgb));
 	c->d65_rad_Y = color->d65_rad_Y;
-	SSB_CUDA(cudaStreamSynchronize(c->stream));
-	cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); c->d_jh_scale = c->d_jh_data = nullptr; c->jh_res = 0;
+	SSB_CUDA(cudaStreamSynchronize(c->stream));  // no render may still read the tables that are replaced below
+	// Jakob-Hanika (9.4 MB) and Meng (69 KB) tables: the device buffers are kept across calls and only re-allocated when
+	// their size changes (a caller that re-uploads its colour tables every frame paid a cudaFree + cudaMalloc of 9.4 MB
+	// per call: the end-to-end leg of the JH configuration)
 	if (color->jh_res) {
 		if (!color->jh_scale || !color->jh_data) return fail(SSB_ERR_ARG, "ssb_upload_color: JH tables missing");
 		size_t res = color->jh_res, nd = 3 * res * res * res * 3;
-		SSB_CUDA(cudaMalloc(&c->d_jh_scale, res * sizeof(float)));
-		SSB_CUDA(cudaMalloc(&c->d_jh_data, nd * sizeof(float)));
+		if (c->jh_res != color->jh_res || !c->d_jh_scale || !c->d_jh_data) {
+			cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); c->d_jh_scale = c->d_jh_data = nullptr; c->jh_res = 0;
+			SSB_CUDA(cudaMalloc(&c->d_jh_scale, res * sizeof(float)));
+			SSB_CUDA(cudaMalloc(&c->d_jh_data, nd * sizeof(float)));
+		}
+		c->jh_res = 0;  // (invalid until both copies have landed)
 		SSB_CUDA(copy_to_device(c, c->d_jh_scale, color->jh_scale, res * sizeof(float)));
 		SSB_CUDA(copy_to_device(c, c->d_jh_data, color->jh_data, nd * sizeof(float)));
 		c->jh_res = color->jh_res;
+	} else {
+		cudaFree(c->d_jh_scale); cudaFree(c->d_jh_data); c->d_jh_scale = c->d_jh_data = nullptr; c->jh_res = 0;
 	}
-	cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points); c->d_meng_grid = nullptr; c->d_meng_points = nullptr; c->have_meng = false;
 	if (color->meng) {
 		const ssb_meng_tables& m = *color->meng;
 		if (!m.grid || !m.points || m.grid_w == 0 || m.grid_h == 0 || m.npoints == 0 || m.nsamples < 2) return fail(SSB_ERR_ARG, "ssb_upload_color: bad Meng tables");
 		size_t ng = (size_t)m.grid_w * m.grid_h * 8, np = (size_t)m.npoints * (5 + m.nsamples);
-		SSB_CUDA(cudaMalloc(&c->d_meng_grid, ng * sizeof(int32_t)));
-		SSB_CUDA(cudaMalloc(&c->d_meng_points, np * sizeof(float)));
+		const bool same = c->have_meng && c->meng.grid_w == m.grid_w && c->meng.grid_h == m.grid_h && c->meng.npoints == m.npoints && c->meng.nsamples == m.nsamples;
+		c->have_meng = false;
+		if (!same) {
+			cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points); c->d_meng_grid = nullptr; c->d_meng_points = nullptr;
+			SSB_CUDA(cudaMalloc(&c->d_meng_grid, ng * sizeof(int32_t)));
+			SSB_CUDA(cudaMalloc(&c->d_meng_points, np * sizeof(float)));
+		}
 		SSB_CUDA(copy_to_device(c, c->d_meng_grid, m.grid, ng * sizeof(int32_t)));
 		SSB_CUDA(copy_to_device(c, c->d_meng_points, m.points, np * sizeof(float)));
 		c->meng = m; c->meng.grid = nullptr; c->meng.points = nullptr;
 		c->have_meng = true;
+	} else {
+		cudaFree(c->d_meng_grid); cudaFree(c->d_meng_points); c->d_meng_grid = nullptr; c->d_meng_points = nullptr; c->have_meng = false;
 	}
 	c->have_color = true; c->blob_dirty = true;
 	c->coef_valid = false;  // the JH tables may have changed

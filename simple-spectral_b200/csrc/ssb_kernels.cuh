@@ -323,66 +323,86 @@ __device__ __noinline__ Hero jh_upsample(const KParams& P, float r, float g, flo
 __device__ __noinline__ Hero jh_eval_baked(const KParams& P, float4 cf, float lambda_0) {
 	return jh_eval(P, cf.x, cf.y, cf.z, lambda_0);
 }
-// spectrum_xyz_to_p (meng-et-al.-2015/spectrum_grid.h:13-137)
-__device__ __noinline__ float meng_xyz_to_p(const KParams& P, float lambda, const float* xyz) {
+// spectrum_xyz_to_p (meng-et-al.-2015/spectrum_grid.h:13-137) for the hero wavelengths of one colour.  The reference calls
+// it once per wavelength (color.cpp:196-199) and every call repeats the part that does not depend on the wavelength: the
+// chromaticity, the grid cell, and — for a border cell — the walk around the triangle fan that ends with the barycentric
+// weights (u, v, w) of the triangle holding the point.  Here that part runs ONCE per colour and only the spectral
+// interpolation of the cell's corner points runs per wavelength: the same operations on the same operands, so every
+// returned value is the per-call one bit for bit (as with the shared grid arithmetic of spec_sample3).
+__device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
+	// color.cpp:189-200: xyz_rel = transpose(M) * 100 * lrgb
+	const float M[9] = { 0.41231515f, 0.3576f, 0.1805f, 0.2126f, 0.7152f, 0.0722f, 0.01932727f, 0.1192f, 0.95063333f };
+	float xyz[3];
+	for (int rr = 0; rr < 3; ++rr)
+		xyz[rr] = ((M[rr * 3 + 0] * 100.0f) * r + (M[rr * 3 + 1] * 100.0f) * g) + (M[rr * 3 + 2] * 100.0f) * b;
+	Hero h;
+	h.v[0] = h.v[1] = h.v[2] = h.v[3] = 0.0f;
 	float xyY[3], uv[2];
 	const float norm = (float)(1.0 / (double)((xyz[0] + xyz[1]) + xyz[2]));
-	if (!(norm < 3.402823466e+38f)) return 0.0f;
+	if (!(norm < 3.402823466e+38f)) return h;
 	xyY[0] = xyz[0] * norm; xyY[1] = xyz[1] * norm; xyY[2] = xyz[1];
 	uv[0] = P.meng_xy_to_uv[0] * xyY[0] + P.meng_xy_to_uv[1] * xyY[1] + P.meng_xy_to_uv[2];
 	uv[1] = P.meng_xy_to_uv[3] * xyY[0] + P.meng_xy_to_uv[4] * xyY[1] + P.meng_xy_to_uv[5];
-	if (uv[0] < 0.0f || uv[0] >= (float)P.meng_grid_w || uv[1] < 0.0f || uv[1] >= (float)P.meng_grid_h) return 0.f;
-	int uvi[2] = { (int)uv[0], (int)uv[1] };
+	if (uv[0] < 0.0f || uv[0] >= (float)P.meng_grid_w || uv[1] < 0.0f || uv[1] >= (float)P.meng_grid_h) return h;
+	const int uvi[2] = { (int)uv[0], (int)uv[1] };
 	const int cell_idx = uvi[0] + (int)P.meng_grid_w * uvi[1];
-	const int32_t* cell = P.meng_grid + 8 * cell_idx;
-	const int inside = cell[0], num = cell[1];
-	const int32_t* idx = cell + 2;
+	const int32_t* __restrict__ cell = P.meng_grid + 8 * cell_idx;
+	const int4 c0 = __ldg(reinterpret_cast<const int4*>(cell)), c1 = __ldg(reinterpret_cast<const int4*>(cell) + 1);
+	const int inside = c0.x, num = c0.y;
+	const int idx[6] = { c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
 	const uint32_t stride = 5 + P.meng_nsamples;
-	float p[6];
+	const float* __restrict__ pts = P.meng_points;
 	const int ns = (int)P.meng_nsamples;
-	const float sb = (lambda - P.meng_sample_min) / (P.meng_sample_max - P.meng_sample_min) * (float)(ns - 1);
-	const int sb0 = (int)sb;
-	const int sb1 = sb + 1 < (float)ns ? (int)(sb + 1) : ns - 1;
-	const float sbf = sb - (float)sb0;
-	for (int i = 0; i < num; ++i) {
-		const float* spectrum = P.meng_points + (size_t)stride * idx[i] + 5;
-		p[i] = spectrum[sb0] * (1.0f - sbf) + spectrum[sb1] * sbf;
-	}
-	float interpolated_p = 0.0f;
+	// ---- the wavelength-independent part: which corner points are blended, with which weights
+	//   inside: the bilinear weights of the four corners (layout 2 3 / 0 1);  border: p[0] * w + p[ia] * v + p[ib] * u
+	int ia = -1, ib = -1;
+	float wu = 0.0f, wv = 0.0f, ww = 0.0f, fu = 0.0f, fv = 0.0f;
 	if (inside) {
-		uv[0] -= (float)uvi[0]; uv[1] -= (float)uvi[1];
-		interpolated_p = p[0] * (1.0f - uv[0]) * (1.0f - uv[1]) + p[2] * (1.0f - uv[0]) * uv[1] +
-		                 p[3] * uv[0] * uv[1] + p[1] * uv[0] * (1.0f - uv[1]);
+		fu = uv[0] - (float)uvi[0]; fv = uv[1] - (float)uvi[1];
 	} else {
-#define SSB_MENG_UV(k, c) (P.meng_points[(size_t)stride * idx[k] + 3 + (c)])
-		const float ex = uv[0] - SSB_MENG_UV(0, 0), ey = uv[1] - SSB_MENG_UV(0, 1);
-		float e0x = SSB_MENG_UV(1, 0) - SSB_MENG_UV(0, 0), e0y = SSB_MENG_UV(1, 1) - SSB_MENG_UV(0, 1);
+#define SSB_MENG_UV(k, c) __ldg(pts + (size_t)stride * idx[k] + 3 + (c))
+		const float p0u = SSB_MENG_UV(0, 0), p0v = SSB_MENG_UV(0, 1);
+		const float p1u = SSB_MENG_UV(1, 0), p1v = SSB_MENG_UV(1, 1);
+		const float ex = uv[0] - p0u, ey = uv[1] - p0v;
+		float e0x = p1u - p0u, e0y = p1v - p0v;
 		float uu = e0x * ey - ex * e0y;
 		for (int i = 0; i < num - 1; i++) {
 			float e1x, e1y;
-			if (i == num - 2) { e1x = SSB_MENG_UV(1, 0) - SSB_MENG_UV(0, 0); e1y = SSB_MENG_UV(1, 1) - SSB_MENG_UV(0, 1); }
-			else { e1x = SSB_MENG_UV(i + 2, 0) - SSB_MENG_UV(0, 0); e1y = SSB_MENG_UV(i + 2, 1) - SSB_MENG_UV(0, 1); }
-			float vv = ex * e1y - e1x * ey;
+			if (i == num - 2) { e1x = p1u - p0u; e1y = p1v - p0v; }
+			else { e1x = SSB_MENG_UV(i + 2, 0) - p0u; e1y = SSB_MENG_UV(i + 2, 1) - p0v; }
+			const float vv = ex * e1y - e1x * ey;
 			const float area = e0x * e1y - e1x * e0y;
 			const float u = uu / area, v = vv / area;
-			float w = 1.0f - u - v;
+			const float w = 1.0f - u - v;
 			if (u < 0.0f || v < 0.0f || w < 0.0f) { uu = -vv; e0x = e1x; e0y = e1y; continue; }
-			interpolated_p = p[0] * w + p[i + 1] * v + p[(i == num - 2) ? 1 : (i + 2)] * u;
+			ia = i + 1; ib = (i == num - 2) ? 1 : (i + 2);
+			wu = u; wv = v; ww = w;
 			break;
 		}
 #undef SSB_MENG_UV
 	}
-	return interpolated_p / norm;
-}
-__device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
-	// color.cpp:189-200: xyz_rel = transpose(M) * 100 * lrgb
-	const float M[9] = { 0.41231515f, 0.3576f, 0.1805f, 0.2126f, 0.7152f, 0.0722f, 0.01932727f, 0.1192f, 0.95063333f };
-	float xyz_rel[3];
-	for (int rr = 0; rr < 3; ++rr)
-		xyz_rel[rr] = ((M[rr * 3 + 0] * 100.0f) * r + (M[rr * 3 + 1] * 100.0f) * g) + (M[rr * 3 + 2] * 100.0f) * b;
-	Hero h;
-	for (int k = 0; k < 4; ++k)  // (wavelengths past the last channel may lie outside the tables: not evaluated)
-		h.v[k] = (uint32_t)k < P.n_wavelengths ? meng_xyz_to_p(P, lambda_0 + (float)k * P.lambda_step, xyz_rel) : 0.0f;
+	// ---- per wavelength: the corner points' spectra at lambda (linear in the table's sample grid), blended
+	for (int k = 0; k < 4; ++k) {  // (wavelengths past the last channel may lie outside the tables: not evaluated)
+		if ((uint32_t)k >= P.n_wavelengths) break;
+		const float lambda = lambda_0 + (float)k * P.lambda_step;
+		const float sb = (lambda - P.meng_sample_min) / (P.meng_sample_max - P.meng_sample_min) * (float)(ns - 1);
+		const int sb0 = (int)sb;
+		const int sb1 = sb + 1 < (float)ns ? (int)(sb + 1) : ns - 1;
+		const float sbf = sb - (float)sb0;
+		auto corner = [&](int i) {
+			const float* spectrum = pts + (size_t)stride * idx[i] + 5;
+			return __ldg(spectrum + sb0) * (1.0f - sbf) + __ldg(spectrum + sb1) * sbf;
+		};
+		float interpolated_p = 0.0f;
+		if (inside) {
+			const float p0 = corner(0), p1 = corner(1), p2 = corner(2), p3 = corner(3);
+			interpolated_p = p0 * (1.0f - fu) * (1.0f - fv) + p2 * (1.0f - fu) * fv + p3 * fu * fv + p1 * fu * (1.0f - fv);
+		} else if (ia >= 0) {
+			const float p0 = corner(0), pa = corner(ia), pb = corner(ib);
+			interpolated_p = p0 * ww + pa * wv + pb * wu;
+		}
+		h.v[k] = interpolated_p / norm;
+	}
 	return h;
 }
 
