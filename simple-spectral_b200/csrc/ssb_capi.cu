@@ -707,7 +707,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	memcpy(P.meng_xy_to_uv, c->meng.xy_to_uv, sizeof(P.meng_xy_to_uv));
 	P.meng_sample_min = c->meng.sample_min; P.meng_sample_max = c->meng.sample_max;
 
-	const size_t smem = c->blob_bytes;
+	const size_t smem = c->blob_bytes;  // the scene tables; the two big kernels add their record pipelines behind them
+	const size_t smem_i = align_up(smem, 128) + SSB_INTERSECT_PIPE_BYTES, smem_s = align_up(smem, 128) + SSB_SHADE_PIPE_BYTES;
 	typedef void (*kfn)(const KParams);
 	kfn k_shade_first = nullptr, k_shade_next = nullptr, k_isect_first = nullptr, k_isect_next = nullptr;
 	// one instantiation per upsampling mode keeps the instruction footprint small; LIST = ssb_options.scan_mode
@@ -728,12 +729,12 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	// (four attribute calls and four occupancy queries per ssb_render were a measurable part of a 2 ms strong-scaling slice)
 	int occ_sf = 0, occ_sn = 0, occ_if = 0, occ_in = 0;
 	if (c->occ_key_kernel != (const void*)k_shade_next || c->occ_key_smem != smem) {
-		for (kfn k : { k_shade_first, k_shade_next, k_isect_first, k_isect_next })
-			SSB_CUDA(raise_dynamic_smem_limit(c->device, (const void*)k, smem));
-		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[0], k_shade_first, SSB_SHADE_THREADS, smem));
-		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[1], k_shade_next, SSB_SHADE_THREADS, smem));
-		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[2], k_isect_first, SSB_INTERSECT_THREADS, smem));
-		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[3], k_isect_next, SSB_INTERSECT_THREADS, smem));
+		for (kfn k : { k_shade_first, k_shade_next }) SSB_CUDA(raise_dynamic_smem_limit(c->device, (const void*)k, smem_s));
+		for (kfn k : { k_isect_first, k_isect_next }) SSB_CUDA(raise_dynamic_smem_limit(c->device, (const void*)k, smem_i));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[0], k_shade_first, SSB_SHADE_THREADS, smem_s));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[1], k_shade_next, SSB_SHADE_THREADS, smem_s));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[2], k_isect_first, SSB_INTERSECT_THREADS, smem_i));
+		SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ[3], k_isect_next, SSB_INTERSECT_THREADS, smem_i));
 		c->occ_key_kernel = (const void*)k_shade_next; c->occ_key_smem = smem;
 	}
 	occ_sf = c->occ[0]; occ_sn = c->occ[1]; occ_if = c->occ[2]; occ_in = c->occ[3];
@@ -760,7 +761,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			const unsigned long long want_s = (P.total_work + SSB_SHADE_THREADS - 1) / SSB_SHADE_THREADS;
 			const unsigned grid_i = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_if : occ_in), want_i);
 			const unsigned grid_s = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * (d == 0 ? occ_sf : occ_sn), want_s);
-			(d == 0 ? k_isect_first : k_isect_next)<<<grid_i, SSB_INTERSECT_THREADS, smem, c->stream>>>(P);
+			(d == 0 ? k_isect_first : k_isect_next)<<<grid_i, SSB_INTERSECT_THREADS, smem_i, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
 			if (c->tex_pending) {  // texels are first read by the shade stage: the camera-ray queries overlap the upload
 				SSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tex_ready, 0));
@@ -769,7 +770,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			const unsigned grid_b = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * 8, (P.total_work + 1023) / 1024);
 			ssb_bin_scatter_kernel<<<grid_b, SSB_MAX_QUADS, 0, c->stream>>>(P, d == 0 ? 1u : 0u, nquads);
 			SSB_CUDA(cudaGetLastError());
-			(d == 0 ? k_shade_first : k_shade_next)<<<grid_s, SSB_SHADE_THREADS, smem, c->stream>>>(P);
+			(d == 0 ? k_shade_first : k_shade_next)<<<grid_s, SSB_SHADE_THREADS, smem_s, c->stream>>>(P);
 			SSB_CUDA(cudaGetLastError());
 			launches += 3;
 		}

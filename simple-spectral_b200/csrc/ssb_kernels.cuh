@@ -637,13 +637,14 @@ __device__ __forceinline__ void ld_sector(const float4* p, float4& a, float4& b)
 	asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p) : "memory");
 }
 
-// launch bounds, measured (profiles/r5e_ab.txt, r5f_ab.txt): intersect 512 x 2 beats 256 x 4 by 1 % (the same 32 warps per SM
-// in half as many CTAs: half the blob stagings and histogram flushes); shade 256 x 3 beats 192 x 4 and 128 x 6 by 4 %
+// launch bounds, measured (profiles/r5e_ab.txt, r5p_ab.txt): intersect 1024 x 1 beats 512 x 2 by 1 % and 256 x 4 by 2 % (the same
+// 32 warps per SM in fewer CTAs: fewer blob stagings and histogram flushes per launch); shade 256 x 3 beats 384 x 2 by 0.4 %,
+// 192 x 4 and 128 x 6 by 4 %
 #ifndef SSB_INTERSECT_THREADS
-#define SSB_INTERSECT_THREADS 512
+#define SSB_INTERSECT_THREADS 1024
 #endif
 #ifndef SSB_INTERSECT_MIN_BLOCKS
-#define SSB_INTERSECT_MIN_BLOCKS 2
+#define SSB_INTERSECT_MIN_BLOCKS 1
 #endif
 #ifndef SSB_SHADE_THREADS
 #define SSB_SHADE_THREADS 256
@@ -667,6 +668,11 @@ __device__ __forceinline__ void scene_query(const SceneView& S, float eps, int i
 	if (LIST) scene_intersect_listscan_noinline(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
 	else scene_intersect(S, eps, ignore, hit, ox, oy, oz, dx, dy, dz);
 }
+
+// the record pipelines live in dynamic shared memory right behind the blob (host side: ssb_pipe_offset / launch sizes in ssb_render)
+__device__ __forceinline__ uint32_t pipe_offset(const SceneView& S) { return (S.hdr()->total_bytes + 127u) & ~127u; }
+#define SSB_INTERSECT_PIPE_BYTES (2u * 2u * SSB_INTERSECT_THREADS * 16u)
+#define SSB_SHADE_PIPE_BYTES (2u * 4u * SSB_SHADE_THREADS * 16u)
 
 __device__ __forceinline__ void stage_scene(const KParams& P, unsigned long long* bar) {
 	const DevHeader* gh = reinterpret_cast<const DevHeader*>(P.blob);
@@ -699,7 +705,8 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 #if SSB_PIPELINE_ISECT
 	// [stage][record: recA.0, recA.1][thread]  (the sample id, needed only by the few paths that miss, is fetched on demand:
 	// prefetching recR for every path moved 32 B per query for nothing)
-	__shared__ float4 s_pipe[FIRST ? 1 : 2][FIRST ? 1 : 2][FIRST ? 1 : SSB_INTERSECT_THREADS];
+	// (in DYNAMIC shared memory behind the blob: launch bounds above 384 threads would exceed the 48 KB of static shared memory)
+	float4 (*s_pipe)[2][SSB_INTERSECT_THREADS] = reinterpret_cast<float4 (*)[2][SSB_INTERSECT_THREADS]>(ssb_smem + pipe_offset(S));
 	auto prefetch = [&](uint32_t it, int stage) {
 		if (!FIRST && it < n_in) {
 			cp_async16(&s_pipe[stage][0][threadIdx.x], &P.recA[pin][2 * (size_t)it]);
@@ -907,7 +914,7 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 #if SSB_PIPELINE_SHADE
 	// order[] is read two iterations ahead (a register), the records it points at one iteration ahead (cp.async into the
 	// thread's slot: [stage][recH.0, recH.1, recR.0, recR.1][thread])
-	__shared__ float4 s_pipe[2][4][SSB_SHADE_THREADS];
+	float4 (*s_pipe)[4][SSB_SHADE_THREADS] = reinterpret_cast<float4 (*)[4][SSB_SHADE_THREADS]>(ssb_smem + pipe_offset(S));  // dynamic shared memory, behind the blob
 	auto prefetch = [&](uint32_t it, bool ok, int stage) {
 		if (ok) {
 			cp_async16(&s_pipe[stage][0][threadIdx.x], &P.recH[2 * (size_t)it]);
