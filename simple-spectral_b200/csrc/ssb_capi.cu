@@ -692,6 +692,8 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 	P.indirect_only = o->indirect_only; P.upsampling = o->upsampling; P.max_depth = o->max_depth;
 	P.els = o->explicit_light_sampling; P.flat_field = o->flat_field_correction;
 	P.render_mode = o->render_mode;
+	P.has_mirror = 0;
+	for (const HostMaterial& m : c->materials) if (m.kind == SSB_MATERIAL_MIRROR) P.has_mirror = 1;
 	P.band_h = banded ? o->band_height : 1u; P.band_n = banded ? o->band_count : 1u; P.band_i = banded ? o->band_index : 0u;
 	P.eps = o->eps; P.lambda_min = o->lambda_min;
 	P.n_wavelengths = o->n_wavelengths ? o->n_wavelengths : 4u;  // SAMPLE_WAVELENGTHS (stdafx.hpp:90)
@@ -767,7 +769,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 				SSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tex_ready, 0));
 				c->tex_pending = false;
 			}
-			const unsigned grid_b = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * 8, (P.total_work + 1023) / 1024);
+			const unsigned grid_b = (unsigned)std::min<unsigned long long>((unsigned long long)c->sm_count * 8, (P.total_work + SSB_MAX_QUADS * SSB_SCATTER_PER_THREAD - 1) / (SSB_MAX_QUADS * SSB_SCATTER_PER_THREAD));
 			ssb_bin_scatter_kernel<<<grid_b, SSB_MAX_QUADS, 0, c->stream>>>(P, d == 0 ? 1u : 0u, nquads);
 			SSB_CUDA(cudaGetLastError());
 			(d == 0 ? k_shade_first : k_shade_next)<<<grid_s, SSB_SHADE_THREADS, smem_s, c->stream>>>(P);
@@ -775,7 +777,7 @@ int ssb_render(ssb_ctx* c, const ssb_options* o) {
 			launches += 3;
 		}
 		SSB_CUDA(cudaEventRecord(c->ev_pass[2 * passes + 1], c->stream));
-		ssb_fold_kernel<<<(unsigned)((P.total_work + 255) / 256), 256, 0, c->stream>>>(P);
+		ssb_fold_kernel<<<(unsigned)((P.total_work + SSB_FOLD_THREADS - 1) / SSB_FOLD_THREADS), SSB_FOLD_THREADS, 0, c->stream>>>(P);
 		SSB_CUDA(cudaGetLastError());
 		ssb_accumulate_kernel<<<(unsigned)((npix_rect + 127) / 128), 128, 0, c->stream>>>(P);
 		SSB_CUDA(cudaGetLastError());

@@ -78,6 +78,7 @@ struct KParams {
 	uint32_t render_mode;  // SSB_RENDER_SPECTRAL / SSB_RENDER_RGB
 	uint32_t n_wavelengths;  // SAMPLE_WAVELENGTHS (2..4): channels >= n of every Hero are exactly 0
 	uint32_t depth;     // depth processed by this launch
+	uint32_t has_mirror;  // some material is a MaterialMirror: the shade stage then reads the incoming direction from recA
 	uint32_t band_h, band_n, band_i;  // ssb_options.band_*: rows j with (j / band_h) % band_n == band_i (band_n <= 1: all rows of the rectangle)
 	uint32_t scan_list;  // ssb_debug_intersect only: SSB_SCAN_LIST (the render kernels take the scan mode as a template parameter)
 	float eps, lambda_min, lambda_step;
@@ -760,7 +761,8 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 				// hero wavelength (renderer.cpp:134-143): drawn in spectral mode only
 				const float lambda_0 = (P.render_mode == SSB_RENDER_RGB) ? 0.0f : P.lambda_min + rand_1f(rng) * P.lambda_step;
 				if (!P.flat_field) P.ff[id] = dot3(dx, dy, dz, P.cam_dir[0], P.cam_dir[1], P.cam_dir[2]);
-				st_sector(&P.recA[0][2 * (size_t)item], make_float4(ox, oy, oz, __int_as_float(-1)), make_float4(dx, dy, dz, lambda_0));
+				// (the camera ray is consumed right here; only MaterialMirror::interact_bsdf looks at it again — 32 B per sample saved otherwise)
+				if (P.has_mirror) st_sector(&P.recA[0][2 * (size_t)item], make_float4(ox, oy, oz, __int_as_float(-1)), make_float4(dx, dy, dz, lambda_0));
 				st_sector(&P.recR[0][2 * (size_t)item],
 				          make_float4(__uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
 				                      __uint_as_float((uint32_t)rng.inc), __uint_as_float((uint32_t)(rng.inc >> 32))),
@@ -810,7 +812,9 @@ ssb_intersect_kernel(const __grid_constant__ KParams P) {
 // a launch gap + ~5 us nine times per frame), then takes tiles of 4 x blockDim queue entries: it counts the tile's hits
 // per quad in shared memory, reserves one contiguous range per quad with a single global atomic on the quad's cursor
 // (zeroed with the other counters at the start of the pass), and places the entries through shared-memory cursors.
+#ifndef SSB_SCATTER_PER_THREAD
 #define SSB_SCATTER_PER_THREAD 4
+#endif
 __global__ void __launch_bounds__(SSB_MAX_QUADS) ssb_bin_scatter_kernel(const __grid_constant__ KParams P, uint32_t first_depth, uint32_t nquads) {
 	__shared__ uint32_t s_cnt[SSB_MAX_QUADS];
 	__shared__ uint32_t s_base[SSB_MAX_QUADS];
@@ -1136,7 +1140,10 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 // One thread per sample (ncu on the one-thread-per-pixel form: a single wave of 262 k threads, `long_scoreboard` 6.2 —
 // latency bound at half the DRAM rate); lanes = neighbouring pixels of the same sample index, so every record array is
 // read coalesced.  The float4 (X,Y,Z,hit) goes to `samples`, which aliases path-state memory that is dead by now.
-__global__ void __launch_bounds__(256) ssb_fold_kernel(const __grid_constant__ KParams P) {
+#ifndef SSB_FOLD_THREADS
+#define SSB_FOLD_THREADS 256
+#endif
+__global__ void __launch_bounds__(SSB_FOLD_THREADS) ssb_fold_kernel(const __grid_constant__ KParams P) {
 	const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (id >= P.total_work) return;
 	const DevHeader* hdr = reinterpret_cast<const DevHeader*>(P.blob);
