@@ -431,6 +431,7 @@ def main_ours(args, rank, local_rank, world):
             strong[mode] = {"value": npix * SPP / (times["frame"] * 1e-3) / 1e6, "unit": METRIC, "ms_per_frame": times["frame"],
                             "render_only_ms": times["render_only"], "reduce_and_resolve_ms": times["frame"] - times["render_only"],
                             "frame_sha": sha, "scaling": "strong",
+                            "bit_identical_to_1gpu": (sha == HEADLINE_SHA) if (mode == "tiles" and (SCENE, VARIANT, W, H, SPP) == ("cornell-srgb", "ours1931", 512, 512, 64) and rank == 0) else None,
                             "shard": "interleaved bands of 8 rows (ssb_options.band_*)" if mode == "tiles" else "sample ranges"}
         dist.barrier()
 

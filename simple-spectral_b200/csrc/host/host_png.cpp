@@ -57,7 +57,10 @@ Texture load_png_rgb8(std::string const& path) {
 		pos += 12 + static_cast<size_t>(len);
 	}
 	int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-	if (w == 0 || h == 0 || depth != 8 || channels == 0 || interlace != 0) return fail();
+	// Supported subset: 8 bits per channel, non-interlaced (what the reference's scenes ship; lodepng also reads 16-bit and
+	// Adam7 files).  The dimensions are bounded so that the size products below cannot overflow or exhaust memory on a
+	// crafted header.
+	if (w == 0 || h == 0 || w > 65536u || h > 65536u || depth != 8 || channels == 0 || interlace != 0) return fail();
 	size_t stride = static_cast<size_t>(w) * channels;
 	std::vector<unsigned char> raw((stride + 1) * h);
 	uLongf rawlen = static_cast<uLongf>(raw.size());
