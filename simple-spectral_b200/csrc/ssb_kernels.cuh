@@ -174,25 +174,56 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 
 // Single, non-inlined copies of the exact libm restatements: the trace kernel calls them from ~20 sites and its
 // instruction footprint must stay inside the instruction cache (ncu: `stalled_no_instruction` dominated v1).
-__device__ __noinline__ float acosf_x(float x) { return ssbm::acosf_exact(x); }
+#ifndef SSB_INLINE_MATH
+// Measured (profiles/r5v_ab.txt, r5w_ab.txt; every call of a non-inlined function moves its arguments into fixed registers and
+// anything passed by reference or returned as a struct through LOCAL MEMORY): inlining spec_hero4 +1.7 %, sincosf_x +0.3 %;
+// acosf_x / acosf2_x / sinf_x inlined at their 3-4 call sites each cost 0.3-1 % (code size) and stay functions.
+#define SSB_INLINE_MATH 24  // bit k set: inline 1 acosf_x, 2 acosf2_x, 4 sinf_x/cosf_x, 8 sincosf_x, 16 spec_hero4
+#endif
+#if !(SSB_INLINE_MATH & 1)
+#define SSB_ATTR_ACOS __device__ __noinline__
+#else
+#define SSB_ATTR_ACOS __device__ __forceinline__
+#endif
+#if !(SSB_INLINE_MATH & 2)
+#define SSB_ATTR_ACOS2 __device__ __noinline__
+#else
+#define SSB_ATTR_ACOS2 __device__ __forceinline__
+#endif
+#if !(SSB_INLINE_MATH & 4)
+#define SSB_ATTR_SIN __device__ __noinline__
+#else
+#define SSB_ATTR_SIN __device__ __forceinline__
+#endif
+#if !(SSB_INLINE_MATH & 8)
+#define SSB_ATTR_SINCOS __device__ __noinline__
+#else
+#define SSB_ATTR_SINCOS __device__ __forceinline__
+#endif
+#if !(SSB_INLINE_MATH & 16)
+#define SSB_ATTR_SPEC __device__ __noinline__
+#else
+#define SSB_ATTR_SPEC __device__ __forceinline__
+#endif
+SSB_ATTR_ACOS float acosf_x(float x) { return ssbm::acosf_exact(x); }
 // two arc cosines per call, evaluated with packed-fp32 instructions (ssbm::acosf_exact2: bit-identical per lane, ~45 % of
 // the instructions of two scalar calls)
 #ifndef SSB_ACOS_PAIRS
 #define SSB_ACOS_PAIRS 1
 #endif
-__device__ __noinline__ float2 acosf2_x(float x0, float x1) {
+SSB_ATTR_ACOS2 float2 acosf2_x(float x0, float x1) {
 #if SSB_ACOS_PAIRS
 	return ssbm::acosf_exact2(make_float2(x0, x1));
 #else
 	return make_float2(ssbm::acosf_exact(x0), ssbm::acosf_exact(x1));
 #endif
 }
-__device__ __noinline__ float sinf_x(float x) { return ssbm::sinf_exact(x); }
-__device__ __noinline__ float cosf_x(float x) { return ssbm::cosf_exact(x); }
+SSB_ATTR_SIN float sinf_x(float x) { return ssbm::sinf_exact(x); }
+SSB_ATTR_SIN float cosf_x(float x) { return ssbm::cosf_exact(x); }
 // sin and cos of the same argument share glibc's argument reduction (ssbm::sincosf_exact): each result is the scalar
 // function's, bit for bit, for ~40 % fewer instructions than two calls (measured: +0.8 % frame rate, profiles/r1p_tune.txt).
 // (Returned by value: reference parameters of a non-inlined function would go through local memory.)
-__device__ __noinline__ float2 sincosf_x(float x) {  // (sin, cos)
+SSB_ATTR_SINCOS float2 sincosf_x(float x) {  // (sin, cos)
 	float s, c;
 	ssbm::sincosf_exact(x, &s, &c);
 	return make_float2(s, c);
@@ -215,7 +246,7 @@ __device__ __forceinline__ float spec_sample(const float* pool, const DevSpectru
 	return val0 * (1.0f - frac) + val1 * frac;
 }
 // _Spectrum::operator[] (spectrum.cpp:61-67)
-__device__ __noinline__ float4 spec_hero4(DevSpectrum s, float lambda_0, float step) {
+SSB_ATTR_SPEC float4 spec_hero4(DevSpectrum s, float lambda_0, float step) {
 	const float* pool = SceneView().pool();
 	float4 h;
 	h.x = spec_sample(pool, s, lambda_0 + 0.0f * step);
@@ -283,11 +314,13 @@ __device__ __forceinline__ int jh_find_interval(const float* values, int size_, 
 // rgb2spec_fetch (rgb2spec.c:77-118), no FMA (parity build): l-RGB -> the three polynomial coefficients
 __device__ __forceinline__ void jh_fetch(const float* __restrict__ jh_scale, const float* __restrict__ d, int res,
                                          float r, float g, float b, float coeff[3]) {
-	float rgb[3] = { r, g, b };
+	// i = index of the largest component, later ones winning ties (rgb2spec.c:84-86), without a dynamically indexed local array
 	int i = 0;
-	for (int j = 1; j < 3; ++j) if (rgb[j] >= rgb[i]) i = j;
-	float z = rgb[i], scale = (float)(res - 1) / z;
-	float x = rgb[(i + 1) % 3] * scale, y = rgb[(i + 2) % 3] * scale;
+	float z = r;
+	if (g >= z) { i = 1; z = g; }
+	if (b >= z) { i = 2; z = b; }
+	const float scale = (float)(res - 1) / z;
+	const float x = (i == 0 ? g : (i == 1 ? b : r)) * scale, y = (i == 0 ? b : (i == 1 ? r : g)) * scale;
 	uint32_t xu = (x != x) ? 0u : (uint32_t)x, yu = (y != y) ? 0u : (uint32_t)y;  // see oracle note on NaN
 	uint32_t xi = min(xu, (uint32_t)(res - 2)), yi = min(yu, (uint32_t)(res - 2));
 	uint32_t zi = (uint32_t)jh_find_interval(jh_scale, res, z);
@@ -315,13 +348,21 @@ __device__ __forceinline__ Hero jh_eval(const KParams& P, float c0, float c1, fl
 	return h;
 }
 // Color::lrgb_to_specrefl, JH build (color.cpp:202-232): both steps per lookup, as the reference does
-__device__ __noinline__ Hero jh_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
+#ifndef SSB_INLINE_UPS
+#define SSB_INLINE_UPS 1  // 1: the Jakob-Hanika / Meng upsampling functions inlined into their single call site (+1 % on those configurations)
+#endif
+#if SSB_INLINE_UPS
+#define SSB_ATTR_UPS __device__ __forceinline__
+#else
+#define SSB_ATTR_UPS __device__ __noinline__
+#endif
+SSB_ATTR_UPS Hero jh_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
 	float coeff[3];
 	jh_fetch(P.jh_scale, P.jh_data, (int)P.jh_res, r, g, b, coeff);
 	return jh_eval(P, coeff[0], coeff[1], coeff[2], lambda_0);
 }
 // the second step alone, on coefficients fetched once per texel by ssb_bake_jh_kernel (ssb_options.prebaked_textures)
-__device__ __noinline__ Hero jh_eval_baked(const KParams& P, float4 cf, float lambda_0) {
+SSB_ATTR_UPS Hero jh_eval_baked(const KParams& P, float4 cf, float lambda_0) {
 	return jh_eval(P, cf.x, cf.y, cf.z, lambda_0);
 }
 // spectrum_xyz_to_p (meng-et-al.-2015/spectrum_grid.h:13-137) for the hero wavelengths of one colour.  The reference calls
@@ -330,7 +371,7 @@ __device__ __noinline__ Hero jh_eval_baked(const KParams& P, float4 cf, float la
 // weights (u, v, w) of the triangle holding the point.  Here that part runs ONCE per colour and only the spectral
 // interpolation of the cell's corner points runs per wavelength: the same operations on the same operands, so every
 // returned value is the per-call one bit for bit (as with the shared grid arithmetic of spec_sample3).
-__device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
+SSB_ATTR_UPS Hero meng_upsample(const KParams& P, float r, float g, float b, float lambda_0) {
 	// color.cpp:189-200: xyz_rel = transpose(M) * 100 * lrgb
 	const float M[9] = { 0.41231515f, 0.3576f, 0.1805f, 0.2126f, 0.7152f, 0.0722f, 0.01932727f, 0.1192f, 0.95063333f };
 	float xyz[3];
@@ -350,7 +391,11 @@ __device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, f
 	const int32_t* __restrict__ cell = P.meng_grid + 8 * cell_idx;
 	const int4 c0 = __ldg(reinterpret_cast<const int4*>(cell)), c1 = __ldg(reinterpret_cast<const int4*>(cell) + 1);
 	const int inside = c0.x, num = c0.y;
-	const int idx[6] = { c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+	const int idx0 = c0.z, idx1 = c0.w;
+	// (corner indices beyond the first two are needed at run-time positions: re-read from the cell — an L1 hit — rather than
+	// from a dynamically indexed local array, which would live in local memory)
+	auto idx_at = [&](int k) { return k == 0 ? idx0 : (k == 1 ? idx1 : __ldg(cell + 2 + k)); };
+	(void)c1;
 	const uint32_t stride = 5 + P.meng_nsamples;
 	const float* __restrict__ pts = P.meng_points;
 	const int ns = (int)P.meng_nsamples;
@@ -361,7 +406,7 @@ __device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, f
 	if (inside) {
 		fu = uv[0] - (float)uvi[0]; fv = uv[1] - (float)uvi[1];
 	} else {
-#define SSB_MENG_UV(k, c) __ldg(pts + (size_t)stride * idx[k] + 3 + (c))
+#define SSB_MENG_UV(k, c) __ldg(pts + (size_t)stride * idx_at(k) + 3 + (c))
 		const float p0u = SSB_MENG_UV(0, 0), p0v = SSB_MENG_UV(0, 1);
 		const float p1u = SSB_MENG_UV(1, 0), p1v = SSB_MENG_UV(1, 1);
 		const float ex = uv[0] - p0u, ey = uv[1] - p0v;
@@ -391,7 +436,7 @@ __device__ __noinline__ Hero meng_upsample(const KParams& P, float r, float g, f
 		const int sb1 = sb + 1 < (float)ns ? (int)(sb + 1) : ns - 1;
 		const float sbf = sb - (float)sb0;
 		auto corner = [&](int i) {
-			const float* spectrum = pts + (size_t)stride * idx[i] + 5;
+			const float* spectrum = pts + (size_t)stride * idx_at(i) + 5;
 			return __ldg(spectrum + sb0) * (1.0f - sbf) + __ldg(spectrum + sb1) * sbf;
 		};
 		float interpolated_p = 0.0f;
@@ -485,8 +530,17 @@ __device__ __forceinline__ void func_bar(float xx, float xy, float xz, float yx,
 
 __device__ __noinline__ float cos_double_cold(float x) { return (float)cos((double)x); }  // degenerate triangles only
 
-__device__ __noinline__ void sample_spherical_triangle(int light_quad, int light_tri, float px, float py, float pz, float r0, float r1,
-                                                       float& wx, float& wy, float& wz, float& pdf) {
+// Returns (direction, pdf) BY VALUE: reference parameters of a non-inlined function live in local memory.
+#ifndef SSB_INLINE_SPHTRI
+#define SSB_INLINE_SPHTRI 1  // (one call site; +0.3 %)
+#endif
+#if SSB_INLINE_SPHTRI
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+float4 sample_spherical_triangle(int light_quad, int light_tri, float px, float py, float pz, float r0, float r1) {
+	float wx, wy, wz, pdf;
 	const ssb_tri& t = SceneView().quads()[light_quad].tri[light_tri];
 	// unit vectors toward the vertices: glm::normalize(v - from) = v * (1/sqrt(dot))
 	float Ax = t.v[0].pos[0] - px, Ay = t.v[0].pos[1] - py, Az = t.v[0].pos[2] - pz;
@@ -572,6 +626,7 @@ __device__ __noinline__ void sample_spherical_triangle(int light_quad, int light
 	func_bar(Chx, Chy, Chz, Bx, By, Bz, fx, fy, fz);
 	float sz = sqrtf(1.0f - z * z);
 	wx = z * Bx + sz * fx; wy = z * By + sz * fy; wz = z * Bz + sz * fz;
+	return make_float4(wx, wy, wz, pdf);
 }
 
 // ------------------------------------------------------------------ TMA bulk copy of the blob into shared memory
@@ -1013,7 +1068,8 @@ ssb_shade_kernel(const __grid_constant__ KParams P) {
 			const int lt = (rand_1f(rng) <= 0.5f) ? 0 : 1;
 			float r0 = rand_1f(rng);
 			float r1 = rand_1f(rng);
-			sample_spherical_triangle(light_quad, lt, hx, hy, hz, r0, r1, sx, sy, sz, pdf);
+			const float4 ls = sample_spherical_triangle(light_quad, lt, hx, hy, hz, r0, r1);
+			sx = ls.x; sy = ls.y; sz = ls.z; pdf = ls.w;
 			pdf *= 0.5f;
 			{  // pdf /= nlights (scene.cpp:428-430); inf / n = inf without the division's slow path
 				const bool pinf = pdf == __int_as_float(0x7f800000);

@@ -28,16 +28,21 @@ import sys, importlib, hashlib, ctypes as C
 import numpy as np
 sys.path.insert(0, %r)
 ssb = importlib.import_module("simple-spectral_b200"); host = importlib.import_module("simple-spectral_b200.host")
-color = host.Color(None, 1931, ssb.SSB_UPSAMPLE_OURS); scene = host.Scene("cornell-srgb", color)
+import os
+# the headline frame, or (environment) SSB_AB="scene,variant,width,height,spp" e.g. "cornell-srgb,meng,1024,1024,16"
+sc, var, W, H, SPP = (os.environ.get("SSB_AB") or "cornell-srgb,ours1931,512,512,64").split(",")
+W, H, SPP = int(W), int(H), int(SPP)
+color = host.Color(None, *host.VARIANTS[var]); scene = host.Scene(sc, color)
 ctx = ssb.Context(0); ctx.upload_color(color.flat); ctx.upload_scene(scene.flat)
-opt = host.options_for(color, 512, 512, 64, seed=1)
+opt = host.options_for(color, W, H, SPP, seed=1)
 for _ in range(3): ctx.render(opt)
 ctx.synchronize()
 ms, tr = [], []
 for _ in range(7):
     ctx.render(opt); st = ctx.stats(); ms.append(st.device_ms); tr.append(st.trace_ms)
 ms.sort(); tr.sort()
-acc = ctx.read_accum(512, 512)
+acc = ctx.read_accum(W, H)
+print("SAMPLES", W * H * SPP)
 print("RESULT", ms[len(ms)//2], tr[len(tr)//2], hashlib.sha256(np.ascontiguousarray(acc).tobytes()).hexdigest()[:16])
 ''' % ROOT
 
@@ -79,7 +84,8 @@ def run(names):
                     print(f"{n:24s} RUN FAILED: {out.stderr[-400:]}", flush=True)
                     continue
                 ms, tr, sha = res[0].split()[1:4]
-                print(f"{n:24s} frame {float(ms):8.3f} ms  bounce {float(tr):8.3f} ms  {512 * 512 * 64 / float(ms) / 1e3:8.1f} Msamples/s  xyza sha256 {sha}", flush=True)
+                ns = int([ln for ln in out.stdout.split("\n") if ln.startswith("SAMPLES")][0].split()[1])
+                print(f"{n:24s} frame {float(ms):8.3f} ms  bounce {float(tr):8.3f} ms  {ns / float(ms) / 1e3:8.1f} Msamples/s  xyza sha256 {sha}", flush=True)
     finally:
         shutil.copyfile(backup, LIB)
         os.remove(backup)
