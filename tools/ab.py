@@ -34,7 +34,7 @@ sc, var, W, H, SPP = (os.environ.get("SSB_AB") or "cornell-srgb,ours1931,512,512
 W, H, SPP = int(W), int(H), int(SPP)
 color = host.Color(None, *host.VARIANTS[var]); scene = host.Scene(sc, color)
 ctx = ssb.Context(0); ctx.upload_color(color.flat); ctx.upload_scene(scene.flat)
-opt = host.options_for(color, W, H, SPP, seed=1)
+opt = host.options_for(color, W, H, SPP, seed=1, **({'render_mode': ssb.SSB_RENDER_RGB} if var == 'rgb' else {}))
 for _ in range(3): ctx.render(opt)
 ctx.synchronize()
 ms, tr = [], []
