@@ -128,6 +128,7 @@ def patch_hooks(src_dir):
     # thread count override (renderer.cpp:45)
     t = sub_once(t, r"_threads\.resize\(std::thread::hardware_concurrency\(\)\);",
                  "_threads.resize(ssb_hooks::threads(std::thread::hardware_concurrency()));\n"
+                 "\tssb_hooks::replace_scene(scene);\n"
                  "\tssb_hooks::dump_tables(scene);", "threads")
     # per-sample seeding + sample dump (renderer.cpp:293-295, spectral branch)
     t = sub_once(t, r"avg \+= _render_sample\(rng, i,j\) \* 0\.001f;",

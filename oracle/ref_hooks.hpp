@@ -12,7 +12,8 @@
 //                           (renderer.cpp:292-296, never stored by the reference);
 //   SSB_DUMP_SAMPLES=<path> write every sample's float4 (X,Y,Z,hit);
 //   SSB_DUMP_TABLES=<path>  write Color::data, the camera and the flattened scene;
-//   SSB_THREADS=<n>         override the worker-thread count.
+//   SSB_THREADS=<n>         override the worker-thread count;
+//   SSB_SCENE_QUADS=<path>  replace the scene's quads by the ones in a file (random-scene tests).
 // This file is ours (no reference code); it is #included after the reference's own
 // headers, so it sees Scene / PrimQuad / MaterialLambertian / Color::data.
 #pragma once
@@ -119,6 +120,39 @@ inline void rec_spectrum(FILE* f, std::string const& name, _Spectrum const& s) {
 	rec_f32(f, name + ".lowhigh", lh, 2);
 }
 #endif
+
+// SSB_SCENE_QUADS=<path>: replace the primitive list of the scene just built by quads read from a file — the way the
+// tests put RANDOM geometry (arbitrary lights, slivers, non-planar and degenerate quads) through the real reference.
+// File: u32 n, then per quad u32 material (index into the ORIGINAL scene's materials in first-use order over its primitive
+// list, the order dump_tables() writes them in) and 4 x (pos.xyz, st.xy) f32 for v00, v10, v11, v01.  The quads are built by
+// the reference's own PrimQuad constructor (normals, is_light from the material), the light list as Scene::_init() does.
+inline void replace_scene(Scene* scene) {
+	const char* path = std::getenv("SSB_SCENE_QUADS");
+	if (!path) return;
+	FILE* f = std::fopen(path, "rb");
+	if (!f) { std::fprintf(stderr, "SSB_SCENE_QUADS: cannot open %s\n", path); std::exit(3); }
+	std::vector<MaterialBase*> mats;
+	for (PrimBase* prim : scene->primitives) {
+		size_t m = 0;
+		for (; m < mats.size(); ++m) if (mats[m] == prim->material) break;
+		if (m == mats.size()) mats.push_back(prim->material);
+	}
+	uint32_t n = 0;
+	if (std::fread(&n, 4, 1, f) != 1) std::exit(3);
+	std::vector<PrimBase*> prims;
+	for (uint32_t q = 0; q < n; ++q) {
+		uint32_t m = 0; float v[20];
+		if (std::fread(&m, 4, 1, f) != 1 || std::fread(v, 4, 20, f) != 20 || m >= mats.size()) { std::fprintf(stderr, "SSB_SCENE_QUADS: bad record %u\n", q); std::exit(3); }
+		Vertex vert[4];
+		for (size_t k = 0; k < 4; ++k) { vert[k].pos = Pos(v[5 * k], v[5 * k + 1], v[5 * k + 2]); vert[k].st = ST(v[5 * k + 3], v[5 * k + 4]); }
+		prims.push_back(new PrimQuad(mats[m], vert[0], vert[1], vert[2], vert[3]));
+	}
+	std::fclose(f);
+	scene->primitives = prims;  // (the old primitives leak: test binary)
+	scene->lights.clear();
+	for (PrimBase* prim : scene->primitives) if (prim->is_light) scene->lights.emplace_back(prim);
+	if (scene->lights.empty()) { std::fprintf(stderr, "SSB_SCENE_QUADS: no light in the scene\n"); std::exit(3); }
+}
 
 inline void dump_tables(Scene* scene) {
 	State& s = st();

@@ -12,7 +12,9 @@
  * Pinning: this file is checked bit-for-bit against the real reference compiled here
  * (oracle/_ref/simple_spectral_*_hooked, see oracle/build_ref.py) at matched per-sample seeds:
  * tests/test_oracle_golden.py (live, when oracle/_ref exists) and the committed fixtures under
- * tests/golden/ (made by tests/golden/make_golden.py).
+ * tests/golden/ (made by tests/golden/make_golden.py); and, beyond the reference's three scenes,
+ * on random scenes pushed through the real reference (tests/test_oracle_random_scenes.py: live
+ * runs of the hooked binaries with SSB_SCENE_QUADS, four of them committed as fixtures).
  *
  * Third-party arithmetic the reference inherits and that is NOT under /root/reference:
  *   GLM (unpinned)           — restated as GLM 0.9.9 scalar semantics (oracle/glm_shim)

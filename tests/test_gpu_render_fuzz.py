@@ -126,3 +126,40 @@ def test_random_scene_full_path(case, scene, variant, kind):
     assert pu.bits_equal(xg, xo) and pu.bits_equal(sg, so)
     # the scene must actually be lit and visible, or the comparison proves nothing
     assert np.nansum(np.abs(acc_o[..., 3])) > 0, f"case {case}: no pixel hit anything"
+
+
+# ---- the same kind of scene through the REAL reference (tests/test_oracle_random_scenes.py): CUDA path vs the reference's own
+# f64 XYZA, from the committed fixtures and — where oracle/_ref travelled to the box — from live runs of the hooked binaries
+import os
+
+import test_oracle_random_scenes as rs
+
+
+def _gpu_xyza(flat, variant, w, h, spp, seed):
+    opt = pu.options(variant, w, h, spp, seed=seed)
+    with pu.gpu_context(flat) as ctx:
+        xyza, _ = ctx.render_frame(opt)
+    return xyza
+
+
+@pytest.mark.parametrize("i", rs.FIXTURES)
+def test_random_scene_reference_fixture(i):
+    scene, variant, kind, nquads, w, h, spp = rs.CASES[i]
+    if pu.needs_assets(scene, variant) and not pu.have_assets():
+        pytest.fail("data files not staged on the GPU box (assets/data): run __graft_entry__.build() first")
+    flat = rs.flat_of(os.path.join(pu.GOLDEN, f"random_{i}_{scene}_{variant}_tables.bin"), scene, variant)
+    ref = np.load(os.path.join(pu.GOLDEN, f"random_{i}_{scene}_{variant}_xyza_{w}x{h}_spp{spp}_seed{300 + i}.npy"))
+    assert pu.bits_equal(_gpu_xyza(flat, variant, w, h, spp, 300 + i), ref)
+
+
+@pytest.mark.parametrize("i", range(len(rs.CASES)))
+def test_random_scene_live_reference(i, tmp_path):
+    scene, variant, kind, nquads, w, h, spp = rs.CASES[i]
+    if not pu.have_assets():
+        pytest.fail("data files not staged on the GPU box (assets/data): run __graft_entry__.build() first")
+    if not os.path.exists(os.path.join(rs.REFDIR, f"simple_spectral_{variant}_hooked")):
+        pytest.skip("oracle/_ref not on this box")
+    tables = str(tmp_path / "tables.bin")
+    ref = rs.run_reference(scene, variant, rs._payload(i), w, h, spp, 300 + i, tables)
+    flat = rs.flat_of(tables, scene, variant)
+    assert pu.bits_equal(_gpu_xyza(flat, variant, w, h, spp, 300 + i), ref)
