@@ -163,3 +163,20 @@ def test_random_scene_live_reference(i, tmp_path):
     ref = rs.run_reference(scene, variant, rs._payload(i), w, h, spp, 300 + i, tables)
     flat = rs.flat_of(tables, scene, variant)
     assert pu.bits_equal(_gpu_xyza(flat, variant, w, h, spp, 300 + i), ref)
+
+
+@pytest.mark.parametrize("nquads,nlights,scene,variant", [(256, 64, "cornell", "ours1931"), (256, 3, "cornell-srgb", "jh"), (200, 64, "cornell-srgb", "meng"),
+                                                          (1, 1, "cornell", "ours1931"), (2, 2, "cornell-srgb", "ours1931"), (2, 1, "plane-srgb", "ours1931")])
+def test_extreme_scene_sizes(nquads, nlights, scene, variant):
+    """The ABI's limits (SSB_MAX_QUADS = 256 quads, SSB_MAX_LIGHTS = 64 lights) and the smallest scenes (the light alone)."""
+    if pu.needs_assets(scene, variant) and not pu.have_assets():
+        pytest.fail("data files not staged on the GPU box (assets/data): run __graft_entry__.build() first")
+    rng = np.random.default_rng(8800 + nquads * 7 + nlights)
+    flat = _random_scene(pu.load_flat(scene, variant), rng, nquads, nlights, "mixed" if nquads > 2 else "rect", mirror=False)
+    opt = pu.options(variant, 24, 20, 3, seed=77, max_depth=5)
+    acc_o, samp_o, _ = pu.oracle_render(flat, opt, want_samples=True)
+    with pu.gpu_context(flat) as ctx:
+        ctx.render(opt)
+        acc_g = ctx.read_accum(24, 20)
+        assert pu.bits_equal(ctx.trace_samples(opt, 12, 10), samp_o[10, 12])
+    assert pu.bits_equal(acc_g, acc_o), f"max rel {pu.rel_err(acc_g, acc_o).max()}"
