@@ -90,7 +90,7 @@ def _random_scene(flat, rng, nquads, nlights, kind, mirror):
 
 CASES = []
 _kinds = ["mixed", "rect", "axis", "mixed", "sheared", "trapezoid", "mixed", "nonplanar", "mixed", "mixed"]  # "mixed" includes slivers and degenerate quads
-for _i in range(96):
+for _i in range(int(__import__("os").environ.get("SSB_RENDER_FUZZ_CASES", "96"))):  # a longer campaign: SSB_RENDER_FUZZ_CASES=3000
     _scene, _variant = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("cornell", "ours2006"), ("cornell-srgb", "meng"),
                         ("cornell-srgb", "jh"), ("plane-srgb", "ours1931"), ("cornell-srgb", "rgb"), ("plane-srgb", "jh")][_i % 8]
     CASES.append((_i, _scene, _variant, _kinds[_i % len(_kinds)]))

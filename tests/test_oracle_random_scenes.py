@@ -44,6 +44,15 @@ CASES = [("cornell", "ours1931", "mixed", 24, 28, 20, 3),
          ("plane-srgb", "ours1931_noels", "mixed", 15, 18, 18, 3),  # the plane scene's mirror material
          ("plane-srgb", "jh", "axis", 8, 16, 24, 2)]
 FIXTURES = [0, 5, 8, 12]  # indices of CASES committed under tests/golden/
+# a longer campaign against the real reference: SSB_REF_FUZZ_CASES=300 appends that many generated cases
+_combos = [("cornell", "ours1931"), ("cornell-srgb", "ours1931"), ("cornell", "ours2006"), ("cornell-srgb", "jh"), ("cornell-srgb", "meng"),
+           ("plane-srgb", "ours1931"), ("cornell", "ours1931_noels"), ("cornell-srgb", "rgb"), ("plane-srgb", "ours1931_noels"),
+           ("cornell-srgb", "ours1931_nw3"), ("cornell-srgb", "meng_nw2"), ("cornell-srgb", "ours1931_d3"), ("cornell", "ours1931_noffc"), ("plane-srgb", "jh")]
+_kinds = ["mixed", "rect", "axis", "mixed", "sheared", "trapezoid", "nonplanar"]
+for _k in range(int(os.environ.get("SSB_REF_FUZZ_CASES", "0"))):
+    _r = np.random.default_rng(555 + _k)
+    CASES.append((*_combos[_k % len(_combos)], _kinds[_k % len(_kinds)], int(_r.choice([3, 6, 12, 20, 33, 48, 64])),
+                  int(_r.integers(12, 32)), int(_r.integers(12, 28)), int(_r.integers(2, 5))))
 
 
 def scene_file_bytes(flat, rng, nquads, kind):
