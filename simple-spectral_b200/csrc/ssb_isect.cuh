@@ -120,6 +120,9 @@ struct RayConst {  // per-ray constants of the watertight test (geometry.cpp:17-
 	float Sx, Sy, Sz;
 	float okx, oky, okz;  // ray origin permuted
 };
+#ifndef SSB_RAY_SETUP_ROTATE
+#define SSB_RAY_SETUP_ROTATE 1
+#endif
 SSB_ISECT_FN RayConst ray_setup(float ox, float oy, float oz, float dx, float dy, float dz) {
 	RayConst rc;
 	float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
@@ -129,6 +132,22 @@ SSB_ISECT_FN RayConst ray_setup(float ox, float oy, float oz, float dx, float dy
 	} else {
 		if (ay > az) { kz = 1; kx = 2; ky = 0; } else { kz = 2; kx = 0; ky = 1; }
 	}
+#if SSB_RAY_SETUP_ROTATE
+	// (kx, ky, kz) is a rotation of (0, 1, 2) chosen by kz, then kx <-> ky if the dominant component is negative: rotate the
+	// two triples once (two shared predicates) and swap, instead of seven independent three-way selections
+	const bool z0 = kz == 0, z1 = kz == 1;
+	float dkx = z0 ? dy : (z1 ? dz : dx), dky = z0 ? dz : (z1 ? dx : dy);
+	const float dkz = z0 ? dx : (z1 ? dy : dz);
+	float okx = z0 ? oy : (z1 ? oz : ox), oky = z0 ? oz : (z1 ? ox : oy);
+	rc.okz = z0 ? ox : (z1 ? oy : oz);
+	if (dkz < 0.0f) { int t = kx; kx = ky; ky = t; float f = dkx; dkx = dky; dky = f; f = okx; okx = oky; oky = f; }
+	rc.kx = kx; rc.ky = ky; rc.kz = kz;
+	rc.Sx = dkx / dkz;
+	rc.Sy = dky / dkz;
+	rc.Sz = 1.0f / dkz;
+	rc.okx = okx; rc.oky = oky;
+	return rc;
+#else
 	float dkz = sel3(dx, dy, dz, kz);
 	if (dkz < 0.0f) { int t = kx; kx = ky; ky = t; }
 	rc.kx = kx; rc.ky = ky; rc.kz = kz;
@@ -137,6 +156,7 @@ SSB_ISECT_FN RayConst ray_setup(float ox, float oy, float oz, float dx, float dy
 	rc.Sz = 1.0f / dkz;
 	rc.okx = sel3(ox, oy, oz, kx); rc.oky = sel3(ox, oy, oz, ky); rc.okz = sel3(ox, oy, oz, kz);
 	return rc;
+#endif
 }
 
 struct Hit {
