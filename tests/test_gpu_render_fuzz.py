@@ -28,16 +28,18 @@ abi = pu.abi
 pytestmark = pytest.mark.gpu
 
 
-def _quad_from_corners(template, corners, material, is_light):
-    """PrimQuad(v00, v10, v11, v01) (geometry.hpp:93-95) with the template's texture coordinates."""
+def _quad_from_corners(template, corners, material, is_light, st=None):
+    """PrimQuad(v00, v10, v11, v01) (geometry.hpp:93-95) with the template's texture coordinates, or st[4][2] for the corners."""
     q = abi.ssb_quad()
     C.memmove(C.byref(q), C.byref(template), C.sizeof(abi.ssb_quad))
     v00, v10, v11, v01 = (corners[k].astype(np.float32) for k in range(4))
     with np.errstate(invalid="ignore", divide="ignore"):
-        for ti, tri in enumerate(((v00, v10, v11), (v00, v11, v01))):
+        for ti, (tri, idx) in enumerate((((v00, v10, v11), (0, 1, 2)), ((v00, v11, v01), (0, 2, 3)))):
             for vi in range(3):
                 for k in range(3):
                     q.tri[ti].v[vi].pos[k] = float(tri[vi][k])
+                if st is not None:
+                    q.tri[ti].v[vi].st[0], q.tri[ti].v[vi].st[1] = float(st[idx[vi]][0]), float(st[idx[vi]][1])
             nrm = np.cross((tri[1] - tri[0]).astype(np.float32), (tri[2] - tri[0]).astype(np.float32)).astype(np.float32)
             ln = np.float32(np.sqrt(np.float32(np.dot(nrm, nrm))))
             nrm = nrm / ln if ln > 0 else np.zeros(3, np.float32)
@@ -66,10 +68,12 @@ def _random_scene(flat, rng, nquads, nlights, kind, mirror):
     quads = []
     light_ids = set(rng.choice(nquads, size=min(nlights, nquads), replace=False).tolist())
     for qi in range(nquads):
+        # texture coordinates beyond [0,1] and negative ones: clamped nearest texel (material.cpp:73-84); every third quad keeps the template's
+        st = None if qi % 3 == 0 else rng.uniform(-1.5, 2.5, (4, 2)).astype(np.float32)
         if qi in light_ids:
-            quads.append(_quad_from_corners(template, corners[qi], int(rng.choice(light_mats)), 1))
+            quads.append(_quad_from_corners(template, corners[qi], int(rng.choice(light_mats)), 1, st))
         else:
-            quads.append(_quad_from_corners(template, corners[qi], int(rng.choice(other_mats)), 0))
+            quads.append(_quad_from_corners(template, corners[qi], int(rng.choice(other_mats)), 0, st))
     if mirror:
         m = int(rng.choice(other_mats))
         if sc.materials[m].albedo_mode != abi.SSB_ALBEDO_TEXTURE:

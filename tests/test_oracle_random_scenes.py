@@ -69,7 +69,7 @@ def scene_file_bytes(flat, rng, nquads, kind):
     out = [struct.pack("<I", nquads)]
     for qi in range(nquads):
         mat = int(rng.choice(light_mats if qi in light_ids else other_mats))
-        rec = np.concatenate([np.concatenate([corners[qi, k].astype(np.float32), st[k] * np.float32(rng.uniform(0.2, 3.0))]) for k in range(4)])
+        rec = np.concatenate([np.concatenate([corners[qi, k].astype(np.float32), st[k] * np.float32(rng.uniform(-1.5, 3.0))]) for k in range(4)])
         out.append(struct.pack("<I", mat) + rec.astype("<f4").tobytes())
     return b"".join(out)
 
